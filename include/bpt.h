@@ -1,0 +1,206 @@
+/*
+ * bpt.h — C ABI of the B200-native wavefront path tracer ("bpt").
+ *
+ * This is the drop-in boundary for the ONE hot path of
+ * yknishidate/single-file-vulkan-pathtracing: "build an acceleration structure over the
+ * uploaded triangle buffers, then trace W x H x spp paths and accumulate radiance".
+ * Every entry point names the reference call site it replaces (paths relative to the
+ * reference checkout, e.g. main.cpp:659).
+ *
+ * Conventions
+ *   - plain C types only; no CUDA, torch or C++ types cross this boundary
+ *     (streams / device pointers travel as void*).
+ *   - every call returns 0 on success, a negative BPT_E_* code on failure; the message is
+ *     available from bpt_last_error(ctx). No C++ exception crosses the ABI
+ *     (the reference throws std::runtime_error, main.cpp:35,63,118,151,221,594,612,681).
+ *   - a context is bound to one GPU and one CUDA stream and is externally synchronised
+ *     (the reference is single-threaded with one queue, main.cpp:171,683).
+ *   - calls are stream-ordered and asynchronous unless they return host data.
+ *   - there is NO CPU fallback: without a CUDA device bpt_create fails.
+ */
+#ifndef BPT_H_
+#define BPT_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPT_ABI_VERSION 1
+
+/* error codes */
+#define BPT_OK            0
+#define BPT_E_INVALID    -1  /* bad argument / call order                           */
+#define BPT_E_CUDA       -2  /* a CUDA runtime call failed (message has the detail) */
+#define BPT_E_NCCL       -3  /* NCCL missing or a NCCL call failed                  */
+#define BPT_E_NOMEM      -4
+#define BPT_E_STATE      -5  /* e.g. trace before build                             */
+
+/* accumulate modes (raygen.rgen:86-90) */
+#define BPT_ACCUM_FLOAT4  0  /* running mean kept in a float4 image (north-star default)          */
+#define BPT_ACCUM_RGBA8   1  /* running mean re-quantised to unorm8 every frame, exactly what the
+                                reference's B8G8R8A8Unorm storage image does (main.cpp:481-484)   */
+
+/* sampler modes */
+#define BPT_SAMPLER_UNIFORM 0 /* raygen.rgen:23-30,79 — uniform hemisphere, pdf 1/2pi (PARITY)    */
+#define BPT_SAMPLER_COSINE  1 /* opt-in, NOT same-seed comparable with the reference              */
+
+typedef struct bpt_context bpt_context; /* opaque; owns all device memory */
+
+/*
+ * Launch parameters of one frame. The reference hard-codes all of these
+ * (main.cpp:16-17, raygen.rgen:43,55-56,62,71,73, miss.rmiss:10); bpt_params_default()
+ * returns exactly those constants.
+ */
+typedef struct bpt_params {
+    uint32_t width;          /* full image width  (gl_LaunchSizeEXT.x, main.cpp:659)   */
+    uint32_t height;         /* full image height (gl_LaunchSizeEXT.y)                 */
+    uint32_t spp_per_frame;  /* maxSamples, raygen.rgen:43 (32)                        */
+    uint32_t max_depth;      /* segment bound, raygen.rgen:62 (8)                      */
+    int32_t  frame;          /* push constant `frame`, main.cpp:658                    */
+    uint32_t tile_y0;        /* first image row this context renders (multi-GPU tile)  */
+    uint32_t tile_rows;      /* number of rows; 0 = all rows                           */
+    float    cam_origin[3];  /* raygen.rgen:55 (0,-1,5)                                */
+    float    cam_target[3];  /* target = (d.x + t[0], d.y + t[1], t[2]); raygen.rgen:56 (0,-1,2) */
+    float    sky[3];         /* miss.rmiss:10 (0.7,0.6,0.5)                            */
+    float    tmin;           /* raygen.rgen:71 (0.001)                                 */
+    float    tmax;           /* raygen.rgen:73 (10000)                                 */
+    uint32_t accum_mode;     /* BPT_ACCUM_*                                            */
+    uint32_t sampler;        /* BPT_SAMPLER_*                                          */
+} bpt_params;
+
+/* Counters of the last bpt_trace / since bpt_reset_stats. */
+typedef struct bpt_stats {
+    uint64_t rays_traced;     /* sum over bounces of live-queue length (device counted)     */
+    uint64_t paths;           /* tile pixels * spp traced                                   */
+    uint64_t trace_launches;  /* launches of the traversal kernel                           */
+    uint64_t kernel_launches; /* all kernel launches issued by bpt_trace                    */
+    double   trace_kernel_ms; /* device time inside the traversal kernel (CUDA events);
+                                 only filled when profiling is on (bpt_set_option)          */
+    double   frame_ms;        /* device time of the whole bpt_trace call(s) (CUDA events)   */
+    double   build_ms;        /* device time of the last bpt_build_accel                    */
+    uint64_t nodes_visited;   /* instrumented builds only (BPT_OPT_COUNT_TRAVERSAL)         */
+    uint64_t tris_tested;     /*   "                                                        */
+} bpt_stats;
+
+/* Sizes of the acceleration structure, for layout/roofline documentation and tests. */
+typedef struct bpt_accel_info {
+    uint32_t num_tris;        /* triangles in the bottom-level structure                    */
+    uint32_t num_instances;
+    uint32_t num_nodes8;      /* BVH8 nodes (80 B each)                                     */
+    uint32_t num_binary_nodes;/* LBVH internal nodes (N-1)                                  */
+    uint32_t top_nodes_smem;  /* nodes of the BFS prefix staged into shared memory by TMA   */
+    uint32_t max_depth8;      /* depth of the BVH8                                          */
+    uint64_t bytes_nodes;     /* num_nodes8 * 80                                            */
+    uint64_t bytes_tris;      /* num_tris * 48 (Woop)                                       */
+    uint32_t num_tlas_nodes8; /* two-level builds: nodes in the instance BVH8               */
+    uint32_t reserved;
+} bpt_accel_info;
+
+/* options for bpt_set_option */
+#define BPT_OPT_PROFILE          1 /* 1: bracket every traversal launch with CUDA events     */
+#define BPT_OPT_COUNT_TRAVERSAL  2 /* 1: use the instrumented traversal kernel (nodes/tris)  */
+#define BPT_OPT_SMEM_TOP_NODES   3 /* max BVH8 nodes staged into shared memory (0 = none)    */
+#define BPT_OPT_TRACE_CTAS_PER_SM 4 /* persistent grid = 148 * this                          */
+#define BPT_OPT_SORT_RAYS        5 /* reserved                                               */
+#define BPT_OPT_USE_GRAPH        6 /* 1: replay a captured CUDA graph per sample pass        */
+
+/* ---- lifecycle: replaces Context ctor/dtor (main.cpp:74-267) ------------------------- */
+int  bpt_abi_version(void);
+void bpt_params_default(bpt_params* p);
+/* device: CUDA ordinal. stream: a cudaStream_t to enqueue on, or NULL to create one. */
+int  bpt_create(int device, void* stream, bpt_context** out);
+void bpt_destroy(bpt_context* ctx);
+const char* bpt_last_error(const bpt_context* ctx); /* ctx may be NULL: last create error */
+int  bpt_set_option(bpt_context* ctx, int option, int64_t value);
+
+/* ---- scene upload: replaces the three Buffer(...) constructions (main.cpp:492-494) ----
+ * verts   : xyz float triples, stride 12 B   (struct Vertex, main.cpp:19-21)
+ * indices : uint32, 3 per triangle           (main.cpp:45)
+ * faces   : Kd.rgb, Ke.rgb per triangle, stride 24 B (struct Face, main.cpp:23-26)
+ * Host arrays are copied during the call (like the memcpy at main.cpp:321-325). */
+int bpt_upload_mesh(bpt_context* ctx,
+                    const float* verts, uint32_t nverts,
+                    const uint32_t* indices, uint32_t nindices,
+                    const float* faces, uint32_t nfaces);
+/* Same, but the arrays are already device pointers on ctx's GPU (zero-copy adoption is not
+ * implied: they are copied device-to-device). */
+int bpt_upload_mesh_device(bpt_context* ctx,
+                           const void* d_verts, uint32_t nverts,
+                           const void* d_indices, uint32_t nindices,
+                           const void* d_faces, uint32_t nfaces);
+/* Instance transforms: n row-major 3x4 float matrices (VkTransformMatrixKHR,
+ * main.cpp:515-520). Default after upload: one identity instance. */
+int bpt_set_instances(bpt_context* ctx, const float* xforms3x4, uint32_t n);
+
+/* Synthetic triangle soup generated on the device (no reference equivalent —
+ * bench/test input only). Equivalent to bpt_upload_mesh of the oracle's orc_soup output. */
+int bpt_upload_soup(bpt_context* ctx, uint32_t ntris, uint32_t seed);
+
+/* ---- build: replaces Accel(...) -> buildAccelerationStructuresKHR (main.cpp:416-450,
+ *      called for the BLAS at :512 and the TLAS at :538). Stream-ordered, no host sync. */
+int bpt_build_accel(bpt_context* ctx);
+int bpt_accel_info_get(bpt_context* ctx, bpt_accel_info* out);
+
+/* ---- trace: replaces pushConstants(frame) + traceRaysKHR(..., W, H, 1)
+ *      (main.cpp:658-659) and everything raygen/closesthit/miss do per frame. Enqueues the
+ *      whole wavefront launch loop on the stream; no host synchronisation. */
+int bpt_trace(bpt_context* ctx, const bpt_params* p);
+
+/* host-visible completion: replaces queue.waitIdle() (main.cpp:237,683) */
+int bpt_sync(bpt_context* ctx);
+
+/* ---- output: replaces the storage image bound at binding 1 (main.cpp:481-484,637) ---- */
+/* rgba: width*height*4 floats, row-major, full image (rows outside the tile are whatever
+ * the image buffer holds: zero, or the gathered tiles after bpt_allgather_image). Syncs. */
+int bpt_read_image(bpt_context* ctx, float* rgba, size_t nfloats);
+/* BGRA8 view as the reference's B8G8R8A8Unorm image would hold it (main.cpp:483). Syncs. */
+int bpt_read_image_bgra8(bpt_context* ctx, uint8_t* bgra, size_t nbytes);
+/* device pointer of the float4 image (valid until the next resize); for interop/present. */
+int bpt_image_device_ptr(bpt_context* ctx, void** dptr, size_t* nbytes);
+/* zero the image and restart accumulation (a fresh outputImage). */
+int bpt_clear_image(bpt_context* ctx);
+
+int bpt_get_stats(bpt_context* ctx, bpt_stats* out); /* syncs the stream */
+int bpt_reset_stats(bpt_context* ctx);
+
+/* ---- stage-level entry points (what traceRayEXT alone does, raygen.rgen:63-75).
+ * Used by the parity tests and by callers that bring their own rays.
+ * rays : n records of 8 floats {ox,oy,oz,tmin, dx,dy,dz,tmax} (host memory)
+ * hits : n records of 4 words  {t, u, v, prim}; prim = 0xffffffff on miss; for
+ *        multi-instance scenes prim = instance * ntris + primitive. */
+int bpt_trace_rays(bpt_context* ctx, const float* rays, uint32_t n, void* hits);
+/* primary rays + seeds of sample `sample_in_frame` for the tile in p
+ * (raygen.rgen:47-57). rays: tile_pixels*8 floats, seeds: tile_pixels uint32 (post-jitter
+ * RNG state). */
+int bpt_generate_rays(bpt_context* ctx, const bpt_params* p, uint32_t sample_in_frame,
+                      float* rays, uint32_t* seeds);
+
+/* ---- BVH introspection for the build-invariant tests (copies device -> host) --------- */
+/* nodes8: num_nodes8 * 80 bytes; tri_index: num_tris uint32 (leaf order -> primitive);
+ * woop: num_tris*12 floats. Any pointer may be NULL. */
+int bpt_download_accel(bpt_context* ctx, void* nodes8, uint32_t* tri_index, float* woop);
+/* sorted 64-bit (morton<<32 | prim) keys of the last build. */
+int bpt_download_morton(bpt_context* ctx, uint64_t* keys, uint32_t n);
+/* binary LBVH: parent-less arrays left[n-1], right[n-1] (child >= n-1 means leaf
+ * child-(n-1)), and aabbs[(2n-1)*6] (internal nodes first, then leaves). */
+int bpt_download_lbvh(bpt_context* ctx, uint32_t* left, uint32_t* right, float* aabbs);
+
+/* ---- multi-GPU (no reference equivalent: it uses enumeratePhysicalDevices().front(),
+ *      main.cpp:105). One context per process/GPU; NCCL is dlopen'ed at first use. ------ */
+#define BPT_NCCL_UNIQUE_ID_BYTES 128
+int bpt_nccl_unique_id(uint8_t id[BPT_NCCL_UNIQUE_ID_BYTES]);
+int bpt_nccl_init(bpt_context* ctx, const uint8_t id[BPT_NCCL_UNIQUE_ID_BYTES],
+                  int rank, int nranks);
+/* In-place all-gather of the row tiles into every rank's full float4 image. Tiles must be
+ * the equal contiguous split bpt_tile_rows() returns (height % nranks == 0). */
+int bpt_allgather_image(bpt_context* ctx, uint32_t width, uint32_t height);
+/* contiguous row split used by every caller: rank r gets rows [y0, y0+rows). */
+void bpt_tile_rows(uint32_t height, int rank, int nranks, uint32_t* y0, uint32_t* rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPT_H_ */

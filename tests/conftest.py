@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def cornell():
+    import oracle_lib
+    verts, idx, faces, meta = oracle_lib.load_cornell_golden()
+    return verts, idx, faces
+
+
+@pytest.fixture(scope="session")
+def cornell_oracle(cornell):
+    import oracle_lib
+    return oracle_lib.Scene(*cornell)

@@ -1,0 +1,195 @@
+"""ctypes binding of oracle/_build/liboracle.so — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module. The product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
+REF_LOADER_PATH = os.path.join(ORACLE_DIR, "_ref", "libref_loader.so")
+MISS = 0xFFFFFFFF
+
+
+class OrcParams(C.Structure):
+    """Mirror of orc_params / bpt_params (include/bpt.h)."""
+    _fields_ = [
+        ("width", C.c_uint32), ("height", C.c_uint32), ("spp_per_frame", C.c_uint32), ("max_depth", C.c_uint32),
+        ("frame", C.c_int32), ("tile_y0", C.c_uint32), ("tile_rows", C.c_uint32),
+        ("cam_origin", C.c_float * 3), ("cam_target", C.c_float * 3), ("sky", C.c_float * 3),
+        ("tmin", C.c_float), ("tmax", C.c_float), ("accum_mode", C.c_uint32), ("sampler", C.c_uint32),
+    ]
+
+
+def default_params(width=1024, height=1024, spp=32, depth=8, frame=0, **kw):
+    """The reference's compile-time constants (main.cpp:16-17, raygen.rgen:43,55-56,62,71,73, miss.rmiss:10)."""
+    p = OrcParams()
+    p.width, p.height, p.spp_per_frame, p.max_depth, p.frame = width, height, spp, depth, frame
+    p.tile_y0, p.tile_rows = 0, 0
+    p.cam_origin[:] = (0.0, -1.0, 5.0)
+    p.cam_target[:] = (0.0, -1.0, 2.0)
+    p.sky[:] = (0.7, 0.6, 0.5)
+    p.tmin, p.tmax = 0.001, 10000.0
+    p.accum_mode, p.sampler = 0, 0
+    for k, v in kw.items():
+        if k in ("cam_origin", "cam_target", "sky"):
+            getattr(p, k)[:] = v
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def build(force=False):
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(
+            os.path.join(ORACLE_DIR, "oracle.cpp")):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+    if os.path.isdir("/root/reference") and not os.path.exists(REF_LOADER_PATH):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "_ref"])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        u32p, f32p, vp = C.POINTER(C.c_uint32), C.POINTER(C.c_float), C.c_void_p
+        L.orc_pcg.restype = C.c_uint32; L.orc_pcg.argtypes = [u32p]
+        L.orc_pcg2d.restype = None; L.orc_pcg2d.argtypes = [u32p, u32p]
+        L.orc_seed.restype = C.c_uint32; L.orc_seed.argtypes = [C.c_uint32] * 3
+        L.orc_rand.restype = C.c_float; L.orc_rand.argtypes = [u32p]
+        L.orc_scene_create.restype = vp
+        L.orc_scene_create.argtypes = [vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32]
+        L.orc_scene_destroy.restype = None; L.orc_scene_destroy.argtypes = [vp]
+        L.orc_scene_ntris.restype = C.c_uint32; L.orc_scene_ntris.argtypes = [vp]
+        L.orc_render.restype = C.c_uint64
+        L.orc_render.argtypes = [vp, C.POINTER(OrcParams), C.c_int, C.c_int, C.c_int, vp]
+        L.orc_generate_rays.restype = None; L.orc_generate_rays.argtypes = [C.POINTER(OrcParams), C.c_uint32, vp, vp]
+        L.orc_intersect.restype = None
+        L.orc_intersect.argtypes = [vp, vp, C.c_uint32, C.c_int, C.c_int, C.c_int, vp]
+        L.orc_shade.restype = None
+        L.orc_shade.argtypes = [vp, C.POINTER(OrcParams), vp, vp, vp, C.c_uint32, vp, vp, vp, vp, vp]
+        L.orc_soup.restype = None; L.orc_soup.argtypes = [C.c_uint32, C.c_uint32, C.c_float, vp, vp, vp]
+        L.orc_morton30.restype = C.c_uint32; L.orc_morton30.argtypes = [C.c_float] * 3
+        L.orc_hardware_threads.restype = C.c_uint
+        _lib = L
+    return _lib
+
+
+HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4")])
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Scene:
+    """Oracle scene: world-space triangle list (+ median-split BVH above `brute_threshold` triangles)."""
+
+    def __init__(self, verts, indices, faces, xforms=None, brute_threshold=64):
+        self.verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
+        self.indices = np.ascontiguousarray(indices, np.uint32).reshape(-1)
+        self.faces = np.ascontiguousarray(faces, np.float32).reshape(-1, 6)
+        self.xforms = None if xforms is None else np.ascontiguousarray(xforms, np.float32).reshape(-1, 12)
+        ninst = 0 if self.xforms is None else len(self.xforms)
+        self.h = lib().orc_scene_create(_ptr(self.verts), len(self.verts), _ptr(self.indices), len(self.indices),
+                                        _ptr(self.faces), len(self.faces), _ptr(self.xforms), ninst, brute_threshold)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_scene_destroy(self.h)
+            self.h = None
+
+    @property
+    def ntris(self):
+        return lib().orc_scene_ntris(self.h)
+
+    def render(self, p, precision=32, brute=False, nthreads=0, image=None):
+        """Runs one frame of the tile in p; returns (image HxWx4 float32, rays_traced)."""
+        if image is None:
+            image = np.zeros((p.height, p.width, 4), np.float32)
+        rays = lib().orc_render(self.h, C.byref(p), precision, int(brute), nthreads, _ptr(image))
+        return image, int(rays)
+
+    def intersect(self, rays, precision=32, brute=False, nthreads=0):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        hits = np.zeros(len(rays), HIT_DTYPE)
+        lib().orc_intersect(self.h, _ptr(rays), len(rays), precision, int(brute), nthreads, _ptr(hits))
+        return hits
+
+    def shade(self, p, hits, weight, seed):
+        n = len(hits)
+        hits = np.ascontiguousarray(hits)
+        weight = np.ascontiguousarray(weight, np.float32).reshape(n, 3)
+        seed = np.ascontiguousarray(seed, np.uint32)
+        out = dict(contrib=np.zeros((n, 3), np.float32), ray=np.zeros((n, 8), np.float32),
+                   weight=np.zeros((n, 3), np.float32), seed=np.zeros(n, np.uint32), alive=np.zeros(n, np.uint8))
+        lib().orc_shade(self.h, C.byref(p), _ptr(hits), _ptr(weight), _ptr(seed), n, _ptr(out["contrib"]),
+                        _ptr(out["ray"]), _ptr(out["weight"]), _ptr(out["seed"]), _ptr(out["alive"]))
+        return out
+
+
+def generate_rays(p, sample_in_frame=0):
+    rows = p.tile_rows if p.tile_rows else p.height
+    n = rows * p.width
+    rays = np.zeros((n, 8), np.float32)
+    seeds = np.zeros(n, np.uint32)
+    lib().orc_generate_rays(C.byref(p), sample_in_frame, _ptr(rays), _ptr(seeds))
+    return rays, seeds
+
+
+def soup_scale(ntris):
+    return float(np.float32(float(ntris) ** (-1.0 / 3.0)))
+
+
+def soup(ntris, seed):
+    verts = np.zeros((3 * ntris, 3), np.float32)
+    idx = np.zeros(3 * ntris, np.uint32)
+    faces = np.zeros((ntris, 6), np.float32)
+    lib().orc_soup(ntris, seed, soup_scale(ntris), _ptr(verts), _ptr(idx), _ptr(faces))
+    return verts, idx, faces
+
+
+def rel_l2(a, b):
+    """The parity metric: ||a-b||2 / ||b||2 over RGB, unclamped."""
+    a = np.asarray(a, np.float64)[..., :3]
+    b = np.asarray(b, np.float64)[..., :3]
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def load_cornell_golden():
+    """Scene fixture produced by the reference's tinyobjloader (tests/golden/make_golden.py)."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "cornell_scene.json")) as f:
+        g = json.load(f)
+    verts = np.array([float.fromhex(h) for h in g["verts_hex"]], np.float32).reshape(-1, 3)
+    faces = np.array([float.fromhex(h) for h in g["faces_hex"]], np.float32).reshape(-1, 6)
+    idx = np.array(g["indices"], np.uint32)
+    return verts, idx, faces, g
+
+
+def ref_load_obj(obj_path, mtl_dir):
+    """Runs the reference's vendored tinyobjloader (oracle/_ref). Raises if the library is absent."""
+    L = C.CDLL(REF_LOADER_PATH)
+    L.ref_load_obj.restype = C.c_int
+    nv, ni, nf, ns = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    err = C.create_string_buffer(1024)
+    shape_tris = (C.c_uint32 * 4096)()
+    rc = L.ref_load_obj(obj_path.encode(), mtl_dir.encode(), None, None, None, C.byref(nv), C.byref(ni), C.byref(nf),
+                        shape_tris, C.byref(ns), err, 1024)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    verts = np.zeros((nv.value, 3), np.float32)
+    idx = np.zeros(ni.value, np.uint32)
+    faces = np.zeros((nf.value, 6), np.float32)
+    rc = L.ref_load_obj(obj_path.encode(), mtl_dir.encode(), _ptr(verts), _ptr(idx), _ptr(faces), C.byref(nv),
+                        C.byref(ni), C.byref(nf), shape_tris, C.byref(ns), err, 1024)
+    assert rc == 0
+    return verts, idx, faces, list(shape_tris[:ns.value])
