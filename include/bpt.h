@@ -182,6 +182,8 @@ int bpt_generate_rays(bpt_context* ctx, const bpt_params* p, uint32_t sample_in_
 /* nodes8: num_nodes8 * 80 bytes; tri_index: num_tris uint32 (leaf order -> primitive);
  * woop: num_tris*12 floats. Any pointer may be NULL. */
 int bpt_download_accel(bpt_context* ctx, void* nodes8, uint32_t* tri_index, float* woop);
+/* the uploaded (or device-generated) mesh, as bpt_upload_mesh would have received it. */
+int bpt_download_mesh(bpt_context* ctx, float* verts, uint32_t* indices, float* faces);
 /* sorted 64-bit (morton<<32 | prim) keys of the last build. */
 int bpt_download_morton(bpt_context* ctx, uint64_t* keys, uint32_t n);
 /* binary LBVH: parent-less arrays left[n-1], right[n-1] (child >= n-1 means leaf

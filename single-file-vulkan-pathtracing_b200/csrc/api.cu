@@ -1,0 +1,654 @@
+// api.cu — the extern "C" boundary of libbpt (include/bpt.h) and the host-side launch loop.
+//
+// The launch loop in bpt_trace is what replaces the reference's single
+// vkCmdTraceRaysKHR(raygen, miss, hit, {}, W, H, 1) (main.cpp:659): per sample pass one
+// `generate`, then per bounce one persistent `trace` + one `shade` (with ballot compaction into
+// the next queue), and one `accumulate` per frame — all enqueued on one CUDA stream, no host
+// synchronisation inside.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "build.cuh"
+#include "nccl_dl.h"
+#include "shade.cuh"
+#include "trace.cuh"
+
+namespace {
+constexpr uint32_t kMaxDepth = 64;
+std::string g_create_error;
+}  // namespace
+
+struct bpt_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = BPT_NUM_SMS_DEFAULT;
+    std::string err;
+
+    // scene (copies of the caller's arrays, main.cpp:492-494)
+    float* d_verts = nullptr;
+    uint32_t* d_idx = nullptr;
+    float* d_faces = nullptr;
+    float* d_xforms = nullptr;  // null: one identity instance
+    uint32_t nverts = 0, nidx = 0, nfaces = 0, ntris = 0, ninst = 1;
+
+    // acceleration structure
+    Bvh8 blas;
+    WoopTri* d_woop = nullptr;
+    bool built = false;
+    uint32_t top_nodes = 0, top_tris = 0;
+
+    // wavefront buffers
+    size_t cap_paths = 0;
+    PathQueue q[2] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    uint4* hits = nullptr;
+    float4* frame_sum = nullptr;
+    float4* image = nullptr;
+    uint32_t img_w = 0, img_h = 0;
+    uint32_t* counters = nullptr;            // counts[kMaxDepth+1] then fetch[kMaxDepth+1]
+    unsigned long long* d_stats = nullptr;   // rays, nodes, tris
+
+    // options
+    bool profile = false, count = false;
+    int64_t opt_top_nodes = 584;  // 1 + 8 + 64 + 511: about four full levels (46 KB)
+    int ctas_per_sm = 1;
+
+    // statistics
+    bpt_stats stats{};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> frame_events, trace_events;
+    std::vector<cudaEvent_t> event_pool;
+
+    // multi-GPU
+    void* nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+int bpt_fail(bpt_context* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+int bpt_fail_cuda(bpt_context* ctx, cudaError_t e, const char* what, const char* file, int line) {
+    return bpt_fail(ctx, BPT_E_CUDA, "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+}
+
+namespace {
+
+cudaEvent_t get_event(bpt_context* c) {
+    if (!c->event_pool.empty()) {
+        cudaEvent_t e = c->event_pool.back();
+        c->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void free_scene(bpt_context* c) {
+    cudaFree(c->d_verts); cudaFree(c->d_idx); cudaFree(c->d_faces); cudaFree(c->d_xforms);
+    c->d_verts = nullptr; c->d_idx = nullptr; c->d_faces = nullptr; c->d_xforms = nullptr;
+    c->nverts = c->nidx = c->nfaces = c->ntris = 0;
+    c->ninst = 1;
+    c->built = false;
+}
+void free_paths(bpt_context* c) {
+    for (auto& q : c->q) {
+        cudaFree(q.rays); cudaFree(q.state); cudaFree(q.pixel);
+        q = PathQueue{nullptr, nullptr, nullptr};
+    }
+    cudaFree(c->hits); cudaFree(c->frame_sum);
+    c->hits = nullptr; c->frame_sum = nullptr;
+    c->cap_paths = 0;
+}
+
+int ensure_paths(bpt_context* c, size_t n) {
+    if (n <= c->cap_paths) return BPT_OK;
+    free_paths(c);
+    for (auto& q : c->q) {
+        BPT_CUDA_TRY(c, cudaMalloc(&q.rays, n * 2 * sizeof(float4)));
+        BPT_CUDA_TRY(c, cudaMalloc(&q.state, n * sizeof(float4)));
+        BPT_CUDA_TRY(c, cudaMalloc(&q.pixel, n * sizeof(uint32_t)));
+    }
+    BPT_CUDA_TRY(c, cudaMalloc(&c->hits, n * sizeof(uint4)));
+    BPT_CUDA_TRY(c, cudaMalloc(&c->frame_sum, n * sizeof(float4)));
+    BPT_CUDA_TRY(c, cudaMemsetAsync(c->frame_sum, 0, n * sizeof(float4), c->stream));
+    c->cap_paths = n;
+    return BPT_OK;
+}
+
+int ensure_image(bpt_context* c, uint32_t w, uint32_t h) {
+    if (c->image && c->img_w == w && c->img_h == h) return BPT_OK;
+    cudaFree(c->image);
+    c->image = nullptr;
+    BPT_CUDA_TRY(c, cudaMalloc(&c->image, (size_t)w * h * sizeof(float4)));
+    BPT_CUDA_TRY(c, cudaMemsetAsync(c->image, 0, (size_t)w * h * sizeof(float4), c->stream));
+    c->img_w = w;
+    c->img_h = h;
+    return BPT_OK;
+}
+
+FrameParams to_frame(const bpt_params* p) {
+    FrameParams f;
+    static_assert(sizeof(FrameParams) == sizeof(bpt_params), "FrameParams mirrors bpt_params");
+    memcpy(&f, p, sizeof(f));
+    return f;
+}
+
+int check_params(bpt_context* c, const bpt_params* p) {
+    if (!p) return bpt_fail(c, BPT_E_INVALID, "params is NULL");
+    if (p->width == 0 || p->height == 0) return bpt_fail(c, BPT_E_INVALID, "empty image %ux%u", p->width, p->height);
+    if (p->spp_per_frame == 0) return bpt_fail(c, BPT_E_INVALID, "spp_per_frame must be >= 1");
+    if (p->max_depth == 0 || p->max_depth > kMaxDepth) return bpt_fail(c, BPT_E_INVALID, "max_depth must be in [1,%u]", kMaxDepth);
+    if (p->frame < 0) return bpt_fail(c, BPT_E_INVALID, "frame must be >= 0");
+    uint32_t rows = p->tile_rows ? p->tile_rows : p->height - (p->tile_y0 < p->height ? p->tile_y0 : p->height);
+    if (p->tile_y0 >= p->height || p->tile_y0 + rows > p->height) return bpt_fail(c, BPT_E_INVALID, "tile rows [%u,%u) outside image height %u", p->tile_y0, p->tile_y0 + rows, p->height);
+    if ((uint64_t)rows * p->width > 0x7fffffffull) return bpt_fail(c, BPT_E_INVALID, "tile too large");
+    if (p->accum_mode > BPT_ACCUM_RGBA8) return bpt_fail(c, BPT_E_INVALID, "bad accum_mode");
+    if (p->sampler > BPT_SAMPLER_COSINE) return bpt_fail(c, BPT_E_INVALID, "bad sampler");
+    return BPT_OK;
+}
+
+TraceArgs make_trace_args(bpt_context* c, const float4* rays, uint4* hits, const uint32_t* count, uint32_t* fetch) {
+    TraceArgs a;
+    a.rays = rays; a.hits = hits; a.count_ptr = count; a.fetch_ctr = fetch;
+    a.nodes = reinterpret_cast<const uint4*>(c->blas.nodes);
+    a.woop = reinterpret_cast<const float4*>(c->d_woop);
+    a.prim_index = c->blas.prim_index;
+    a.top_nodes = c->top_nodes; a.top_tris = c->top_tris;
+    a.stat_rays = c->d_stats; a.stat_nodes = c->d_stats + 1; a.stat_tris = c->d_stats + 2;
+    return a;
+}
+
+void launch_trace(bpt_context* c, const TraceArgs& a) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->profile) {
+        e0 = get_event(c); e1 = get_event(c);
+        cudaEventRecord(e0, c->stream);
+    }
+    trace_launch(a, (unsigned)(c->num_sms * c->ctas_per_sm), c->count, c->stream);
+    if (c->profile) {
+        cudaEventRecord(e1, c->stream);
+        c->trace_events.emplace_back(e0, e1);
+    }
+    c->stats.trace_launches++;
+    c->stats.kernel_launches++;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bpt_abi_version(void) { return BPT_ABI_VERSION; }
+
+void bpt_params_default(bpt_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->width = 1024; p->height = 1024;          // main.cpp:16-17
+    p->spp_per_frame = 32;                      // raygen.rgen:43
+    p->max_depth = 8;                           // raygen.rgen:62
+    p->frame = 0;
+    p->tile_y0 = 0; p->tile_rows = 0;
+    p->cam_origin[0] = 0.f; p->cam_origin[1] = -1.f; p->cam_origin[2] = 5.f;   // raygen.rgen:55
+    p->cam_target[0] = 0.f; p->cam_target[1] = -1.f; p->cam_target[2] = 2.f;   // raygen.rgen:56
+    p->sky[0] = 0.7f; p->sky[1] = 0.6f; p->sky[2] = 0.5f;                      // miss.rmiss:10
+    p->tmin = 0.001f; p->tmax = 10000.0f;       // raygen.rgen:71,73
+    p->accum_mode = BPT_ACCUM_FLOAT4;
+    p->sampler = BPT_SAMPLER_UNIFORM;
+}
+
+int bpt_create(int device, void* stream, bpt_context** out) {
+    if (!out) return bpt_fail(nullptr, BPT_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return bpt_fail(nullptr, BPT_E_CUDA, "no CUDA device available (%s); libbpt has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return bpt_fail(nullptr, BPT_E_INVALID, "device %d out of range [0,%d)", device, ndev);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bpt_fail(nullptr, BPT_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bpt_fail(nullptr, BPT_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10) return bpt_fail(nullptr, BPT_E_CUDA, "device %d is sm_%d%d; libbpt is built for sm_100a only", device, prop.major, prop.minor);
+    bpt_context* c = new bpt_context;
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    if (stream) c->stream = static_cast<cudaStream_t>(stream);
+    else {
+        if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            delete c;
+            return bpt_fail(nullptr, BPT_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        }
+        c->own_stream = true;
+    }
+    if ((e = cudaMalloc(&c->counters, 2 * (kMaxDepth + 1) * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_stats, 4 * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMemsetAsync(c->d_stats, 0, 4 * sizeof(unsigned long long), c->stream)) != cudaSuccess ||
+        (e = trace_configure()) != cudaSuccess) {
+        int rc = bpt_fail(nullptr, BPT_E_CUDA, "context setup: %s", cudaGetErrorString(e));
+        bpt_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return BPT_OK;
+}
+
+void bpt_destroy(bpt_context* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->nccl_comm) bpt_nccl_comm_destroy(c->nccl_comm);
+    free_scene(c);
+    free_paths(c);
+    bvh8_free(c->blas);
+    cudaFree(c->d_woop); cudaFree(c->image); cudaFree(c->counters); cudaFree(c->d_stats);
+    for (auto& p : c->frame_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (auto& p : c->trace_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* bpt_last_error(const bpt_context* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int bpt_set_option(bpt_context* c, int option, int64_t value) {
+    if (!c) return BPT_E_INVALID;
+    switch (option) {
+        case BPT_OPT_PROFILE: c->profile = value != 0; return BPT_OK;
+        case BPT_OPT_COUNT_TRAVERSAL: c->count = value != 0; return BPT_OK;
+        case BPT_OPT_SMEM_TOP_NODES:
+            if (value < 0) return bpt_fail(c, BPT_E_INVALID, "top node count must be >= 0");
+            c->opt_top_nodes = value;
+            if (c->built) {
+                uint32_t cap = (uint32_t)((kTraceMaxSmem - trace_smem_bytes(0, c->top_tris)) / 80);
+                c->top_nodes = (uint32_t)std::min<int64_t>(std::min<int64_t>(value, c->blas.num_nodes), cap);
+            }
+            return BPT_OK;
+        case BPT_OPT_TRACE_CTAS_PER_SM:
+            if (value != 1) return bpt_fail(c, BPT_E_INVALID, "the traversal kernel runs one 1024-thread CTA per SM");
+            c->ctas_per_sm = 1;
+            return BPT_OK;
+        case BPT_OPT_SORT_RAYS:
+        case BPT_OPT_USE_GRAPH: return bpt_fail(c, BPT_E_INVALID, "option %d is reserved", option);
+        default: return bpt_fail(c, BPT_E_INVALID, "unknown option %d", option);
+    }
+}
+
+static int adopt_mesh(bpt_context* c, const void* verts, uint32_t nverts, const void* indices, uint32_t nindices,
+                      const void* faces, uint32_t nfaces, cudaMemcpyKind kind) {
+    if (!c) return BPT_E_INVALID;
+    if (!verts || !indices || !faces) return bpt_fail(c, BPT_E_INVALID, "NULL mesh array");
+    if (nindices == 0 || nindices % 3 != 0) return bpt_fail(c, BPT_E_INVALID, "index count %u is not a positive multiple of 3", nindices);
+    if (nfaces != nindices / 3) return bpt_fail(c, BPT_E_INVALID, "face count %u != triangle count %u", nfaces, nindices / 3);
+    if (nverts == 0) return bpt_fail(c, BPT_E_INVALID, "no vertices");
+    cudaSetDevice(c->device);
+    free_scene(c);
+    BPT_CUDA_TRY(c, cudaMalloc(&c->d_verts, (size_t)nverts * 12));
+    BPT_CUDA_TRY(c, cudaMalloc(&c->d_idx, (size_t)nindices * 4));
+    BPT_CUDA_TRY(c, cudaMalloc(&c->d_faces, (size_t)nfaces * 24));
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(c->d_verts, verts, (size_t)nverts * 12, kind, c->stream));
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(c->d_idx, indices, (size_t)nindices * 4, kind, c->stream));
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(c->d_faces, faces, (size_t)nfaces * 24, kind, c->stream));
+    if (kind == cudaMemcpyHostToDevice) {
+        // validate indices on the host copy (the caller's arrays may be freed after return)
+        const uint32_t* idx = static_cast<const uint32_t*>(indices);
+        for (uint32_t i = 0; i < nindices; ++i)
+            if (idx[i] >= nverts) {
+                cudaStreamSynchronize(c->stream);
+                free_scene(c);
+                return bpt_fail(c, BPT_E_INVALID, "index %u = %u out of range (%u vertices)", i, idx[i], nverts);
+            }
+        BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    c->nverts = nverts; c->nidx = nindices; c->nfaces = nfaces; c->ntris = nindices / 3;
+    return BPT_OK;
+}
+
+int bpt_upload_mesh(bpt_context* c, const float* verts, uint32_t nverts, const uint32_t* indices, uint32_t nindices,
+                    const float* faces, uint32_t nfaces) {
+    return adopt_mesh(c, verts, nverts, indices, nindices, faces, nfaces, cudaMemcpyHostToDevice);
+}
+int bpt_upload_mesh_device(bpt_context* c, const void* verts, uint32_t nverts, const void* indices, uint32_t nindices,
+                           const void* faces, uint32_t nfaces) {
+    return adopt_mesh(c, verts, nverts, indices, nindices, faces, nfaces, cudaMemcpyDeviceToDevice);
+}
+
+int bpt_upload_soup(bpt_context* c, uint32_t ntris, uint32_t seed) {
+    if (!c) return BPT_E_INVALID;
+    if (ntris == 0 || ntris > 0x10000000u) return bpt_fail(c, BPT_E_INVALID, "soup size %u out of range", ntris);
+    cudaSetDevice(c->device);
+    free_scene(c);
+    BPT_CUDA_TRY(c, cudaMalloc(&c->d_verts, (size_t)ntris * 36));
+    BPT_CUDA_TRY(c, cudaMalloc(&c->d_idx, (size_t)ntris * 12));
+    BPT_CUDA_TRY(c, cudaMalloc(&c->d_faces, (size_t)ntris * 24));
+    const float scale = (float)std::pow((double)ntris, -1.0 / 3.0);
+    launch_soup(ntris, seed, scale, c->d_verts, c->d_idx, c->d_faces, c->stream);
+    BPT_CUDA_TRY(c, cudaGetLastError());
+    c->nverts = 3 * ntris; c->nidx = 3 * ntris; c->nfaces = ntris; c->ntris = ntris;
+    return BPT_OK;
+}
+
+int bpt_set_instances(bpt_context* c, const float* xforms3x4, uint32_t n) {
+    if (!c) return BPT_E_INVALID;
+    if (n == 0 || !xforms3x4) return bpt_fail(c, BPT_E_INVALID, "need at least one instance transform");
+    return bpt_fail(c, BPT_E_INVALID, "multi-instance (two-level) scenes are not implemented yet");
+}
+
+int bpt_build_accel(bpt_context* c) {
+    if (!c) return BPT_E_INVALID;
+    if (c->ntris == 0) return bpt_fail(c, BPT_E_STATE, "bpt_build_accel before bpt_upload_mesh");
+    cudaSetDevice(c->device);
+    c->built = false;
+    cudaEvent_t e0 = get_event(c), e1 = get_event(c);
+    cudaEventRecord(e0, c->stream);
+    BPT_CUDA_TRY(c, bvh8_alloc(c->blas, c->ntris));
+    bvh8_launch_tri_bounds(c->blas, c->d_verts, c->d_idx, c->stream);
+    BPT_CUDA_TRY(c, bvh8_build(c->blas, c->stream));
+    if (c->blas.num_leaf_slots != c->ntris)
+        return bpt_fail(c, BPT_E_STATE, "BVH8 collapse placed %u of %u triangles", c->blas.num_leaf_slots, c->ntris);
+    if (c->blas.depth > (uint32_t)(kTraceSmemStack + 40 - 2))
+        return bpt_fail(c, BPT_E_STATE, "BVH8 depth %u exceeds the traversal stack", c->blas.depth);
+    cudaFree(c->d_woop);
+    c->d_woop = nullptr;
+    BPT_CUDA_TRY(c, cudaMalloc(&c->d_woop, (size_t)c->ntris * sizeof(WoopTri) + 16));
+    bvh8_launch_woop(c->blas, c->d_verts, c->d_idx, c->d_woop, c->stream);
+    cudaEventRecord(e1, c->stream);
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    BPT_CUDA_TRY(c, cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    c->stats.build_ms = ms;
+    c->event_pool.push_back(e0); c->event_pool.push_back(e1);
+    // staging plan: whole triangle array if it is tiny, then the BFS prefix of the nodes
+    c->top_tris = (size_t)c->ntris * 48 <= 32768 ? c->ntris : 0;
+    uint32_t cap = (uint32_t)((kTraceMaxSmem - trace_smem_bytes(0, c->top_tris)) / 80);
+    c->top_nodes = (uint32_t)std::min<int64_t>(std::min<int64_t>(c->opt_top_nodes, c->blas.num_nodes), cap);
+    c->built = true;
+    return BPT_OK;
+}
+
+int bpt_accel_info_get(bpt_context* c, bpt_accel_info* out) {
+    if (!c || !out) return BPT_E_INVALID;
+    if (!c->built) return bpt_fail(c, BPT_E_STATE, "no acceleration structure built");
+    memset(out, 0, sizeof(*out));
+    out->num_tris = c->ntris;
+    out->num_instances = c->ninst;
+    out->num_nodes8 = c->blas.num_nodes;
+    out->num_binary_nodes = c->ntris - 1;
+    out->top_nodes_smem = c->top_nodes;
+    out->max_depth8 = c->blas.depth;
+    out->bytes_nodes = (uint64_t)c->blas.num_nodes * 80;
+    out->bytes_tris = (uint64_t)c->ntris * 48;
+    return BPT_OK;
+}
+
+int bpt_trace(bpt_context* c, const bpt_params* p) {
+    if (!c) return BPT_E_INVALID;
+    int rc = check_params(c, p);
+    if (rc) return rc;
+    if (!c->built) return bpt_fail(c, BPT_E_STATE, "bpt_trace before bpt_build_accel");
+    cudaSetDevice(c->device);
+    FrameParams f = to_frame(p);
+    if (f.tile_rows == 0) f.tile_rows = f.height - f.tile_y0;
+    const uint32_t npix = f.tile_rows * f.width;
+    if ((rc = ensure_paths(c, npix)) != BPT_OK) return rc;
+    if ((rc = ensure_image(c, f.width, f.height)) != BPT_OK) return rc;
+    SceneView sv{c->d_verts, c->d_idx, c->d_faces, c->d_xforms, c->ntris};
+    uint32_t* counts = c->counters;
+    uint32_t* fetch = c->counters + (kMaxDepth + 1);
+
+    cudaEvent_t e0 = get_event(c), e1 = get_event(c);
+    cudaEventRecord(e0, c->stream);
+    for (uint32_t s = 0; s < f.spp_per_frame; ++s) {
+        launch_generate(f, s, c->q[0], counts, fetch, f.max_depth + 1, c->stream);
+        c->stats.kernel_launches++;
+        int cur = 0;
+        for (uint32_t d = 0; d < f.max_depth; ++d) {
+            launch_trace(c, make_trace_args(c, c->q[cur].rays, c->hits, counts + d, fetch + d));
+            launch_shade(f, sv, d, c->q[cur], c->hits, c->q[cur ^ 1], counts, c->frame_sum, npix, c->stream);
+            c->stats.kernel_launches++;
+            cur ^= 1;
+        }
+    }
+    launch_accumulate(f, c->frame_sum, c->image, c->stream);
+    c->stats.kernel_launches++;
+    cudaEventRecord(e1, c->stream);
+    c->frame_events.emplace_back(e0, e1);
+    c->stats.paths += (uint64_t)npix * f.spp_per_frame;
+    BPT_CUDA_TRY(c, cudaGetLastError());
+    return BPT_OK;
+}
+
+int bpt_sync(bpt_context* c) {
+    if (!c) return BPT_E_INVALID;
+    cudaSetDevice(c->device);
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return BPT_OK;
+}
+
+int bpt_read_image(bpt_context* c, float* rgba, size_t nfloats) {
+    if (!c || !rgba) return BPT_E_INVALID;
+    if (!c->image) return bpt_fail(c, BPT_E_STATE, "no image yet");
+    size_t need = (size_t)c->img_w * c->img_h * 4;
+    if (nfloats < need) return bpt_fail(c, BPT_E_INVALID, "buffer holds %zu floats, image needs %zu", nfloats, need);
+    cudaSetDevice(c->device);
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(rgba, c->image, need * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return BPT_OK;
+}
+
+int bpt_read_image_bgra8(bpt_context* c, uint8_t* bgra, size_t nbytes) {
+    if (!c || !bgra) return BPT_E_INVALID;
+    if (!c->image) return bpt_fail(c, BPT_E_STATE, "no image yet");
+    size_t npix = (size_t)c->img_w * c->img_h;
+    if (nbytes < npix * 4) return bpt_fail(c, BPT_E_INVALID, "buffer holds %zu bytes, image needs %zu", nbytes, npix * 4);
+    cudaSetDevice(c->device);
+    uint8_t* d = nullptr;
+    BPT_CUDA_TRY(c, cudaMalloc(&d, npix * 4));
+    launch_image_to_bgra8(c->image, d, npix, c->stream);
+    cudaError_t e = cudaMemcpyAsync(bgra, d, npix * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    BPT_CUDA_TRY(c, e);
+    return BPT_OK;
+}
+
+int bpt_image_device_ptr(bpt_context* c, void** dptr, size_t* nbytes) {
+    if (!c || !dptr) return BPT_E_INVALID;
+    if (!c->image) return bpt_fail(c, BPT_E_STATE, "no image yet");
+    *dptr = c->image;
+    if (nbytes) *nbytes = (size_t)c->img_w * c->img_h * sizeof(float4);
+    return BPT_OK;
+}
+
+int bpt_clear_image(bpt_context* c) {
+    if (!c) return BPT_E_INVALID;
+    cudaSetDevice(c->device);
+    if (c->image) BPT_CUDA_TRY(c, cudaMemsetAsync(c->image, 0, (size_t)c->img_w * c->img_h * sizeof(float4), c->stream));
+    if (c->frame_sum) BPT_CUDA_TRY(c, cudaMemsetAsync(c->frame_sum, 0, c->cap_paths * sizeof(float4), c->stream));
+    return BPT_OK;
+}
+
+int bpt_get_stats(bpt_context* c, bpt_stats* out) {
+    if (!c || !out) return BPT_E_INVALID;
+    cudaSetDevice(c->device);
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    unsigned long long h[3];
+    BPT_CUDA_TRY(c, cudaMemcpy(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+    c->stats.rays_traced = h[0];
+    c->stats.nodes_visited = h[1];
+    c->stats.tris_tested = h[2];
+    for (auto& p : c->frame_events) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, p.first, p.second);
+        c->stats.frame_ms += ms;
+        c->event_pool.push_back(p.first); c->event_pool.push_back(p.second);
+    }
+    c->frame_events.clear();
+    for (auto& p : c->trace_events) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, p.first, p.second);
+        c->stats.trace_kernel_ms += ms;
+        c->event_pool.push_back(p.first); c->event_pool.push_back(p.second);
+    }
+    c->trace_events.clear();
+    *out = c->stats;
+    return BPT_OK;
+}
+
+int bpt_reset_stats(bpt_context* c) {
+    if (!c) return BPT_E_INVALID;
+    cudaSetDevice(c->device);
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    bpt_stats tmp;
+    bpt_get_stats(c, &tmp);
+    double build = c->stats.build_ms;
+    c->stats = bpt_stats{};
+    c->stats.build_ms = build;
+    BPT_CUDA_TRY(c, cudaMemset(c->d_stats, 0, 4 * sizeof(unsigned long long)));
+    return BPT_OK;
+}
+
+int bpt_trace_rays(bpt_context* c, const float* rays, uint32_t n, void* hits) {
+    if (!c || !rays || !hits) return BPT_E_INVALID;
+    if (!c->built) return bpt_fail(c, BPT_E_STATE, "bpt_trace_rays before bpt_build_accel");
+    if (n == 0) return BPT_OK;
+    cudaSetDevice(c->device);
+    int rc = ensure_paths(c, n);
+    if (rc) return rc;
+    uint32_t init[2] = {n, 0u};
+    uint32_t* counts = c->counters;
+    uint32_t* fetch = c->counters + (kMaxDepth + 1);
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(c->q[0].rays, rays, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(counts, &init[0], 4, cudaMemcpyHostToDevice, c->stream));
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(fetch, &init[1], 4, cudaMemcpyHostToDevice, c->stream));
+    launch_trace(c, make_trace_args(c, c->q[0].rays, c->hits, counts, fetch));
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(hits, c->hits, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    BPT_CUDA_TRY(c, cudaGetLastError());
+    return BPT_OK;
+}
+
+int bpt_generate_rays(bpt_context* c, const bpt_params* p, uint32_t sample_in_frame, float* rays, uint32_t* seeds) {
+    if (!c || !rays || !seeds) return BPT_E_INVALID;
+    int rc = check_params(c, p);
+    if (rc) return rc;
+    cudaSetDevice(c->device);
+    FrameParams f = to_frame(p);
+    if (f.tile_rows == 0) f.tile_rows = f.height - f.tile_y0;
+    const uint32_t npix = f.tile_rows * f.width;
+    if ((rc = ensure_paths(c, npix)) != BPT_OK) return rc;
+    uint32_t* counts = c->counters;
+    uint32_t* fetch = c->counters + (kMaxDepth + 1);
+    launch_generate(f, sample_in_frame, c->q[0], counts, fetch, f.max_depth + 1, c->stream);
+    std::vector<float4> st(npix);
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(rays, c->q[0].rays, (size_t)npix * 32, cudaMemcpyDeviceToHost, c->stream));
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(st.data(), c->q[0].state, (size_t)npix * 16, cudaMemcpyDeviceToHost, c->stream));
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (uint32_t i = 0; i < npix; ++i) memcpy(&seeds[i], &st[i].w, 4);
+    return BPT_OK;
+}
+
+int bpt_download_accel(bpt_context* c, void* nodes8, uint32_t* tri_index, float* woop) {
+    if (!c) return BPT_E_INVALID;
+    if (!c->built) return bpt_fail(c, BPT_E_STATE, "no acceleration structure built");
+    cudaSetDevice(c->device);
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (nodes8) BPT_CUDA_TRY(c, cudaMemcpy(nodes8, c->blas.nodes, (size_t)c->blas.num_nodes * 80, cudaMemcpyDeviceToHost));
+    if (tri_index) BPT_CUDA_TRY(c, cudaMemcpy(tri_index, c->blas.prim_index, (size_t)c->ntris * 4, cudaMemcpyDeviceToHost));
+    if (woop) BPT_CUDA_TRY(c, cudaMemcpy(woop, c->d_woop, (size_t)c->ntris * 48, cudaMemcpyDeviceToHost));
+    return BPT_OK;
+}
+
+int bpt_download_mesh(bpt_context* c, float* verts, uint32_t* indices, float* faces) {
+    if (!c) return BPT_E_INVALID;
+    if (c->ntris == 0) return bpt_fail(c, BPT_E_STATE, "no mesh uploaded");
+    cudaSetDevice(c->device);
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (verts) BPT_CUDA_TRY(c, cudaMemcpy(verts, c->d_verts, (size_t)c->nverts * 12, cudaMemcpyDeviceToHost));
+    if (indices) BPT_CUDA_TRY(c, cudaMemcpy(indices, c->d_idx, (size_t)c->nidx * 4, cudaMemcpyDeviceToHost));
+    if (faces) BPT_CUDA_TRY(c, cudaMemcpy(faces, c->d_faces, (size_t)c->nfaces * 24, cudaMemcpyDeviceToHost));
+    return BPT_OK;
+}
+
+int bpt_download_morton(bpt_context* c, uint64_t* keys, uint32_t n) {
+    if (!c || !keys) return BPT_E_INVALID;
+    if (!c->built) return bpt_fail(c, BPT_E_STATE, "no acceleration structure built");
+    if (n != c->ntris) return bpt_fail(c, BPT_E_INVALID, "n must equal the triangle count %u", c->ntris);
+    cudaSetDevice(c->device);
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    BPT_CUDA_TRY(c, cudaMemcpy(keys, c->blas.keys, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return BPT_OK;
+}
+
+int bpt_download_lbvh(bpt_context* c, uint32_t* left, uint32_t* right, float* aabbs) {
+    if (!c) return BPT_E_INVALID;
+    if (!c->built) return bpt_fail(c, BPT_E_STATE, "no acceleration structure built");
+    cudaSetDevice(c->device);
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    const uint32_t n = c->ntris;
+    if (left && n > 1) BPT_CUDA_TRY(c, cudaMemcpy(left, c->blas.left, (size_t)(n - 1) * 4, cudaMemcpyDeviceToHost));
+    if (right && n > 1) BPT_CUDA_TRY(c, cudaMemcpy(right, c->blas.right, (size_t)(n - 1) * 4, cudaMemcpyDeviceToHost));
+    if (aabbs) {
+        std::vector<float4> lo(2 * (size_t)n - 1), hi(2 * (size_t)n - 1);
+        BPT_CUDA_TRY(c, cudaMemcpy(lo.data(), c->blas.nlo, lo.size() * 16, cudaMemcpyDeviceToHost));
+        BPT_CUDA_TRY(c, cudaMemcpy(hi.data(), c->blas.nhi, hi.size() * 16, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < lo.size(); ++i) {
+            aabbs[6 * i + 0] = lo[i].x; aabbs[6 * i + 1] = lo[i].y; aabbs[6 * i + 2] = lo[i].z;
+            aabbs[6 * i + 3] = hi[i].x; aabbs[6 * i + 4] = hi[i].y; aabbs[6 * i + 5] = hi[i].z;
+        }
+    }
+    return BPT_OK;
+}
+
+// ---------------------------------------------------------------- multi-GPU
+void bpt_tile_rows(uint32_t height, int rank, int nranks, uint32_t* y0, uint32_t* rows) {
+    if (nranks < 1) nranks = 1;
+    uint32_t per = height / (uint32_t)nranks;
+    if (y0) *y0 = per * (uint32_t)rank;
+    if (rows) *rows = per;
+}
+
+int bpt_nccl_unique_id(uint8_t id[BPT_NCCL_UNIQUE_ID_BYTES]) {
+    std::string err;
+    if (bpt_nccl_get_unique_id(id, &err) != 0) return bpt_fail(nullptr, BPT_E_NCCL, "%s", err.c_str());
+    return BPT_OK;
+}
+
+int bpt_nccl_init(bpt_context* c, const uint8_t id[BPT_NCCL_UNIQUE_ID_BYTES], int rank, int nranks) {
+    if (!c || !id) return BPT_E_INVALID;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return bpt_fail(c, BPT_E_INVALID, "bad rank %d of %d", rank, nranks);
+    cudaSetDevice(c->device);
+    if (c->nccl_comm) { bpt_nccl_comm_destroy(c->nccl_comm); c->nccl_comm = nullptr; }
+    std::string err;
+    if (bpt_nccl_comm_init(&c->nccl_comm, id, rank, nranks, &err) != 0) return bpt_fail(c, BPT_E_NCCL, "%s", err.c_str());
+    c->rank = rank;
+    c->nranks = nranks;
+    return BPT_OK;
+}
+
+int bpt_allgather_image(bpt_context* c, uint32_t width, uint32_t height) {
+    if (!c) return BPT_E_INVALID;
+    if (!c->nccl_comm) return bpt_fail(c, BPT_E_STATE, "bpt_allgather_image before bpt_nccl_init");
+    if (!c->image || c->img_w != width || c->img_h != height) return bpt_fail(c, BPT_E_STATE, "image is not %ux%u", width, height);
+    if (height % (uint32_t)c->nranks) return bpt_fail(c, BPT_E_INVALID, "height %u not divisible by %d ranks", height, c->nranks);
+    cudaSetDevice(c->device);
+    uint32_t y0, rows;
+    bpt_tile_rows(height, c->rank, c->nranks, &y0, &rows);
+    size_t count = (size_t)rows * width * 4;  // floats per rank
+    std::string err;
+    // in place: this rank's tile already sits at its slot of the full image (K12 wrote it there)
+    if (bpt_nccl_allgather_f32(c->nccl_comm, c->image + (size_t)y0 * width, c->image, count, c->stream, &err) != 0)
+        return bpt_fail(c, BPT_E_NCCL, "%s", err.c_str());
+    return BPT_OK;
+}
+
+}  // extern "C"

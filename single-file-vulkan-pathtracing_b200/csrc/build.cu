@@ -1,0 +1,508 @@
+// build.cu — acceleration-structure build on the GPU.
+//
+// Replaces the driver work behind Accel::Accel -> buildAccelerationStructuresKHR
+// (reference main.cpp:416-450; BLAS at :512, TLAS at :538) with:
+//   K1  prim_bounds      per-primitive AABB + scene bounds (warp-shuffle reduce, ordered-int atomics)
+//   K2  morton_keys      30-bit Morton code of the AABB centre; 64-bit key = morton << 32 | prim
+//   K3  radix sort       radix_sort.cu (hand-written 8-bit LSD onesweep-style passes)
+//   K4  lbvh_hierarchy   Karras 2012: one thread per internal node, clz on key XOR
+//   K5  lbvh_refit       bottom-up AABBs with per-node arrival counters
+//   K6  bvh8_collapse    binary -> 8-wide, greedy largest-area opening, octant slot assignment,
+//                        quantisation to the 80-byte Node8 (level-synchronous, BFS node order)
+//   K7  woop_transform   48-byte unit-triangle transforms in leaf order
+// Everything is generic over "primitives with an AABB" so the same code builds the instance-level
+// BVH8 of two-level scenes.
+#include <cfloat>
+#include <cstdio>
+
+#include "build.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+inline unsigned grid_for(uint64_t n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
+
+// ---------------------------------------------------------------- ordered-int float atomics
+__device__ __forceinline__ uint32_t enc_f(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float dec_f(uint32_t u) {
+    uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+
+__global__ void k_init_bounds(uint32_t* b) {
+    if (threadIdx.x < 3) b[threadIdx.x] = 0xffffffffu;       // min
+    else if (threadIdx.x < 6) b[threadIdx.x] = 0u;           // max
+}
+
+__device__ __forceinline__ void warp_reduce_bounds(float lo[3], float hi[3], uint32_t* bounds) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(&bounds[a], enc_f(lo[a]));
+            atomicMax(&bounds[3 + a], enc_f(hi[a]));
+        }
+    }
+}
+
+// K1 (triangles): AABB of triangle i from the indexed vertex buffer (closesthit.rchit:52-54 layout).
+__global__ void k_tri_bounds(const float* __restrict__ verts, const uint32_t* __restrict__ idx, uint32_t n,
+                             float4* __restrict__ plo, float4* __restrict__ phi, uint32_t* bounds) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    if (i < n) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* v = verts + 3 * (size_t)idx[3 * (size_t)i + c];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = fminf(lo[a], v[a]);
+                hi[a] = fmaxf(hi[a], v[a]);
+            }
+        }
+        plo[i] = make_float4(lo[0], lo[1], lo[2], 0.f);
+        phi[i] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    }
+    warp_reduce_bounds(lo, hi, bounds);
+}
+
+// K1 (instances): world AABB of instance i = transformed corners of the mesh bounds.
+__global__ void k_instance_bounds(const float* __restrict__ xf, uint32_t n, float3 mlo, float3 mhi,
+                                  float4* __restrict__ plo, float4* __restrict__ phi, uint32_t* bounds) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    if (i < n) {
+        const float* m = xf + 12 * (size_t)i;
+        for (int c = 0; c < 8; ++c) {
+            float x = (c & 1) ? mhi.x : mlo.x, y = (c & 2) ? mhi.y : mlo.y, z = (c & 4) ? mhi.z : mlo.z;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                float w = m[4 * r] * x + m[4 * r + 1] * y + m[4 * r + 2] * z + m[4 * r + 3];
+                // widen by a few ulp: the shade kernel transforms vertices without FMA
+                float e = 4e-7f * (fabsf(m[4 * r] * x) + fabsf(m[4 * r + 1] * y) + fabsf(m[4 * r + 2] * z) + fabsf(m[4 * r + 3]));
+                lo[r] = fminf(lo[r], w - e);
+                hi[r] = fmaxf(hi[r], w + e);
+            }
+        }
+        plo[i] = make_float4(lo[0], lo[1], lo[2], 0.f);
+        phi[i] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    }
+    warp_reduce_bounds(lo, hi, bounds);
+}
+
+// K2: 10 bits per axis, x most significant inside each triple.
+__device__ __forceinline__ uint32_t expand10(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t morton30(float x, float y, float z) {
+    uint32_t qx = (uint32_t)fminf(fmaxf(x * 1024.0f, 0.0f), 1023.0f);
+    uint32_t qy = (uint32_t)fminf(fmaxf(y * 1024.0f, 0.0f), 1023.0f);
+    uint32_t qz = (uint32_t)fminf(fmaxf(z * 1024.0f, 0.0f), 1023.0f);
+    return expand10(qx) * 4u + expand10(qy) * 2u + expand10(qz);
+}
+__global__ void k_morton_keys(const float4* __restrict__ plo, const float4* __restrict__ phi, uint32_t n,
+                              const uint32_t* __restrict__ bounds, uint64_t* __restrict__ keys) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float3 blo = make_float3(dec_f(bounds[0]), dec_f(bounds[1]), dec_f(bounds[2]));
+    float3 bhi = make_float3(dec_f(bounds[3]), dec_f(bounds[4]), dec_f(bounds[5]));
+    float4 lo = plo[i], hi = phi[i];
+    float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
+    float ex = bhi.x - blo.x, ey = bhi.y - blo.y, ez = bhi.z - blo.z;
+    float nx = ex > 0.f ? (cx - blo.x) / ex : 0.f;
+    float ny = ey > 0.f ? (cy - blo.y) / ey : 0.f;
+    float nz = ez > 0.f ? (cz - blo.z) / ez : 0.f;
+    keys[i] = ((uint64_t)morton30(nx, ny, nz) << 32) | i;
+}
+
+// K4: Karras 2012. Keys are unique (primitive id in the low word), so delta needs no tie-break.
+// Node ids: internal i in [0,n-1); leaf k is n-1+k.
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, uint64_t ki, int j) {
+    if (j < 0 || j >= n) return -1;
+    return __clzll((long long)(ki ^ keys[j]));
+}
+__global__ void k_lbvh_hierarchy(const uint64_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ left,
+                                 uint32_t* __restrict__ right, uint32_t* __restrict__ parent,
+                                 uint32_t* __restrict__ first, uint32_t* __restrict__ last) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int ni = (int)n;
+    if (i >= ni - 1) return;
+    uint64_t ki = keys[i];
+    int d = (delta(keys, ni, ki, i + 1) - delta(keys, ni, ki, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(keys, ni, ki, i - d);
+    int lmax = 2;
+    while (delta(keys, ni, ki, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, ni, ki, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(keys, ni, ki, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, ni, ki, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    uint32_t lc = (lo == gamma) ? (uint32_t)(ni - 1 + gamma) : (uint32_t)gamma;
+    uint32_t rc = (hi == gamma + 1) ? (uint32_t)(ni - 1 + gamma + 1) : (uint32_t)(gamma + 1);
+    left[i] = lc;
+    right[i] = rc;
+    parent[lc] = (uint32_t)i;
+    parent[rc] = (uint32_t)i;
+    first[i] = (uint32_t)lo;
+    last[i] = (uint32_t)hi;
+    if (i == 0) parent[0] = 0xffffffffu;
+}
+
+// K5: leaves copy their primitive box, then climb; the second arrival at a node merges.
+__global__ void k_lbvh_refit(const uint64_t* __restrict__ keys, uint32_t n, const float4* __restrict__ plo,
+                             const float4* __restrict__ phi, const uint32_t* __restrict__ left,
+                             const uint32_t* __restrict__ right, const uint32_t* __restrict__ parent,
+                             uint32_t* __restrict__ arrive, float4* __restrict__ nlo, float4* __restrict__ nhi) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t prim = (uint32_t)(keys[k] & 0xffffffffu);
+    uint32_t node = n - 1 + k;
+    float4 lo = plo[prim], hi = phi[prim];
+    nlo[node] = lo;
+    nhi[node] = hi;
+    if (n == 1) return;
+    uint32_t p = parent[node];
+    while (p != 0xffffffffu) {
+        __threadfence();
+        if (atomicAdd(&arrive[p], 1u) == 0u) return;  // first to arrive: sibling not ready
+        uint32_t a = left[p], b = right[p];
+        float4 alo = __ldcg(&nlo[a]), ahi = __ldcg(&nhi[a]), blo = __ldcg(&nlo[b]), bhi = __ldcg(&nhi[b]);
+        lo = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.f);
+        hi = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.f);
+        nlo[p] = lo;
+        nhi[p] = hi;
+        p = parent[p];
+    }
+}
+
+// ---------------------------------------------------------------- K6: collapse to BVH8
+struct CollapseArgs {
+    uint32_t n;  // primitives
+    const uint64_t* keys;
+    const uint32_t *left, *right, *first, *last;
+    const float4 *nlo, *nhi;
+    Node8* nodes;
+    uint32_t* wide_src;    // node8 index -> binary node id it expands
+    uint32_t* prim_index;  // leaf slot -> primitive id
+    uint32_t* counters;    // [0] node count, [1] leaf-slot count
+    uint32_t level_begin, level_end;
+    float pad;             // conservative widening of every quantised box (world units)
+};
+
+__device__ __forceinline__ uint32_t node_count(const CollapseArgs& a, uint32_t node) {
+    return node >= a.n - 1 ? 1u : a.last[node] - a.first[node] + 1u;
+}
+__device__ __forceinline__ uint32_t node_first(const CollapseArgs& a, uint32_t node) {
+    return node >= a.n - 1 ? node - (a.n - 1) : a.first[node];
+}
+__device__ __forceinline__ float half_area(float4 lo, float4 hi) {
+    float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// exponent e with 2^e * 255 >= ext (with margin), clamped away from denormals
+__device__ __forceinline__ int quant_exponent(float ext) {
+    if (!(ext > 0.f)) return -100;
+    int k;
+    frexpf(ext * (1.001f / 255.0f), &k);  // value = m * 2^k, m in [0.5,1)  =>  2^k > value
+    return max(-100, min(k, 120));
+}
+
+__global__ void k_bvh8_collapse(CollapseArgs a) {
+    uint32_t w = a.level_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= a.level_end) return;
+    const uint32_t src = a.wide_src[w];
+
+    uint32_t cand[8];
+    float area[8];
+    uint32_t cnt[8];
+    int nc = 1;
+    cand[0] = src;
+    cnt[0] = node_count(a, src);
+    area[0] = FLT_MAX;
+    // greedy: open the largest-area candidate that still holds >= 2 primitives
+    while (nc < 8) {
+        int best = -1;
+        float barea = -1.f;
+        for (int c = 0; c < nc; ++c)
+            if (cnt[c] >= 2u && area[c] > barea) { barea = area[c]; best = c; }
+        if (best < 0) break;
+        uint32_t b = cand[best];
+        uint32_t l = a.left[b], r = a.right[b];
+        cand[best] = l;
+        cnt[best] = node_count(a, l);
+        area[best] = half_area(a.nlo[l], a.nhi[l]);
+        cand[nc] = r;
+        cnt[nc] = node_count(a, r);
+        area[nc] = half_area(a.nlo[r], a.nhi[r]);
+        ++nc;
+    }
+
+    const float4 blo = a.nlo[src], bhi = a.nhi[src];
+    const float pad = a.pad;
+    const float px = blo.x - pad, py = blo.y - pad, pz = blo.z - pad;
+    const float cx = 0.5f * (blo.x + bhi.x), cy = 0.5f * (blo.y + bhi.y), cz = 0.5f * (blo.z + bhi.z);
+
+    // slot assignment: slot bit 2/1/0 set = child lies on the +x/+y/+z side of the node centre.
+    // Greedy maximum of dot(sign(slot), child centre - node centre) over unassigned pairs.
+    float4 clo[8], chi[8];
+    float ddx[8], ddy[8], ddz[8];
+    for (int c = 0; c < nc; ++c) {
+        clo[c] = a.nlo[cand[c]];
+        chi[c] = a.nhi[cand[c]];
+        ddx[c] = 0.5f * (clo[c].x + chi[c].x) - cx;
+        ddy[c] = 0.5f * (clo[c].y + chi[c].y) - cy;
+        ddz[c] = 0.5f * (clo[c].z + chi[c].z) - cz;
+    }
+    int slot_of[8];
+    int child_in[8];
+    for (int s = 0; s < 8; ++s) child_in[s] = -1;
+    for (int c = 0; c < nc; ++c) slot_of[c] = -1;
+    for (int it = 0; it < nc; ++it) {
+        float bs = -FLT_MAX;
+        int bc = -1, bsl = -1;
+        for (int c = 0; c < nc; ++c) {
+            if (slot_of[c] >= 0) continue;
+            for (int s = 0; s < 8; ++s) {
+                if (child_in[s] >= 0) continue;
+                float sc = ((s & 4) ? ddx[c] : -ddx[c]) + ((s & 2) ? ddy[c] : -ddy[c]) + ((s & 1) ? ddz[c] : -ddz[c]);
+                if (sc > bs) { bs = sc; bc = c; bsl = s; }
+            }
+        }
+        slot_of[bc] = bsl;
+        child_in[bsl] = bc;
+    }
+
+    // allocate internal children (contiguous, in slot order) and leaf slots
+    uint32_t n_int = 0, n_leaf = 0;
+    for (int c = 0; c < nc; ++c) {
+        if (cnt[c] > 3u) ++n_int; else n_leaf += cnt[c];
+    }
+    uint32_t child_base = n_int ? atomicAdd(&a.counters[0], n_int) : 0u;
+    uint32_t tri_base = n_leaf ? atomicAdd(&a.counters[1], n_leaf) : 0u;
+
+    Node8 nd;
+    nd.px = px; nd.py = py; nd.pz = pz;
+    const int ex = quant_exponent((bhi.x + pad) - px), ey = quant_exponent((bhi.y + pad) - py),
+              ez = quant_exponent((bhi.z + pad) - pz);
+    nd.ex = (uint8_t)(ex + 127); nd.ey = (uint8_t)(ey + 127); nd.ez = (uint8_t)(ez + 127);
+    nd.child_base = child_base;
+    nd.tri_base = tri_base;
+    const float sx = exp2f((float)ex), sy = exp2f((float)ey), sz = exp2f((float)ez);
+    const float isx = exp2f((float)-ex), isy = exp2f((float)-ey), isz = exp2f((float)-ez);
+    uint32_t imask = 0, int_rank = 0, leaf_off = 0;
+    for (int s = 0; s < 8; ++s) {
+        int c = child_in[s];
+        if (c < 0) {
+            nd.meta[s] = 0;
+            nd.qlox[s] = nd.qloy[s] = nd.qloz[s] = 255;
+            nd.qhix[s] = nd.qhiy[s] = nd.qhiz[s] = 0;
+            continue;
+        }
+        // conservative quantisation: origin + qlo*scale <= lo - pad, origin + qhi*scale >= hi + pad
+        auto qlo = [&](float v, float p, float sc, float isc) {
+            float t = v - pad;
+            int q = (int)floorf((t - p) * isc);
+            q = max(0, min(q, 255));
+            while (q > 0 && p + (float)q * sc > t) --q;
+            return (uint8_t)q;
+        };
+        auto qhi = [&](float v, float p, float sc, float isc) {
+            float t = v + pad;
+            int q = (int)ceilf((t - p) * isc);
+            q = max(0, min(q, 255));
+            while (q < 255 && p + (float)q * sc < t) ++q;
+            return (uint8_t)q;
+        };
+        nd.qlox[s] = qlo(clo[c].x, px, sx, isx); nd.qhix[s] = qhi(chi[c].x, px, sx, isx);
+        nd.qloy[s] = qlo(clo[c].y, py, sy, isy); nd.qhiy[s] = qhi(chi[c].y, py, sy, isy);
+        nd.qloz[s] = qlo(clo[c].z, pz, sz, isz); nd.qhiz[s] = qhi(chi[c].z, pz, sz, isz);
+        if (cnt[c] > 3u) {
+            imask |= 1u << s;
+            nd.meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));
+            a.wide_src[child_base + int_rank] = cand[c];
+            ++int_rank;
+        } else {
+            uint32_t k = cnt[c];
+            nd.meta[s] = (uint8_t)((((1u << k) - 1u) << 5) | leaf_off);
+            uint32_t f = node_first(a, cand[c]);
+            for (uint32_t j = 0; j < k; ++j)
+                a.prim_index[tri_base + leaf_off + j] = (uint32_t)(a.keys[f + j] & 0xffffffffu);
+            leaf_off += k;
+        }
+    }
+    nd.imask = (uint8_t)imask;
+    uint4* dst = reinterpret_cast<uint4*>(a.nodes + w);
+    const uint4* srcw = reinterpret_cast<const uint4*>(&nd);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) dst[q] = srcw[q];
+}
+
+// K7: Woop transform of the triangle in leaf slot s. Rows are computed in double and rounded once.
+__global__ void k_woop(const float* __restrict__ verts, const uint32_t* __restrict__ idx,
+                       const uint32_t* __restrict__ prim_index, uint32_t n, WoopTri* __restrict__ out) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    uint32_t prim = prim_index[s];
+    double v[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* p = verts + 3 * (size_t)idx[3 * (size_t)prim + c];
+        v[c][0] = p[0]; v[c][1] = p[1]; v[c][2] = p[2];
+    }
+    double e1[3] = {v[1][0] - v[0][0], v[1][1] - v[0][1], v[1][2] - v[0][2]};
+    double e2[3] = {v[2][0] - v[0][0], v[2][1] - v[0][1], v[2][2] - v[0][2]};
+    double nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
+    double det = nx * nx + ny * ny + nz * nz;  // det [e1 e2 n]
+    WoopTri w;
+    if (!(det > 0.0) || !isfinite(det)) {
+        w.ru = w.rv = w.rw = make_float4(0.f, 0.f, 0.f, 0.f);  // degenerate: d'.z == 0 -> never hit
+    } else {
+        double inv = 1.0 / det;
+        // rows of [e1 e2 n]^-1: (e2 x n)/det, (n x e1)/det, n/det
+        double ru[3] = {(e2[1] * nz - e2[2] * ny) * inv, (e2[2] * nx - e2[0] * nz) * inv, (e2[0] * ny - e2[1] * nx) * inv};
+        double rv[3] = {(ny * e1[2] - nz * e1[1]) * inv, (nz * e1[0] - nx * e1[2]) * inv, (nx * e1[1] - ny * e1[0]) * inv};
+        double rw[3] = {nx * inv, ny * inv, nz * inv};
+        double cu = -(ru[0] * v[0][0] + ru[1] * v[0][1] + ru[2] * v[0][2]);
+        double cv = -(rv[0] * v[0][0] + rv[1] * v[0][1] + rv[2] * v[0][2]);
+        double cw = -(rw[0] * v[0][0] + rw[1] * v[0][1] + rw[2] * v[0][2]);
+        w.ru = make_float4((float)ru[0], (float)ru[1], (float)ru[2], (float)cu);
+        w.rv = make_float4((float)rv[0], (float)rv[1], (float)rv[2], (float)cv);
+        w.rw = make_float4((float)rw[0], (float)rw[1], (float)rw[2], (float)cw);
+    }
+    out[s] = w;
+}
+
+template <class T>
+cudaError_t dalloc(T** p, size_t count) {
+    return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T) + 16);
+}
+
+}  // namespace
+
+void bvh8_free(Bvh8& b) {
+    cudaFree(b.plo); cudaFree(b.phi); cudaFree(b.keys); cudaFree(b.keys_tmp); cudaFree(b.left); cudaFree(b.right);
+    cudaFree(b.parent); cudaFree(b.first); cudaFree(b.last); cudaFree(b.arrive); cudaFree(b.nlo); cudaFree(b.nhi);
+    cudaFree(b.nodes); cudaFree(b.wide_src); cudaFree(b.prim_index); cudaFree(b.counters); cudaFree(b.bounds);
+    cudaFree(b.sort_tmp);
+    b = Bvh8{};
+}
+
+cudaError_t bvh8_alloc(Bvh8& b, uint32_t n) {
+    bvh8_free(b);
+    b.n = n;
+    cudaError_t e;
+#define A(x) if ((e = (x)) != cudaSuccess) return e
+    A(dalloc(&b.plo, n)); A(dalloc(&b.phi, n));
+    A(dalloc(&b.keys, n)); A(dalloc(&b.keys_tmp, n));
+    A(dalloc(&b.left, n)); A(dalloc(&b.right, n)); A(dalloc(&b.first, n)); A(dalloc(&b.last, n));
+    A(dalloc(&b.parent, 2 * (size_t)n)); A(dalloc(&b.arrive, n));
+    A(dalloc(&b.nlo, 2 * (size_t)n)); A(dalloc(&b.nhi, 2 * (size_t)n));
+    // every wide node expands at least one binary internal node, so n nodes always suffice
+    b.nodes_cap = n < 8 ? 8 : n;
+    A(dalloc(&b.nodes, b.nodes_cap)); A(dalloc(&b.wide_src, b.nodes_cap));
+    A(dalloc(&b.prim_index, n));
+    A(dalloc(&b.counters, 8)); A(dalloc(&b.bounds, 8));
+    b.sort_tmp_bytes = radix_sort_u64_temp_bytes(n);
+    A(cudaMalloc(&b.sort_tmp, b.sort_tmp_bytes));
+#undef A
+    return cudaSuccess;
+}
+
+void bvh8_launch_tri_bounds(Bvh8& b, const float* verts, const uint32_t* idx, cudaStream_t st) {
+    k_init_bounds<<<1, 32, 0, st>>>(b.bounds);
+    k_tri_bounds<<<grid_for(b.n), kBlock, 0, st>>>(verts, idx, b.n, b.plo, b.phi, b.bounds);
+}
+void bvh8_launch_instance_bounds(Bvh8& b, const float* xforms, const float mesh_lo[3], const float mesh_hi[3],
+                                 cudaStream_t st) {
+    k_init_bounds<<<1, 32, 0, st>>>(b.bounds);
+    k_instance_bounds<<<grid_for(b.n), kBlock, 0, st>>>(xforms, b.n, make_float3(mesh_lo[0], mesh_lo[1], mesh_lo[2]),
+                                                         make_float3(mesh_hi[0], mesh_hi[1], mesh_hi[2]), b.plo,
+                                                         b.phi, b.bounds);
+}
+
+// Runs K2..K6 on the primitive boxes already in b.plo/b.phi/b.bounds. Synchronises the stream
+// once per BVH8 level (the reference's build is synchronous as well: main.cpp:236-237).
+cudaError_t bvh8_build(Bvh8& b, cudaStream_t st) {
+    const uint32_t n = b.n;
+    cudaError_t e;
+    k_morton_keys<<<grid_for(n), kBlock, 0, st>>>(b.plo, b.phi, n, b.bounds, b.keys);
+    // K3: sort the 62 significant bits (30-bit morton + 32-bit primitive id)
+    uint64_t* sorted = radix_sort_u64(b.keys, b.keys_tmp, n, 0, 62, b.sort_tmp, b.sort_tmp_bytes, st);
+    if (sorted != b.keys) { uint64_t* t = b.keys; b.keys = b.keys_tmp; b.keys_tmp = t; }
+    if ((e = cudaMemsetAsync(b.arrive, 0, sizeof(uint32_t) * n, st)) != cudaSuccess) return e;
+    if (n > 1) k_lbvh_hierarchy<<<grid_for(n - 1), kBlock, 0, st>>>(b.keys, n, b.left, b.right, b.parent, b.first, b.last);
+    k_lbvh_refit<<<grid_for(n), kBlock, 0, st>>>(b.keys, n, b.plo, b.phi, b.left, b.right, b.parent, b.arrive, b.nlo, b.nhi);
+
+    uint32_t hb[6];
+    if ((e = cudaMemcpyAsync(hb, b.bounds, sizeof(hb), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    float diag = 0.f, mag = 0.f;
+    for (int a = 0; a < 3; ++a) {
+        b.scene_lo[a] = dec_f(hb[a]);
+        b.scene_hi[a] = dec_f(hb[3 + a]);
+        float d = b.scene_hi[a] - b.scene_lo[a];
+        diag += d * d;
+        mag = fmaxf(mag, fmaxf(fabsf(b.scene_lo[a]), fabsf(b.scene_hi[a])));
+    }
+    diag = sqrtf(diag);
+
+    CollapseArgs a;
+    a.n = n; a.keys = b.keys; a.left = b.left; a.right = b.right; a.first = b.first; a.last = b.last;
+    a.nlo = b.nlo; a.nhi = b.nhi; a.nodes = b.nodes; a.wide_src = b.wide_src; a.prim_index = b.prim_index;
+    a.counters = b.counters;
+    a.pad = 9.5367431640625e-07f * fmaxf(diag, mag);  // 2^-20 of the scene scale
+    uint32_t init[2] = {1u, 0u};                       // node 0 = root, expands binary root
+    uint32_t root_src = (n == 1) ? 0u : 0u;            // internal 0, or leaf 0 when n == 1 (same id)
+    if ((e = cudaMemcpyAsync(b.counters, init, sizeof(init), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(b.wide_src, &root_src, sizeof(uint32_t), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    uint32_t begin = 0, end = 1, depth = 0;
+    while (begin < end) {
+        a.level_begin = begin;
+        a.level_end = end;
+        k_bvh8_collapse<<<grid_for(end - begin, 64), 64, 0, st>>>(a);
+        uint32_t hc[2];
+        if ((e = cudaMemcpyAsync(hc, b.counters, sizeof(hc), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        ++depth;
+        begin = end;
+        end = hc[0];
+        b.num_leaf_slots = hc[1];
+        if (end > b.nodes_cap) return cudaErrorMemoryAllocation;
+    }
+    b.num_nodes = end;
+    b.depth = depth;
+    return cudaSuccess;
+}
+
+void bvh8_launch_woop(const Bvh8& b, const float* verts, const uint32_t* idx, WoopTri* out, cudaStream_t st) {
+    k_woop<<<grid_for(b.n), kBlock, 0, st>>>(verts, idx, b.prim_index, b.n, out);
+}

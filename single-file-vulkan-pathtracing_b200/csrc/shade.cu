@@ -1,0 +1,243 @@
+// shade.cu — K9 generate, K11 shade, K12 accumulate (+ the synthetic soup generator).
+//
+// This translation unit is compiled with --fmad=false and without fast-math so that every
+// float operation is the single IEEE operation the shader text names, in the same order as the
+// CPU checker (tests) restates it; the only library calls whose last bit may differ from a host libm are
+// sinf/cosf. Reference lines (paths relative to the reference checkout):
+//   K9  shaders/raygen.rgen:47-60   seed, jitter, camera ray, weight = 1
+//   K11 shaders/closesthit.rchit:50-64, shaders/miss.rmiss:8-12, shaders/raygen.rgen:14-39,76-83
+//   K12 shaders/raygen.rgen:86-90   (rgba8 emulation: main.cpp:481-484)
+#include <algorithm>
+
+#include "shade.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 operator*(V3 a, V3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+__device__ __forceinline__ V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ V3 normalize(V3 a) { return a / sqrtf(dot(a, a)); }
+
+constexpr float kTwoPi = 6.2831855f, kPi = 3.1415927f, kPdf = 0.15915494f;
+
+// ---------------------------------------------------------------- K9
+__global__ void k_generate(FrameParams p, uint32_t sample_in_frame, PathQueue q, uint32_t* counts, uint32_t* fetch,
+                           uint32_t ncounters) {
+    const uint32_t rows = p.tile_rows ? p.tile_rows : p.height;
+    const uint32_t npix = rows * p.width;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ncounters) {  // queue lengths and fetch counters of this sample pass
+        counts[i] = i == 0 ? npix : 0u;
+        fetch[i] = 0u;
+    }
+    if (i >= npix) return;
+    const uint32_t px = i % p.width, py = p.tile_y0 + i / p.width;
+    const uint32_t k = sample_in_frame + p.spp_per_frame * (uint32_t)p.frame + 1u;  // raygen.rgen:47
+    uint32_t sx = px * k, sy = py * k;
+    bpt_pcg2d(sx, sy);
+    uint32_t seed = sx + sy;
+    const float r1 = bpt_rand(seed);
+    const float r2 = bpt_rand(seed);
+    const float scx = (float)px + r1, scy = (float)py + r2;            // :51
+    const float ux = scx / (float)p.width, uy = scy / (float)p.height; // :52
+    const float dx = ux * 2.0f - 1.0f, dy = uy * 2.0f - 1.0f;          // :53
+    const V3 o{p.cam_origin[0], p.cam_origin[1], p.cam_origin[2]};
+    const V3 target{dx + p.cam_target[0], dy + p.cam_target[1], p.cam_target[2]};
+    const V3 d = normalize(target - o);                                // :57
+    q.rays[2 * (size_t)i] = make_float4(o.x, o.y, o.z, p.tmin);
+    q.rays[2 * (size_t)i + 1] = make_float4(d.x, d.y, d.z, p.tmax);
+    q.state[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
+    q.pixel[i] = i;
+}
+
+// ---------------------------------------------------------------- K11
+__device__ __forceinline__ V3 load_vertex(const SceneView& s, uint32_t prim, int c, const float* m) {
+    const float* v = s.verts + 3 * (size_t)__ldg(&s.indices[3 * (size_t)prim + c]);
+    const float x = __ldg(v), y = __ldg(v + 1), z = __ldg(v + 2);
+    if (!m) return {x, y, z};
+    return {m[0] * x + m[1] * y + m[2] * z + m[3], m[4] * x + m[5] * y + m[6] * z + m[7],
+            m[8] * x + m[9] * y + m[10] * z + m[11]};
+}
+
+__global__ void k_shade(FrameParams p, SceneView s, uint32_t depth, PathQueue in, const uint4* __restrict__ hits,
+                        PathQueue out, uint32_t* counts, float4* frame_sum) {
+    const uint32_t n = counts[depth];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    bool alive = false;
+    float4 nro, nrd, nst;
+    uint32_t pix = 0;
+    if (i < n) {
+        const uint4 h = hits[i];
+        const float4 st = in.state[i];
+        pix = in.pixel[i];
+        V3 w{st.x, st.y, st.z};
+        uint32_t seed = __float_as_uint(st.w);
+        if (h.w == BPT_MISS) {
+            // miss.rmiss:10-11 then raygen.rgen:76 and the break at :81
+            const V3 c = w * V3{p.sky[0], p.sky[1], p.sky[2]};
+            float4 acc = frame_sum[pix];
+            acc.x += c.x; acc.y += c.y; acc.z += c.z;
+            frame_sum[pix] = acc;
+        } else {
+            const uint32_t inst = s.xforms ? h.w / s.ntris : 0u;
+            const uint32_t prim = s.xforms ? h.w - inst * s.ntris : h.w;
+            const float* m = s.xforms ? s.xforms + 12 * (size_t)inst : nullptr;
+            const V3 v0 = load_vertex(s, prim, 0, m), v1 = load_vertex(s, prim, 1, m), v2 = load_vertex(s, prim, 2, m);
+            const float u = __uint_as_float(h.y), v = __uint_as_float(h.z);
+            const float b0 = 1.0f - u - v;                           // closesthit.rchit:56
+            const V3 pos = v0 * b0 + v1 * u + v2 * v;                // :57
+            const V3 nrm = -normalize(cross(v1 - v0, v2 - v0));      // :58, :43-48
+            const float* f = s.faces + 6 * (size_t)prim;
+            const V3 kd{__ldg(f), __ldg(f + 1), __ldg(f + 2)}, ke{__ldg(f + 3), __ldg(f + 4), __ldg(f + 5)};
+            if (ke.x != 0.0f || ke.y != 0.0f || ke.z != 0.0f) {      // raygen.rgen:76 (adding 0 is exact)
+                const V3 c = w * ke;
+                float4 acc = frame_sum[pix];
+                acc.x += c.x; acc.y += c.y; acc.z += c.z;
+                frame_sum[pix] = acc;
+            }
+            if (depth + 1u < p.max_depth) {                          // the next segment will be traced
+                const V3 brdf = kd / kPi;                            // closesthit.rchit:61
+                const float r1 = bpt_rand(seed);
+                const float r2 = bpt_rand(seed);                     // raygen.rgen:78
+                V3 T, B;                                             // :14-21
+                if (fabsf(nrm.x) > fabsf(nrm.y)) T = V3{nrm.z, 0.0f, -nrm.x} / sqrtf(nrm.x * nrm.x + nrm.z * nrm.z);
+                else T = V3{0.0f, -nrm.z, nrm.y} / sqrtf(nrm.y * nrm.y + nrm.z * nrm.z);
+                B = cross(nrm, T);
+                V3 l;
+                if (p.sampler == BPT_SAMPLER_COSINE) {
+                    const float sr = sqrtf(r1);
+                    l = V3{cosf(kTwoPi * r2) * sr, sinf(kTwoPi * r2) * sr, sqrtf(1.0f - r1)};
+                } else {                                             // :23-30 uniform hemisphere
+                    const float sr = sqrtf(1.0f - r1 * r1);
+                    l = V3{cosf(kTwoPi * r2) * sr, sinf(kTwoPi * r2) * sr, r1};
+                }
+                const V3 d = l.x * T + l.y * B + l.z * nrm;          // :38
+                if (p.sampler == BPT_SAMPLER_COSINE) w = w * (brdf * kPi);
+                else w = w * (brdf * dot(d, nrm) / kPdf);            // :79-80
+                nro = make_float4(pos.x, pos.y, pos.z, p.tmin);
+                nrd = make_float4(d.x, d.y, d.z, p.tmax);
+                nst = make_float4(w.x, w.y, w.z, __uint_as_float(seed));
+                alive = true;
+            }
+        }
+    }
+    // warp-ballot compaction of the surviving paths into the next queue
+    const unsigned live = __ballot_sync(FULL, alive);
+    if (live) {
+        uint32_t base = 0;
+        if (lane == (unsigned)(__ffs(live) - 1)) base = atomicAdd(&counts[depth + 1], (uint32_t)__popc(live));
+        base = __shfl_sync(FULL, base, __ffs(live) - 1);
+        if (alive) {
+            const uint32_t j = base + __popc(live & ((1u << lane) - 1u));
+            out.rays[2 * (size_t)j] = nro;
+            out.rays[2 * (size_t)j + 1] = nrd;
+            out.state[j] = nst;
+            out.pixel[j] = pix;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- K12
+__device__ __forceinline__ float unorm8_roundtrip(float x) {
+    float c = fminf(fmaxf(x, 0.0f), 1.0f);  // NaN -> 0 (fmaxf drops the NaN)
+    return rintf(c * 255.0f) / 255.0f;
+}
+__global__ void k_accumulate(FrameParams p, float4* __restrict__ frame_sum, float4* __restrict__ image) {
+    const uint32_t rows = p.tile_rows ? p.tile_rows : p.height;
+    const uint32_t npix = rows * p.width;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    float4 c = frame_sum[i];
+    frame_sum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float spp = (float)p.spp_per_frame;
+    c.x = c.x / spp; c.y = c.y / spp; c.z = c.z / spp;               // raygen.rgen:86
+    float4* dst = image + (size_t)p.tile_y0 * p.width + i;
+    const float4 old = *dst;                                         // :88
+    const float fr = (float)p.frame, fr1 = (float)(p.frame + 1);
+    float4 nw;                                                       // :89
+    nw.x = (c.x + old.x * fr) / fr1;
+    nw.y = (c.y + old.y * fr) / fr1;
+    nw.z = (c.z + old.z * fr) / fr1;
+    nw.w = (1.0f + old.w * fr) / fr1;
+    if (p.accum_mode == BPT_ACCUM_RGBA8) {
+        nw.x = unorm8_roundtrip(nw.x); nw.y = unorm8_roundtrip(nw.y);
+        nw.z = unorm8_roundtrip(nw.z); nw.w = unorm8_roundtrip(nw.w);
+    }
+    *dst = nw;                                                       // :90
+}
+
+__global__ void k_image_to_bgra8(const float4* __restrict__ image, uint8_t* __restrict__ bgra, size_t npix) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const float4 c = image[i];
+    auto q = [](float x) { return (uint8_t)rintf(fminf(fmaxf(x, 0.0f), 1.0f) * 255.0f); };
+    reinterpret_cast<uchar4*>(bgra)[i] = make_uchar4(q(c.z), q(c.y), q(c.x), q(c.w));  // B8G8R8A8 (main.cpp:483)
+}
+
+// ---------------------------------------------------------------- synthetic soup
+// value j of triangle i = rand-conversion of pcg(seed + (16 i + j) * 0x9E3779B9); one mul and one
+// add per value, no FMA (this file is built with --fmad=false) -> bit-identical to the host definition the tests hold.
+__global__ void k_soup(uint32_t ntris, uint32_t seed, float scale, float* __restrict__ verts,
+                       uint32_t* __restrict__ idx, float* __restrict__ faces) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntris) return;
+    float f[15];
+#pragma unroll
+    for (uint32_t j = 0; j < 15; ++j) {
+        uint32_t st = seed + (16u * i + j) * 0x9E3779B9u;
+        f[j] = __uint2float_rn(bpt_pcg(st)) * 2.3283064365386963e-10f;
+    }
+    const float c[3] = {f[0] * 2.0f - 1.0f, f[1] * 2.0f - 2.0f, f[2] * 2.0f - 1.0f};
+#pragma unroll
+    for (int v = 0; v < 3; ++v)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float off = (f[3 + 3 * v + a] * 2.0f - 1.0f) * scale;
+            verts[9 * (size_t)i + 3 * v + a] = c[a] + off;
+        }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) faces[6 * (size_t)i + a] = f[12 + a] * 0.8f + 0.1f;
+    const bool em = (i % 128u) == 0u;
+    faces[6 * (size_t)i + 3] = em ? 17.0f : 0.0f;
+    faces[6 * (size_t)i + 4] = em ? 12.0f : 0.0f;
+    faces[6 * (size_t)i + 5] = em ? 4.0f : 0.0f;
+    idx[3 * (size_t)i] = 3 * i; idx[3 * (size_t)i + 1] = 3 * i + 1; idx[3 * (size_t)i + 2] = 3 * i + 2;
+}
+
+inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+}  // namespace
+
+void launch_generate(const FrameParams& p, uint32_t sample_in_frame, PathQueue q, uint32_t* counts, uint32_t* fetch,
+                     uint32_t ncounters, cudaStream_t st) {
+    const uint32_t rows = p.tile_rows ? p.tile_rows : p.height;
+    const uint64_t threads = std::max<uint64_t>((uint64_t)rows * p.width, ncounters);  // the first threads also reset the counters
+    k_generate<<<grid_for(threads), kBlock, 0, st>>>(p, sample_in_frame, q, counts, fetch, ncounters);
+}
+void launch_shade(const FrameParams& p, const SceneView& s, uint32_t depth, PathQueue in, const uint4* hits,
+                  PathQueue out, uint32_t* counts, float4* frame_sum, uint32_t max_paths, cudaStream_t st) {
+    k_shade<<<grid_for(max_paths), kBlock, 0, st>>>(p, s, depth, in, hits, out, counts, frame_sum);
+}
+void launch_accumulate(const FrameParams& p, float4* frame_sum, float4* image, cudaStream_t st) {
+    const uint32_t rows = p.tile_rows ? p.tile_rows : p.height;
+    k_accumulate<<<grid_for((uint64_t)rows * p.width), kBlock, 0, st>>>(p, frame_sum, image);
+}
+void launch_soup(uint32_t ntris, uint32_t seed, float scale, float* verts, uint32_t* idx, float* faces, cudaStream_t st) {
+    k_soup<<<grid_for(ntris), kBlock, 0, st>>>(ntris, seed, scale, verts, idx, faces);
+}
+void launch_image_to_bgra8(const float4* image, uint8_t* bgra, size_t npix, cudaStream_t st) {
+    k_image_to_bgra8<<<grid_for(npix), kBlock, 0, st>>>(image, bgra, npix);
+}

@@ -1,0 +1,39 @@
+// shade.cuh — launch interface of the wavefront stages around the traversal kernel (shade.cu).
+#pragma once
+#include "common.cuh"
+
+// Device-resident parameters of the running frame (the reference's push constant + the constants
+// it hard-codes in the shaders).
+struct FrameParams {
+    uint32_t width, height, spp_per_frame, max_depth;
+    int32_t frame;
+    uint32_t tile_y0, tile_rows;
+    float cam_origin[3], cam_target[3], sky[3];
+    float tmin, tmax;
+    uint32_t accum_mode, sampler;
+};
+
+struct SceneView {
+    const float* verts;       // xyz triples (Vertex, main.cpp:19-21)
+    const uint32_t* indices;  // 3 per triangle
+    const float* faces;       // Kd.rgb Ke.rgb per triangle (Face, main.cpp:23-26)
+    const float* xforms;      // 3x4 row-major per instance, or null (single identity instance)
+    uint32_t ntris;
+};
+
+// One wavefront queue (SoA): ray 2 x float4, state float4 {w.rgb, seed bits}, pixel u32.
+struct PathQueue {
+    float4* rays;
+    float4* state;
+    uint32_t* pixel;
+};
+
+void launch_generate(const FrameParams& p, uint32_t sample_in_frame, PathQueue q, uint32_t* counts, uint32_t* fetch,
+                     uint32_t ncounters, cudaStream_t st);
+// depth: index of the bounce being shaded; counts[depth] paths in `in`, survivors appended to `out`
+// and counted in counts[depth+1].
+void launch_shade(const FrameParams& p, const SceneView& s, uint32_t depth, PathQueue in, const uint4* hits,
+                  PathQueue out, uint32_t* counts, float4* frame_sum, uint32_t max_paths, cudaStream_t st);
+void launch_accumulate(const FrameParams& p, float4* frame_sum, float4* image, cudaStream_t st);
+void launch_soup(uint32_t ntris, uint32_t seed, float scale, float* verts, uint32_t* idx, float* faces, cudaStream_t st);
+void launch_image_to_bgra8(const float4* image, uint8_t* bgra, size_t npix, cudaStream_t st);

@@ -1,0 +1,373 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes over libbpt.so), against the oracle.
+
+Run on the B200 box: python -m pytest tests -m gpu. Tolerances are stated per test; integer work is bit-exact.
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+bpt = importlib.import_module("single-file-vulkan-pathtracing_b200")
+
+
+@pytest.fixture(scope="module")
+def pt_cornell(cornell):
+    pt = bpt.PathTracer(0)
+    pt.upload_mesh(*cornell)
+    pt.build_accel()
+    yield pt
+    pt.close()
+
+
+def random_rays(n, seed, lo=(-1.2, -2.2, -1.2), hi=(1.2, 0.2, 1.2)):
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return np.concatenate([o, np.full((n, 1), 1e-3, np.float32), d, np.full((n, 1), 1e4, np.float32)], 1)
+
+
+def compare_hits(gpu, ref, tris_world, max_mismatch=2e-4, tol=2e-4):
+    """prim ids must agree except for a tiny fraction of edge-grazing rays; where they agree t,u,v agree to `tol`
+    (relative for t). Mismatches must at least agree on the hit distance (coincident/adjacent geometry)."""
+    same = gpu["prim"] == ref["prim"]
+    frac = 1.0 - same.mean()
+    assert frac <= max_mismatch, f"{(~same).sum()} of {len(ref)} rays disagree on the primitive"
+    hit = same & (ref["prim"] != O.MISS)
+    np.testing.assert_allclose(gpu["t"][hit], ref["t"][hit], rtol=tol, atol=tol)
+    np.testing.assert_allclose(gpu["u"][hit], ref["u"][hit], atol=tol)
+    np.testing.assert_allclose(gpu["v"][hit], ref["v"][hit], atol=tol)
+    return frac
+
+
+# ------------------------------------------------------------------------------------------ K9
+def test_generate_rays_bit_exact(pt_cornell):
+    for (w, h, spp, frame, s) in ((256, 256, 1, 0, 0), (64, 48, 32, 3, 17), (1024, 8, 4, 1, 2)):
+        p = bpt.default_params(w, h, spp, 8, frame)
+        rays, seeds = pt_cornell.generate_rays(p, s)
+        orays, oseeds = O.generate_rays(O.default_params(w, h, spp, 8, frame), s)
+        assert np.array_equal(seeds, oseeds)
+        assert np.array_equal(rays.view(np.uint32), orays.view(np.uint32)), np.abs(rays - orays).max()
+
+
+def test_generate_rays_tile(pt_cornell):
+    p = bpt.default_params(128, 128, 2, 8, 0, tile_y0=32, tile_rows=16)
+    rays, seeds = pt_cornell.generate_rays(p, 1)
+    orays, oseeds = O.generate_rays(O.default_params(128, 128, 2, 8, 0, tile_y0=32, tile_rows=16), 1)
+    assert np.array_equal(seeds, oseeds) and np.array_equal(rays, orays)
+
+
+# ------------------------------------------------------------------------------------------ K1-K7
+def test_build_invariants_cornell(pt_cornell, cornell):
+    check_build_invariants(pt_cornell, cornell[0], cornell[1])
+
+
+def check_build_invariants(pt, verts, idx):
+    info = pt.accel_info()
+    n = info.num_tris
+    tri = verts[idx].reshape(n, 3, 3)
+    lo, hi = tri.min(1), tri.max(1)
+    keys = pt.download_morton()
+    # K2/K3: sorted, unique, low word is a permutation of the primitives
+    assert np.all(keys[1:] > keys[:-1])
+    prim_sorted = (keys & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    assert np.array_equal(np.sort(prim_sorted), np.arange(n, dtype=np.uint32))
+    # K2: morton codes match the oracle's definition on the normalised AABB centre
+    slo, shi = lo.min(0), hi.max(0)
+    cen = (np.float32(0.5) * (lo + hi)).astype(np.float32)
+    ext = (shi - slo).astype(np.float32)
+    nrm = np.where(ext > 0, (cen - slo) / np.where(ext > 0, ext, 1), 0).astype(np.float32)
+    L = O.lib()
+    sample = np.random.default_rng(0).choice(n, min(n, 2000), replace=False)
+    code_of = {int(k & np.uint64(0xFFFFFFFF)): int(k >> np.uint64(32)) for k in keys}
+    for i in sample:
+        assert code_of[int(i)] == L.orc_morton30(float(nrm[i, 0]), float(nrm[i, 1]), float(nrm[i, 2]))
+    # K4/K5: binary hierarchy — every leaf reachable exactly once, child boxes inside parents
+    left, right, aabbs = pt.download_lbvh()
+    if n > 1:
+        seen = np.zeros(2 * n - 1, np.int32)
+        stack = [0]
+        while stack:
+            b = stack.pop()
+            seen[b] += 1
+            if b < n - 1:
+                for c in (int(left[b]), int(right[b])):
+                    assert np.all(aabbs[c, :3] >= aabbs[b, :3]) and np.all(aabbs[c, 3:] <= aabbs[b, 3:])
+                    stack.append(c)
+        assert np.all(seen == 1)
+        leaf_boxes = aabbs[n - 1:]
+        np.testing.assert_array_equal(leaf_boxes[:, :3], lo[prim_sorted])
+        np.testing.assert_array_equal(leaf_boxes[:, 3:], hi[prim_sorted])
+        np.testing.assert_array_equal(aabbs[0, :3], slo)
+        np.testing.assert_array_equal(aabbs[0, 3:], shi)
+    # K6: BVH8 — every triangle in exactly one leaf slot; quantised child boxes contain their triangles
+    nodes, tri_index, woop = pt.download_accel()
+    assert np.array_equal(np.sort(tri_index), np.arange(n, dtype=np.uint32))
+    visited_nodes = np.zeros(len(nodes), np.int32)
+    tri_seen = np.zeros(n, np.int32)
+    stack = [(0, None, None)]
+    depth = 0
+    level = [(0, None, None)]
+    while level:
+        depth += 1
+        nxt = []
+        for (ni, plo, phi) in level:
+            nd = nodes[ni]
+            visited_nodes[ni] += 1
+            scale = np.ldexp(np.float64(1.0), nd["e"].astype(np.int32) - 127)
+            p = nd["p"].astype(np.float64)
+            rank = 0
+            for s in range(8):
+                m = int(nd["meta"][s])
+                if m == 0:
+                    continue
+                qlo = np.array([nd["qlox"][s], nd["qloy"][s], nd["qloz"][s]], np.float64)
+                qhi = np.array([nd["qhix"][s], nd["qhiy"][s], nd["qhiz"][s]], np.float64)
+                blo, bhi = p + qlo * scale, p + qhi * scale
+                if plo is not None:  # child box inside the parent's box for it (up to the padding)
+                    assert np.all(blo >= plo - 1e-4) and np.all(bhi <= phi + 1e-4)
+                if (m & 0x1F) >= 24 and (m >> 5) == 1:
+                    assert (nd["imask"] >> s) & 1 and (m & 0x1F) == 24 + s
+                    nxt.append((int(nd["child_base"]) + rank, blo, bhi))
+                    rank += 1
+                else:
+                    assert not (nd["imask"] >> s) & 1
+                    cnt = {1: 1, 3: 2, 7: 3}[m >> 5]
+                    off = m & 0x1F
+                    for j in range(cnt):
+                        slot = int(nd["tri_base"]) + off + j
+                        prim = tri_index[slot]
+                        tri_seen[prim] += 1
+                        assert np.all(blo <= lo[prim]) and np.all(bhi >= hi[prim])  # quantised box contains the triangle
+            assert rank == bin(int(nd["imask"])).count("1")
+        level = nxt
+    assert np.all(visited_nodes == 1) and np.all(tri_seen == 1)
+    assert depth == info.max_depth8
+    # K7: Woop rows map v0,v1,v2 to (0,0,0),(1,0,0),(0,1,0)
+    t = tri[tri_index].astype(np.float64)
+    area = np.linalg.norm(np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0]), axis=1)
+    ok = area > 1e-12
+    M, c = woop[:, :, :3].astype(np.float64), woop[:, :, 3].astype(np.float64)
+    for k, want in enumerate(([0, 0, 0], [1, 0, 0], [0, 1, 0])):
+        got = np.einsum("nij,nj->ni", M, t[:, k]) + c
+        np.testing.assert_allclose(got[ok], np.tile(want, (ok.sum(), 1)), atol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------ K10
+def test_trace_primary_rays_cornell(pt_cornell, cornell_oracle, cornell):
+    rays, _ = O.generate_rays(O.default_params(256, 256, 1, 2), 0)
+    gpu = pt_cornell.trace_rays(rays)
+    ref = cornell_oracle.intersect(rays, 64, brute=True)
+    compare_hits(gpu, ref, None)
+    # KAT-2 named pixels
+    assert gpu[128 * 256 + 128]["prim"] == 30 and gpu[200 * 256 + 200]["prim"] == 6
+    assert gpu[0]["prim"] == O.MISS
+
+
+def test_trace_random_rays_cornell(pt_cornell, cornell_oracle):
+    rays = random_rays(200_000, 3)
+    gpu = pt_cornell.trace_rays(rays)
+    ref = cornell_oracle.intersect(rays, 64, brute=True)
+    compare_hits(gpu, ref, None)
+
+
+def test_trace_ragged_counts(pt_cornell, cornell_oracle):
+    """Ray counts that are not multiples of the warp / CTA size, including 1."""
+    for n in (1, 31, 33, 1023, 1025, 4097):
+        rays = random_rays(n, 100 + n)
+        gpu = pt_cornell.trace_rays(rays)
+        ref = cornell_oracle.intersect(rays, 64, brute=True)
+        assert (gpu["prim"] != ref["prim"]).sum() <= 1
+    assert len(pt_cornell.trace_rays(np.zeros((0, 8), np.float32))) == 0
+
+
+def test_trace_axis_aligned_and_degenerate_rays(pt_cornell, cornell_oracle):
+    """Directions with exact zeros (1/d = inf guarded) and rays starting on surfaces."""
+    o = np.array([[0, -1, 5], [0, -1, 0.5], [0.3, -0.5, 0.2], [0, -1, 5]], np.float32)
+    d = np.array([[0, 0, -1], [0, 1, 0], [1, 0, 0], [0, -0.0, -1]], np.float32)
+    rays = np.concatenate([o, np.full((4, 1), 1e-3, np.float32), d, np.full((4, 1), 1e4, np.float32)], 1)
+    gpu = pt_cornell.trace_rays(rays)
+    ref = cornell_oracle.intersect(rays, 64, brute=True)
+    assert np.array_equal(gpu["prim"], ref["prim"])
+    np.testing.assert_allclose(gpu["t"], ref["t"], rtol=1e-5)
+
+
+@pytest.fixture(scope="module")
+def soup20k():
+    verts, idx, faces = O.soup(20_000, 0x5EED0001)
+    return verts, idx, faces, O.Scene(verts, idx, faces)
+
+
+def test_soup_generator_bit_exact(soup20k):
+    verts, idx, faces, _ = soup20k
+    with bpt.PathTracer(0) as pt:
+        pt.upload_soup(20_000, 0x5EED0001)
+        gv, gi, gf = pt.download_mesh(20_000)
+    assert np.array_equal(gi, idx)
+    assert np.array_equal(gv.view(np.uint32), verts.view(np.uint32))
+    assert np.array_equal(gf.view(np.uint32), faces.view(np.uint32))
+
+
+def test_soup_build_and_trace(soup20k):
+    verts, idx, faces, scene = soup20k
+    with bpt.PathTracer(0) as pt:
+        pt.upload_soup(20_000, 0x5EED0001)
+        pt.build_accel()
+        check_build_invariants(pt, verts, idx)
+        rays = random_rays(100_000, 5)
+        gpu = pt.trace_rays(rays)
+        ref = scene.intersect(rays, 64)
+        compare_hits(gpu, ref, None, max_mismatch=5e-4)
+        # staging on/off must not change a single hit
+        pt.set_option(bpt.OPT_SMEM_TOP_NODES, 0)
+        gpu0 = pt.trace_rays(rays)
+        assert np.array_equal(gpu0, gpu)
+        pt.set_option(bpt.OPT_SMEM_TOP_NODES, 2000)
+        gpu1 = pt.trace_rays(rays)
+        assert np.array_equal(gpu1, gpu)
+        # instrumented kernel: same hits, plausible counters
+        pt.set_option(bpt.OPT_COUNT_TRAVERSAL, 1)
+        pt.reset_stats()
+        gpu2 = pt.trace_rays(rays)
+        st = pt.stats()
+        assert np.array_equal(gpu2, gpu)
+        assert st.rays_traced == len(rays) and st.nodes_visited >= len(rays) and st.tris_tested > 0
+
+
+def test_tiny_meshes():
+    """1, 2, 3, 4, 9 triangles (root-only trees, single leaf) incl. a degenerate triangle."""
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 3, 4, 9):
+        verts = rng.uniform(-1, 1, (3 * n, 3)).astype(np.float32)
+        if n >= 3:
+            verts[3:6] = verts[3]  # zero-area triangle
+        idx = np.arange(3 * n, dtype=np.uint32)
+        faces = np.tile(np.array([0.5, 0.5, 0.5, 0, 0, 0], np.float32), (n, 1))
+        scene = O.Scene(verts, idx, faces)
+        with bpt.PathTracer(0) as pt:
+            pt.upload_mesh(verts, idx, faces)
+            pt.build_accel()
+            rays = random_rays(20_000, n, lo=(-2, -2, -2), hi=(2, 2, 2))
+            gpu = pt.trace_rays(rays)
+            ref = scene.intersect(rays, 64, brute=True)
+            compare_hits(gpu, ref, None, max_mismatch=5e-4)
+
+
+# ------------------------------------------------------------------------------------------ whole path
+def test_cfg1_image_parity(pt_cornell, cornell_oracle):
+    """BASELINE config 1: Cornell 256x256, 1 spp, depth 2. rel-L2 <= 1e-3 (north_star tolerance)."""
+    pt_cornell.clear_image()
+    pt_cornell.reset_stats()
+    img = pt_cornell.render(bpt.default_params(256, 256, 1, 2))
+    ref, rays = cornell_oracle.render(O.default_params(256, 256, 1, 2), 32)
+    assert pt_cornell.stats().rays_traced == rays
+    err = O.rel_l2(img, ref)
+    assert err <= 1e-3, err
+    assert np.array_equal(img[0, 0], np.array([0.7, 0.6, 0.5, 1.0], np.float32))
+    # strict per-pixel view of the same thing: all but a handful of pixels agree to 1e-5
+    bad = np.abs(img - ref).max(-1) > 1e-5 * (1 + np.abs(ref).max(-1))
+    assert bad.mean() < 1e-3, bad.sum()
+
+
+def test_reference_defaults_crop_parity(pt_cornell, cornell_oracle):
+    """The reference's own constants (1024x1024, 32 spp, depth 8) on a 24-row tile; 2 frames."""
+    pt_cornell.clear_image()
+    ref = np.zeros((1024, 1024, 4), np.float32)
+    for f in range(2):
+        pt_cornell.trace(bpt.default_params(1024, 1024, 32, 8, f, tile_y0=500, tile_rows=24))
+        cornell_oracle.render(O.default_params(1024, 1024, 32, 8, f, tile_y0=500, tile_rows=24), 32, image=ref)
+    img = pt_cornell.read_image(1024, 1024)
+    assert np.all(img[:500] == 0) and np.all(img[524:] == 0)
+    err = O.rel_l2(img[500:524], ref[500:524])
+    assert err <= 1e-3, err
+
+
+def test_cfg2_downscaled_parity(pt_cornell, cornell_oracle):
+    """Config 2's depth/spp structure at 128x128: 64 spp as 2 frames x 32, depth 8."""
+    pt_cornell.clear_image()
+    ref = np.zeros((128, 128, 4), np.float32)
+    for f in range(2):
+        pt_cornell.trace(bpt.default_params(128, 128, 32, 8, f))
+        cornell_oracle.render(O.default_params(128, 128, 32, 8, f), 32, image=ref)
+    img = pt_cornell.read_image(128, 128)
+    err = O.rel_l2(img, ref)
+    assert err <= 1e-3, err
+
+
+def test_frame_split_and_tile_invariance_gpu(pt_cornell):
+    """T3 on the device: tiles reproduce the full image bit for bit; 4x8 spp == 1x32 spp to float order."""
+    pt_cornell.clear_image()
+    full = pt_cornell.render(bpt.default_params(96, 96, 8, 6))
+    pt_cornell.clear_image()
+    for y0 in range(0, 96, 32):
+        pt_cornell.trace(bpt.default_params(96, 96, 8, 6, tile_y0=y0, tile_rows=32))
+    tiled = pt_cornell.read_image(96, 96)
+    assert np.array_equal(full, tiled)
+    pt_cornell.clear_image()
+    one = pt_cornell.render(bpt.default_params(96, 96, 32, 6))
+    pt_cornell.clear_image()
+    four = pt_cornell.render(bpt.default_params(96, 96, 8, 6), frames=4)
+    assert O.rel_l2(four, one) < 1e-5
+
+
+def test_determinism(pt_cornell):
+    pt_cornell.clear_image()
+    a = pt_cornell.render(bpt.default_params(200, 120, 4, 8))
+    pt_cornell.clear_image()
+    b = pt_cornell.render(bpt.default_params(200, 120, 4, 8))
+    assert np.array_equal(a, b)
+
+
+def test_rgba8_mode(pt_cornell, cornell_oracle):
+    """T2: unorm8 running mean, two frames, against the oracle's emulation; BGRA8 readback order."""
+    pt_cornell.clear_image()
+    ref = np.zeros((64, 64, 4), np.float32)
+    for f in range(2):
+        pt_cornell.trace(bpt.default_params(64, 64, 4, 4, f, accum_mode=bpt.ACCUM_RGBA8))
+        cornell_oracle.render(O.default_params(64, 64, 4, 4, f, accum_mode=1), 32, image=ref)
+    img = pt_cornell.read_image(64, 64)
+    q = np.rint(img * 255).astype(np.int32)
+    qr = np.rint(ref * 255).astype(np.int32)
+    assert np.abs(q - qr).max() <= 1 and (q != qr).mean() < 2e-3
+    bgra = pt_cornell.read_image_bgra8(64, 64)
+    assert np.array_equal(bgra[..., 2], q[..., 0]) and np.array_equal(bgra[..., 0], q[..., 2])
+    assert np.all(bgra[..., 3] == 255)
+
+
+def test_soup_image_parity(soup20k):
+    verts, idx, faces, scene = soup20k
+    with bpt.PathTracer(0) as pt:
+        pt.upload_mesh(verts, idx, faces)
+        pt.build_accel()
+        img = pt.render(bpt.default_params(128, 128, 4, 8))
+        rays_gpu = pt.stats().rays_traced
+    ref, rays = scene.render(O.default_params(128, 128, 4, 8), 32)
+    err = O.rel_l2(img, ref)
+    assert err <= 1e-3, err
+    assert abs(rays_gpu - rays) <= 1e-4 * rays
+
+
+def test_error_paths(cornell):
+    verts, idx, faces = cornell
+    with bpt.PathTracer(0) as pt:
+        with pytest.raises(bpt.BptError):
+            pt.trace(bpt.default_params(8, 8, 1, 1))            # trace before build
+        with pytest.raises(bpt.BptError):
+            pt.build_accel()                                     # build before upload
+        with pytest.raises(bpt.BptError):
+            pt.upload_mesh(verts, idx[:-1], faces)               # ragged index buffer
+        bad = idx.copy(); bad[5] = 10_000
+        with pytest.raises(bpt.BptError):
+            pt.upload_mesh(verts, bad, faces)                    # index out of range
+        pt.upload_mesh(verts, idx, faces)
+        pt.build_accel()
+        for kw in (dict(spp=0), dict(depth=0), dict(width=0), dict(tile_y0=9), dict(frame=-1)):
+            args = dict(width=8, height=8, spp=1, depth=1)
+            args.update(kw)
+            with pytest.raises(bpt.BptError):
+                pt.trace(bpt.default_params(**args))
+    with pytest.raises(bpt.BptError):
+        bpt.PathTracer(99)
