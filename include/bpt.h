@@ -60,8 +60,8 @@ typedef struct bpt_params {
     uint32_t spp_per_frame;  /* maxSamples, raygen.rgen:43 (32)                        */
     uint32_t max_depth;      /* segment bound, raygen.rgen:62 (8)                      */
     int32_t  frame;          /* push constant `frame`, main.cpp:658                    */
-    uint32_t tile_y0;        /* first image row this context renders (multi-GPU tile)  */
-    uint32_t tile_rows;      /* number of rows; 0 = all rows                           */
+    uint32_t tile_y0;        /* first image row this context renders (contiguous tile) */
+    uint32_t tile_rows;      /* number of rows; 0 = all rows from tile_y0              */
     float    cam_origin[3];  /* raygen.rgen:55 (0,-1,5)                                */
     float    cam_target[3];  /* target = (d.x + t[0], d.y + t[1], t[2]); raygen.rgen:56 (0,-1,2) */
     float    sky[3];         /* miss.rmiss:10 (0.7,0.6,0.5)                            */
@@ -69,6 +69,16 @@ typedef struct bpt_params {
     float    tmax;           /* raygen.rgen:73 (10000)                                 */
     uint32_t accum_mode;     /* BPT_ACCUM_*                                            */
     uint32_t sampler;        /* BPT_SAMPLER_*                                          */
+    /* Interleaved multi-GPU tiling (tile_block != 0; tile_y0/tile_rows must then be 0): the
+     * image is cut into blocks of tile_block rows, dealt round-robin to tile_nranks contexts;
+     * this context renders the blocks b with b % tile_nranks == tile_rank, so sky rows and
+     * geometry rows spread evenly over the GPUs. height % (tile_block*tile_nranks) == 0.
+     * Its rows are stored contiguously ("rank-major") at row tile_rank*height/tile_nranks of
+     * the image buffer, which is what lets one in-place all-gather assemble the image;
+     * bpt_read_image* return ordinary row-major images in every mode. */
+    uint32_t tile_block;
+    uint32_t tile_nranks;
+    uint32_t tile_rank;
 } bpt_params;
 
 /* Counters of the last bpt_trace / since bpt_reset_stats. */
@@ -197,7 +207,9 @@ int bpt_nccl_unique_id(uint8_t id[BPT_NCCL_UNIQUE_ID_BYTES]);
 int bpt_nccl_init(bpt_context* ctx, const uint8_t id[BPT_NCCL_UNIQUE_ID_BYTES],
                   int rank, int nranks);
 /* In-place all-gather of the row tiles into every rank's full float4 image. Tiles must be
- * the equal contiguous split bpt_tile_rows() returns (height % nranks == 0). */
+ * either the equal contiguous split bpt_tile_rows() returns (height % nranks == 0) or the
+ * interleaved split of bpt_params.tile_block with tile_nranks == nranks, tile_rank == rank
+ * (the tiling of the last bpt_trace decides). */
 int bpt_allgather_image(bpt_context* ctx, uint32_t width, uint32_t height);
 /* contiguous row split used by every caller: rank r gets rows [y0, y0+rows). */
 void bpt_tile_rows(uint32_t height, int rank, int nranks, uint32_t* y0, uint32_t* rows);

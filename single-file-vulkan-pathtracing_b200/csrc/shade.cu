@@ -35,15 +35,14 @@ constexpr float kTwoPi = 6.2831855f, kPi = 3.1415927f, kPdf = 0.15915494f;
 // ---------------------------------------------------------------- K9
 __global__ void k_generate(FrameParams p, uint32_t sample_in_frame, PathQueue q, uint32_t* counts, uint32_t* fetch,
                            uint32_t ncounters) {
-    const uint32_t rows = p.tile_rows ? p.tile_rows : p.height;
-    const uint32_t npix = rows * p.width;
+    const uint32_t npix = tile_local_rows(p) * p.width;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < ncounters) {  // queue lengths and fetch counters of this sample pass
         counts[i] = i == 0 ? npix : 0u;
         fetch[i] = 0u;
     }
     if (i >= npix) return;
-    const uint32_t px = i % p.width, py = p.tile_y0 + i / p.width;
+    const uint32_t px = i % p.width, py = tile_global_row(p, i / p.width);
     const uint32_t k = sample_in_frame + p.spp_per_frame * (uint32_t)p.frame + 1u;  // raygen.rgen:47
     uint32_t sx = px * k, sy = py * k;
     bpt_pcg2d(sx, sy);
@@ -156,15 +155,14 @@ __device__ __forceinline__ float unorm8_roundtrip(float x) {
     return rintf(c * 255.0f) / 255.0f;
 }
 __global__ void k_accumulate(FrameParams p, float4* __restrict__ frame_sum, float4* __restrict__ image) {
-    const uint32_t rows = p.tile_rows ? p.tile_rows : p.height;
-    const uint32_t npix = rows * p.width;
+    const uint32_t npix = tile_local_rows(p) * p.width;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
     float4 c = frame_sum[i];
     frame_sum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float spp = (float)p.spp_per_frame;
     c.x = c.x / spp; c.y = c.y / spp; c.z = c.z / spp;               // raygen.rgen:86
-    float4* dst = image + (size_t)p.tile_y0 * p.width + i;
+    float4* dst = image + (size_t)tile_store_row(p, 0) * p.width + i;  // the tile's rows are contiguous in the buffer
     const float4 old = *dst;                                         // :88
     const float fr = (float)p.frame, fr1 = (float)(p.frame + 1);
     float4 nw;                                                       // :89
@@ -185,6 +183,15 @@ __global__ void k_image_to_bgra8(const float4* __restrict__ image, uint8_t* __re
     const float4 c = image[i];
     auto q = [](float x) { return (uint8_t)rintf(fminf(fmaxf(x, 0.0f), 1.0f) * 255.0f); };
     reinterpret_cast<uchar4*>(bgra)[i] = make_uchar4(q(c.z), q(c.y), q(c.x), q(c.w));  // B8G8R8A8 (main.cpp:483)
+}
+
+__global__ void k_deinterleave(const float4* __restrict__ src, float4* __restrict__ dst, uint32_t width, uint32_t height,
+                               uint32_t block, uint32_t nranks) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)width * height) return;
+    const uint32_t y = (uint32_t)(i / width), x = (uint32_t)(i % width);
+    const uint32_t b = y / block, rank = b % nranks, l = (b / nranks) * block + y % block;
+    dst[i] = src[((size_t)rank * (height / nranks) + l) * width + x];
 }
 
 // ---------------------------------------------------------------- synthetic soup
@@ -223,8 +230,7 @@ inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kBlock - 1) / kBlo
 
 void launch_generate(const FrameParams& p, uint32_t sample_in_frame, PathQueue q, uint32_t* counts, uint32_t* fetch,
                      uint32_t ncounters, cudaStream_t st) {
-    const uint32_t rows = p.tile_rows ? p.tile_rows : p.height;
-    const uint64_t threads = std::max<uint64_t>((uint64_t)rows * p.width, ncounters);  // the first threads also reset the counters
+    const uint64_t threads = std::max<uint64_t>((uint64_t)tile_local_rows(p) * p.width, ncounters);  // the first threads also reset the counters
     k_generate<<<grid_for(threads), kBlock, 0, st>>>(p, sample_in_frame, q, counts, fetch, ncounters);
 }
 void launch_shade(const FrameParams& p, const SceneView& s, uint32_t depth, PathQueue in, const uint4* hits,
@@ -232,11 +238,14 @@ void launch_shade(const FrameParams& p, const SceneView& s, uint32_t depth, Path
     k_shade<<<grid_for(max_paths), kBlock, 0, st>>>(p, s, depth, in, hits, out, counts, frame_sum);
 }
 void launch_accumulate(const FrameParams& p, float4* frame_sum, float4* image, cudaStream_t st) {
-    const uint32_t rows = p.tile_rows ? p.tile_rows : p.height;
-    k_accumulate<<<grid_for((uint64_t)rows * p.width), kBlock, 0, st>>>(p, frame_sum, image);
+    k_accumulate<<<grid_for((uint64_t)tile_local_rows(p) * p.width), kBlock, 0, st>>>(p, frame_sum, image);
 }
 void launch_soup(uint32_t ntris, uint32_t seed, float scale, float* verts, uint32_t* idx, float* faces, cudaStream_t st) {
     k_soup<<<grid_for(ntris), kBlock, 0, st>>>(ntris, seed, scale, verts, idx, faces);
+}
+void launch_deinterleave(const float4* rank_major, float4* row_major, uint32_t width, uint32_t height, uint32_t block,
+                         uint32_t nranks, cudaStream_t st) {
+    k_deinterleave<<<grid_for((uint64_t)width * height), kBlock, 0, st>>>(rank_major, row_major, width, height, block, nranks);
 }
 void launch_image_to_bgra8(const float4* image, uint8_t* bgra, size_t npix, cudaStream_t st) {
     k_image_to_bgra8<<<grid_for(npix), kBlock, 0, st>>>(image, bgra, npix);

@@ -11,7 +11,22 @@ struct FrameParams {
     float cam_origin[3], cam_target[3], sky[3];
     float tmin, tmax;
     uint32_t accum_mode, sampler;
+    uint32_t tile_block, tile_nranks, tile_rank;
 };
+
+// Row bookkeeping of a tile (bpt_params.tile_*): l is the tile-local row.
+__host__ __device__ __forceinline__ uint32_t tile_local_rows(const FrameParams& p) {
+    if (p.tile_block) return p.height / p.tile_nranks;
+    return p.tile_rows ? p.tile_rows : p.height - p.tile_y0;
+}
+__host__ __device__ __forceinline__ uint32_t tile_global_row(const FrameParams& p, uint32_t l) {  // image row (seeds, camera)
+    if (p.tile_block) return ((l / p.tile_block) * p.tile_nranks + p.tile_rank) * p.tile_block + l % p.tile_block;
+    return p.tile_y0 + l;
+}
+__host__ __device__ __forceinline__ uint32_t tile_store_row(const FrameParams& p, uint32_t l) {   // row of the image buffer
+    if (p.tile_block) return p.tile_rank * (p.height / p.tile_nranks) + l;
+    return p.tile_y0 + l;
+}
 
 struct SceneView {
     const float* verts;       // xyz triples (Vertex, main.cpp:19-21)
@@ -37,3 +52,6 @@ void launch_shade(const FrameParams& p, const SceneView& s, uint32_t depth, Path
 void launch_accumulate(const FrameParams& p, float4* frame_sum, float4* image, cudaStream_t st);
 void launch_soup(uint32_t ntris, uint32_t seed, float scale, float* verts, uint32_t* idx, float* faces, cudaStream_t st);
 void launch_image_to_bgra8(const float4* image, uint8_t* bgra, size_t npix, cudaStream_t st);
+// rank-major (interleaved tiling) image buffer -> row-major image
+void launch_deinterleave(const float4* rank_major, float4* row_major, uint32_t width, uint32_t height, uint32_t block,
+                         uint32_t nranks, cudaStream_t st);

@@ -52,6 +52,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// 0xff in every byte of x whose top bit is set. __byte_perm() masks each selector nibble to 3 bits, which drops
+// prmt's sign-replicate mode (selector bit 3), so the instruction is issued directly.
+__device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, 0x0, 0x0000BA98;" : "=r"(r) : "r"(x));
+    return r;
+}
+
 // byte j of w as float (exact): build 2^23 + byte with a byte permute, subtract 2^23
 template <int J>
 __device__ __forceinline__ float byte_f(uint32_t w) {
@@ -69,7 +77,7 @@ __device__ __forceinline__ uint32_t test_quad(uint32_t meta4, uint32_t xn, uint3
                                               uint32_t yf, uint32_t zf, float adx, float ady, float adz, float bx,
                                               float by, float bz, float tmin, float tbest, uint32_t octinv4) {
     const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-    const uint32_t inner_mask4 = __byte_perm(is_inner4 << 3, 0u, 0xba98u);  // 0xff where internal
+    const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);  // 0xff where internal
     const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
     const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
     uint32_t hit = 0;
