@@ -100,7 +100,18 @@ struct orc_params {
     float cam_origin[3], cam_target[3], sky[3];
     float tmin, tmax;
     uint32_t accum_mode, sampler;
+    uint32_t tile_block, tile_nranks, tile_rank;  // interleaved tiling (include/bpt.h)
 };
+
+// the image rows a tile covers, in tile-local order (contiguous rows, or round-robin row blocks)
+inline uint32_t tile_local_rows(const orc_params& p) {
+    if (p.tile_block) return p.height / p.tile_nranks;
+    return p.tile_rows ? p.tile_rows : p.height - p.tile_y0;
+}
+inline uint32_t tile_global_row(const orc_params& p, uint32_t l) {
+    if (p.tile_block) return ((l / p.tile_block) * p.tile_nranks + p.tile_rank) * p.tile_block + l % p.tile_block;
+    return p.tile_y0 + l;
+}
 
 constexpr uint32_t MISS = 0xffffffffu;
 
@@ -139,51 +150,81 @@ void build_bvh(Scene& s) {
     }
     s.order.resize(n);
     std::iota(s.order.begin(), s.order.end(), 0u);
-    s.nodes.clear();
-    s.nodes.reserve(size_t(n));
-    s.nodes.push_back(BNode{});
+    // every leaf holds >= 2 triangles (or is the root), so n + 1 nodes always suffice
+    s.nodes.assign(size_t(n) + 1, BNode{});
+    std::atomic<uint32_t> nnodes{1};
     struct Job { uint32_t node, first, count; };
-    std::vector<Job> stack{{0u, 0u, n}};
-    while (!stack.empty()) {
-        Job j = stack.back();
-        stack.pop_back();
+    // splits one job: fills its node, returns true and the two child jobs if it became internal
+    auto split = [&](const Job& j, Job& a, Job& b) {
         BNode nd{};
         float clo[3], chi[3];
-        for (int a = 0; a < 3; ++a) {
-            nd.lo[a] = clo[a] = std::numeric_limits<float>::max();
-            nd.hi[a] = chi[a] = -std::numeric_limits<float>::max();
+        for (int ax = 0; ax < 3; ++ax) {
+            nd.lo[ax] = clo[ax] = std::numeric_limits<float>::max();
+            nd.hi[ax] = chi[ax] = -std::numeric_limits<float>::max();
         }
         for (uint32_t k = j.first; k < j.first + j.count; ++k) {
             size_t p = s.order[k];
-            for (int a = 0; a < 3; ++a) {
-                nd.lo[a] = std::min(nd.lo[a], lo[3 * p + a]);
-                nd.hi[a] = std::max(nd.hi[a], hi[3 * p + a]);
-                clo[a] = std::min(clo[a], cen[3 * p + a]);
-                chi[a] = std::max(chi[a], cen[3 * p + a]);
+            for (int ax = 0; ax < 3; ++ax) {
+                nd.lo[ax] = std::min(nd.lo[ax], lo[3 * p + ax]);
+                nd.hi[ax] = std::max(nd.hi[ax], hi[3 * p + ax]);
+                clo[ax] = std::min(clo[ax], cen[3 * p + ax]);
+                chi[ax] = std::max(chi[ax], cen[3 * p + ax]);
             }
         }
         int axis = 0;
         float ext = chi[0] - clo[0];
-        for (int a = 1; a < 3; ++a)
-            if (chi[a] - clo[a] > ext) { ext = chi[a] - clo[a]; axis = a; }
+        for (int ax = 1; ax < 3; ++ax)
+            if (chi[ax] - clo[ax] > ext) { ext = chi[ax] - clo[ax]; axis = ax; }
         if (j.count <= 4 || !(ext > 0.0f)) {
             nd.left = j.first;
             nd.count = j.count;
             s.nodes[j.node] = nd;
-            continue;
+            return false;
         }
         uint32_t mid = j.count / 2;
         std::nth_element(s.order.begin() + j.first, s.order.begin() + j.first + mid,
-                         s.order.begin() + j.first + j.count,
-                         [&](uint32_t a, uint32_t b) { return cen[3 * size_t(a) + axis] < cen[3 * size_t(b) + axis]; });
-        nd.left = static_cast<uint32_t>(s.nodes.size());
+                         s.order.begin() + j.first + j.count, [&](uint32_t x, uint32_t y) {
+                             float cx = cen[3 * size_t(x) + axis], cy = cen[3 * size_t(y) + axis];
+                             return cx < cy || (cx == cy && x < y);  // total order: the build is deterministic
+                         });
+        nd.left = nnodes.fetch_add(2);
         nd.count = 0;
         s.nodes[j.node] = nd;
-        s.nodes.push_back(BNode{});
-        s.nodes.push_back(BNode{});
-        stack.push_back({nd.left, j.first, mid});
-        stack.push_back({nd.left + 1, j.first + mid, j.count - mid});
+        a = {nd.left, j.first, mid};
+        b = {nd.left + 1, j.first + mid, j.count - mid};
+        return true;
+    };
+    // breadth-first on one thread until there is enough independent work, then one subtree per task
+    std::vector<Job> frontier{{0u, 0u, n}};
+    const unsigned nthreads = std::max(1u, std::thread::hardware_concurrency());
+    while (!frontier.empty() && frontier.size() < 8 * size_t(nthreads) && frontier.front().count > 4096) {
+        std::vector<Job> next;
+        for (const Job& j : frontier) {
+            Job a, b;
+            if (split(j, a, b)) { next.push_back(a); next.push_back(b); }
+        }
+        frontier.swap(next);
     }
+    std::atomic<size_t> cursor{0};
+    auto worker = [&]() {
+        std::vector<Job> stack;
+        for (;;) {
+            size_t k = cursor.fetch_add(1);
+            if (k >= frontier.size()) break;
+            stack.push_back(frontier[k]);
+            while (!stack.empty()) {
+                Job j = stack.back();
+                stack.pop_back();
+                Job a, b;
+                if (split(j, a, b)) { stack.push_back(a); stack.push_back(b); }
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned i = 1; i < nthreads && i < frontier.size(); ++i) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
+    s.nodes.resize(nnodes.load());
     s.has_bvh = true;
 }
 
@@ -230,14 +271,11 @@ template <class R>
 HitR<R> intersect_bvh(const Scene& s, V3<R> o, V3<R> d, R tmin, R tmax) {
     HitR<R> h{tmax, 0, 0, MISS};
     // slab test in double regardless of R, with a relative pad, so the BVH can never cull a
-    // triangle the brute-force loop would accept.
+    // triangle the brute-force loop would accept. Children are visited near-first (the order
+    // changes only the work done: ties in t resolve to the lowest primitive id either way).
     const double ox = double(o.x), oy = double(o.y), oz = double(o.z);
     const double ix = 1.0 / double(d.x), iy = 1.0 / double(d.y), iz = 1.0 / double(d.z);
-    uint32_t stack[128];
-    int sp = 0;
-    stack[sp++] = 0;
-    while (sp) {
-        const BNode& nd = s.nodes[stack[--sp]];
+    auto slab = [&](const BNode& nd, double& tn_out) {
         double t0 = (double(nd.lo[0]) - ox) * ix, t1 = (double(nd.hi[0]) - ox) * ix;
         double tn = std::fmin(t0, t1), tf = std::fmax(t0, t1);
         t0 = (double(nd.lo[1]) - oy) * iy; t1 = (double(nd.hi[1]) - oy) * iy;
@@ -246,8 +284,20 @@ HitR<R> intersect_bvh(const Scene& s, V3<R> o, V3<R> d, R tmin, R tmax) {
         tn = std::fmax(tn, std::fmin(t0, t1)); tf = std::fmin(tf, std::fmax(t0, t1));
         // fmin/fmax drop NaNs (0 * inf on a degenerate slab), which only widens the interval
         const double pad = 1e-5 * (1.0 + std::fabs(tn) + std::fabs(tf));
-        if (tn - pad > tf + pad) continue;
-        if (tf + pad < double(tmin) || tn - pad > double(h.t)) continue;
+        tn_out = tn - pad;
+        if (tn - pad > tf + pad) return false;
+        if (tf + pad < double(tmin) || tn - pad > double(h.t)) return false;
+        return true;
+    };
+    struct Entry { uint32_t node; double tn; };
+    Entry stack[128];
+    int sp = 0;
+    double tn_root;
+    if (slab(s.nodes[0], tn_root)) stack[sp++] = {0u, tn_root};
+    while (sp) {
+        const Entry e = stack[--sp];
+        if (e.tn > double(h.t)) continue;  // culled by a hit found since it was pushed
+        const BNode& nd = s.nodes[e.node];
         if (nd.count) {
             for (uint32_t k = nd.left; k < nd.left + nd.count; ++k) {
                 uint32_t p = s.order[k];
@@ -255,8 +305,13 @@ HitR<R> intersect_bvh(const Scene& s, V3<R> o, V3<R> d, R tmin, R tmax) {
                 if (tri_hit<R>(s.tris[p], o, d, tmin, h.t, t, u, v) && (t < h.t || h.prim == MISS || p < h.prim)) h = {t, u, v, p};
             }
         } else {
-            stack[sp++] = nd.left;
-            stack[sp++] = nd.left + 1;
+            double ta, tb;
+            const bool ha = slab(s.nodes[nd.left], ta), hb = slab(s.nodes[nd.left + 1], tb);
+            if (ha && hb) {
+                if (ta <= tb) { stack[sp++] = {nd.left + 1, tb}; stack[sp++] = {nd.left, ta}; }
+                else { stack[sp++] = {nd.left, ta}; stack[sp++] = {nd.left + 1, tb}; }
+            } else if (ha) stack[sp++] = {nd.left, ta};
+            else if (hb) stack[sp++] = {nd.left + 1, tb};
         }
     }
     return h;
@@ -369,9 +424,9 @@ inline float unorm8_roundtrip(float x) {
 }
 
 template <class R>
-void render_rows(const Scene& s, const orc_params& p, uint32_t y0, uint32_t y1, bool brute, float* img, uint64_t& rays) {
-    for (uint32_t y = y0; y < y1; ++y)
-        for (uint32_t x = 0; x < p.width; ++x) {
+void render_rows(const Scene& s, const orc_params& p, uint32_t l0, uint32_t l1, bool brute, float* img, uint64_t& rays) {
+    for (uint32_t l = l0; l < l1; ++l)
+        for (uint32_t x = 0, y = tile_global_row(p, l); x < p.width; ++x) {
             V3<R> c = trace_pixel<R>(s, p, x, y, brute, rays);
             c = c / R(p.spp_per_frame);                  // raygen.rgen:86
             float* px = img + 4 * (size_t(y) * p.width + x);
@@ -428,7 +483,7 @@ uint32_t orc_scene_ntris(void* s) { return static_cast<uint32_t>(static_cast<Sce
 // precision: 32 or 64. brute: 1 forces the O(N) loop. Returns rays traced.
 uint64_t orc_render(void* scene, const orc_params* p, int precision, int brute, int nthreads, float* img) {
     const Scene& s = *static_cast<Scene*>(scene);
-    uint32_t y0 = p->tile_y0, y1 = p->tile_rows ? p->tile_y0 + p->tile_rows : p->height;
+    uint32_t y0 = 0, y1 = tile_local_rows(*p);  // tile-local rows
     if (nthreads <= 0) nthreads = int(std::max(1u, std::thread::hardware_concurrency()));
     std::atomic<uint32_t> next{y0};
     std::atomic<uint64_t> total{0};
@@ -452,10 +507,9 @@ uint64_t orc_render(void* scene, const orc_params* p, int precision, int brute, 
 
 // Primary rays of sample `sample_in_frame` for the tile: rays n*8 {o,tmin,d,tmax}, seeds n.
 void orc_generate_rays(const orc_params* p, uint32_t sample_in_frame, float* rays, uint32_t* seeds) {
-    uint32_t y0 = p->tile_y0, y1 = p->tile_rows ? p->tile_y0 + p->tile_rows : p->height;
     size_t i = 0;
-    for (uint32_t y = y0; y < y1; ++y)
-        for (uint32_t x = 0; x < p->width; ++x, ++i) {
+    for (uint32_t l = 0; l < tile_local_rows(*p); ++l)
+        for (uint32_t x = 0, y = tile_global_row(*p, l); x < p->width; ++x, ++i) {
             uint32_t k = sample_in_frame + p->spp_per_frame * uint32_t(p->frame) + 1u;
             uint32_t seed = make_seed(x, y, k);
             V3<float> o, d;

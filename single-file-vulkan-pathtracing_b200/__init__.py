@@ -38,6 +38,7 @@ class Params(C.Structure):
         ("frame", C.c_int32), ("tile_y0", C.c_uint32), ("tile_rows", C.c_uint32),
         ("cam_origin", C.c_float * 3), ("cam_target", C.c_float * 3), ("sky", C.c_float * 3),
         ("tmin", C.c_float), ("tmax", C.c_float), ("accum_mode", C.c_uint32), ("sampler", C.c_uint32),
+        ("tile_block", C.c_uint32), ("tile_nranks", C.c_uint32), ("tile_rank", C.c_uint32),
     ]
 
 
@@ -248,7 +249,8 @@ class PathTracer:
         return hits
 
     def generate_rays(self, params, sample_in_frame=0):
-        rows = params.tile_rows if params.tile_rows else params.height - params.tile_y0
+        rows = (params.height // params.tile_nranks if params.tile_block
+                else (params.tile_rows if params.tile_rows else params.height - params.tile_y0))
         n = rows * params.width
         rays = np.zeros((n, 8), np.float32)
         seeds = np.zeros(n, np.uint32)

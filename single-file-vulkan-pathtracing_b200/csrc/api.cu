@@ -47,8 +47,10 @@ struct bpt_context {
     PathQueue q[2] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     uint4* hits = nullptr;
     float4* frame_sum = nullptr;
-    float4* image = nullptr;
+    float4* image = nullptr;         // accumulation target; rank-major under interleaved tiling (bpt.h)
+    float4* image_linear = nullptr;  // row-major copy produced on demand under interleaved tiling
     uint32_t img_w = 0, img_h = 0;
+    uint32_t tile_block = 0, tile_nranks = 1, tile_rank = 0;  // tiling of the last bpt_trace
     uint32_t* counters = nullptr;            // counts[kMaxDepth+1] then fetch[kMaxDepth+1]
     unsigned long long* d_stats = nullptr;   // rays, nodes, tris
 
@@ -127,8 +129,8 @@ int ensure_paths(bpt_context* c, size_t n) {
 
 int ensure_image(bpt_context* c, uint32_t w, uint32_t h) {
     if (c->image && c->img_w == w && c->img_h == h) return BPT_OK;
-    cudaFree(c->image);
-    c->image = nullptr;
+    cudaFree(c->image); cudaFree(c->image_linear);
+    c->image = nullptr; c->image_linear = nullptr;
     BPT_CUDA_TRY(c, cudaMalloc(&c->image, (size_t)w * h * sizeof(float4)));
     BPT_CUDA_TRY(c, cudaMemsetAsync(c->image, 0, (size_t)w * h * sizeof(float4), c->stream));
     c->img_w = w;
@@ -150,10 +152,26 @@ int check_params(bpt_context* c, const bpt_params* p) {
     if (p->max_depth == 0 || p->max_depth > kMaxDepth) return bpt_fail(c, BPT_E_INVALID, "max_depth must be in [1,%u]", kMaxDepth);
     if (p->frame < 0) return bpt_fail(c, BPT_E_INVALID, "frame must be >= 0");
     uint32_t rows = p->tile_rows ? p->tile_rows : p->height - (p->tile_y0 < p->height ? p->tile_y0 : p->height);
-    if (p->tile_y0 >= p->height || p->tile_y0 + rows > p->height) return bpt_fail(c, BPT_E_INVALID, "tile rows [%u,%u) outside image height %u", p->tile_y0, p->tile_y0 + rows, p->height);
+    if (p->tile_block) {
+        if (p->tile_y0 || p->tile_rows) return bpt_fail(c, BPT_E_INVALID, "interleaved tiling (tile_block != 0) excludes tile_y0/tile_rows");
+        if (p->tile_nranks == 0 || p->tile_rank >= p->tile_nranks) return bpt_fail(c, BPT_E_INVALID, "bad tile_rank %u of %u", p->tile_rank, p->tile_nranks);
+        if (p->height % ((uint64_t)p->tile_block * p->tile_nranks)) return bpt_fail(c, BPT_E_INVALID, "height %u is not a multiple of tile_block*tile_nranks = %u*%u", p->height, p->tile_block, p->tile_nranks);
+        rows = p->height / p->tile_nranks;
+    } else if (p->tile_y0 >= p->height || p->tile_y0 + rows > p->height) return bpt_fail(c, BPT_E_INVALID, "tile rows [%u,%u) outside image height %u", p->tile_y0, p->tile_y0 + rows, p->height);
     if ((uint64_t)rows * p->width > 0x7fffffffull) return bpt_fail(c, BPT_E_INVALID, "tile too large");
     if (p->accum_mode > BPT_ACCUM_RGBA8) return bpt_fail(c, BPT_E_INVALID, "bad accum_mode");
     if (p->sampler > BPT_SAMPLER_COSINE) return bpt_fail(c, BPT_E_INVALID, "bad sampler");
+    return BPT_OK;
+}
+
+// Row-major view of the image: the buffer itself, or its de-interleaved copy (interleaved tiling).
+int row_major_image(bpt_context* c, const float4** out) {
+    *out = c->image;
+    if (!c->tile_block) return BPT_OK;
+    const size_t bytes = (size_t)c->img_w * c->img_h * sizeof(float4);
+    if (!c->image_linear) BPT_CUDA_TRY(c, cudaMalloc(&c->image_linear, bytes));
+    launch_deinterleave(c->image, c->image_linear, c->img_w, c->img_h, c->tile_block, c->tile_nranks, c->stream);
+    *out = c->image_linear;
     return BPT_OK;
 }
 
@@ -249,7 +267,7 @@ void bpt_destroy(bpt_context* c) {
     free_scene(c);
     free_paths(c);
     bvh8_free(c->blas);
-    cudaFree(c->d_woop); cudaFree(c->image); cudaFree(c->counters); cudaFree(c->d_stats);
+    cudaFree(c->d_woop); cudaFree(c->image); cudaFree(c->image_linear); cudaFree(c->counters); cudaFree(c->d_stats);
     for (auto& p : c->frame_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto& p : c->trace_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
@@ -397,10 +415,16 @@ int bpt_trace(bpt_context* c, const bpt_params* p) {
     if (!c->built) return bpt_fail(c, BPT_E_STATE, "bpt_trace before bpt_build_accel");
     cudaSetDevice(c->device);
     FrameParams f = to_frame(p);
-    if (f.tile_rows == 0) f.tile_rows = f.height - f.tile_y0;
-    const uint32_t npix = f.tile_rows * f.width;
+    const uint32_t npix = tile_local_rows(f) * f.width;
     if ((rc = ensure_paths(c, npix)) != BPT_OK) return rc;
     if ((rc = ensure_image(c, f.width, f.height)) != BPT_OK) return rc;
+    if (f.tile_block != c->tile_block || (f.tile_block && (f.tile_nranks != c->tile_nranks || f.tile_rank != c->tile_rank))) {
+        // the storage layout of the image buffer changes with the tiling: start from a fresh image
+        BPT_CUDA_TRY(c, cudaMemsetAsync(c->image, 0, (size_t)f.width * f.height * sizeof(float4), c->stream));
+        c->tile_block = f.tile_block;
+        c->tile_nranks = f.tile_block ? f.tile_nranks : 1;
+        c->tile_rank = f.tile_block ? f.tile_rank : 0;
+    }
     SceneView sv{c->d_verts, c->d_idx, c->d_faces, c->d_xforms, c->ntris};
     uint32_t* counts = c->counters;
     uint32_t* fetch = c->counters + (kMaxDepth + 1);
@@ -440,7 +464,10 @@ int bpt_read_image(bpt_context* c, float* rgba, size_t nfloats) {
     size_t need = (size_t)c->img_w * c->img_h * 4;
     if (nfloats < need) return bpt_fail(c, BPT_E_INVALID, "buffer holds %zu floats, image needs %zu", nfloats, need);
     cudaSetDevice(c->device);
-    BPT_CUDA_TRY(c, cudaMemcpyAsync(rgba, c->image, need * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    const float4* img = nullptr;
+    int rc = row_major_image(c, &img);
+    if (rc) return rc;
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(rgba, img, need * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return BPT_OK;
 }
@@ -451,9 +478,12 @@ int bpt_read_image_bgra8(bpt_context* c, uint8_t* bgra, size_t nbytes) {
     size_t npix = (size_t)c->img_w * c->img_h;
     if (nbytes < npix * 4) return bpt_fail(c, BPT_E_INVALID, "buffer holds %zu bytes, image needs %zu", nbytes, npix * 4);
     cudaSetDevice(c->device);
+    const float4* img = nullptr;
+    int rc = row_major_image(c, &img);
+    if (rc) return rc;
     uint8_t* d = nullptr;
     BPT_CUDA_TRY(c, cudaMalloc(&d, npix * 4));
-    launch_image_to_bgra8(c->image, d, npix, c->stream);
+    launch_image_to_bgra8(img, d, npix, c->stream);
     cudaError_t e = cudaMemcpyAsync(bgra, d, npix * 4, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(d);
@@ -464,7 +494,11 @@ int bpt_read_image_bgra8(bpt_context* c, uint8_t* bgra, size_t nbytes) {
 int bpt_image_device_ptr(bpt_context* c, void** dptr, size_t* nbytes) {
     if (!c || !dptr) return BPT_E_INVALID;
     if (!c->image) return bpt_fail(c, BPT_E_STATE, "no image yet");
-    *dptr = c->image;
+    cudaSetDevice(c->device);
+    const float4* img = nullptr;
+    int rc = row_major_image(c, &img);  // stream-ordered: valid for work enqueued after this call
+    if (rc) return rc;
+    *dptr = const_cast<float4*>(img);
     if (nbytes) *nbytes = (size_t)c->img_w * c->img_h * sizeof(float4);
     return BPT_OK;
 }
@@ -531,6 +565,7 @@ int bpt_trace_rays(bpt_context* c, const float* rays, uint32_t n, void* hits) {
     BPT_CUDA_TRY(c, cudaMemcpyAsync(counts, &init[0], 4, cudaMemcpyHostToDevice, c->stream));
     BPT_CUDA_TRY(c, cudaMemcpyAsync(fetch, &init[1], 4, cudaMemcpyHostToDevice, c->stream));
     launch_trace(c, make_trace_args(c, c->q[0].rays, c->hits, counts, fetch));
+    launch_refine_hits(SceneView{c->d_verts, c->d_idx, c->d_faces, c->d_xforms, c->ntris}, c->q[0].rays, c->hits, n, c->stream);
     BPT_CUDA_TRY(c, cudaMemcpyAsync(hits, c->hits, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     BPT_CUDA_TRY(c, cudaGetLastError());
@@ -543,8 +578,7 @@ int bpt_generate_rays(bpt_context* c, const bpt_params* p, uint32_t sample_in_fr
     if (rc) return rc;
     cudaSetDevice(c->device);
     FrameParams f = to_frame(p);
-    if (f.tile_rows == 0) f.tile_rows = f.height - f.tile_y0;
-    const uint32_t npix = f.tile_rows * f.width;
+    const uint32_t npix = tile_local_rows(f) * f.width;
     if ((rc = ensure_paths(c, npix)) != BPT_OK) return rc;
     uint32_t* counts = c->counters;
     uint32_t* fetch = c->counters + (kMaxDepth + 1);
@@ -640,12 +674,15 @@ int bpt_allgather_image(bpt_context* c, uint32_t width, uint32_t height) {
     if (!c->nccl_comm) return bpt_fail(c, BPT_E_STATE, "bpt_allgather_image before bpt_nccl_init");
     if (!c->image || c->img_w != width || c->img_h != height) return bpt_fail(c, BPT_E_STATE, "image is not %ux%u", width, height);
     if (height % (uint32_t)c->nranks) return bpt_fail(c, BPT_E_INVALID, "height %u not divisible by %d ranks", height, c->nranks);
+    if (c->tile_block && ((int)c->tile_nranks != c->nranks || (int)c->tile_rank != c->rank))
+        return bpt_fail(c, BPT_E_STATE, "interleaved tile %u/%u does not match NCCL rank %d/%d", c->tile_rank, c->tile_nranks, c->rank, c->nranks);
     cudaSetDevice(c->device);
+    // contiguous and interleaved tilings both keep rank r's rows at row r*height/nranks of the buffer
     uint32_t y0, rows;
     bpt_tile_rows(height, c->rank, c->nranks, &y0, &rows);
     size_t count = (size_t)rows * width * 4;  // floats per rank
     std::string err;
-    // in place: this rank's tile already sits at its slot of the full image (K12 wrote it there)
+    // in place: this rank's tile already sits at its slot of the buffer (K12 wrote it there)
     if (bpt_nccl_allgather_f32(c->nccl_comm, c->image + (size_t)y0 * width, c->image, count, c->stream, &err) != 0)
         return bpt_fail(c, BPT_E_NCCL, "%s", err.c_str());
     return BPT_OK;

@@ -70,6 +70,38 @@ __device__ __forceinline__ V3 load_vertex(const SceneView& s, uint32_t prim, int
             m[8] * x + m[9] * y + m[10] * z + m[11]};
 }
 
+// Barycentrics (u,v) of v1,v2 at the ray/triangle intersection, Moeller-Trumbore with one IEEE operation per step
+// (attribs of closesthit.rchit:56). Falls back to the traversal kernel's values on a degenerate determinant.
+__device__ __forceinline__ void barycentrics(V3 o, V3 d, V3 v0, V3 v1, V3 v2, float u_in, float v_in, float& u, float& v) {
+    const V3 e1 = v1 - v0, e2 = v2 - v0;
+    const V3 p = cross(d, e2);
+    const float det = dot(e1, p);
+    u = u_in; v = v_in;
+    if (det == 0.0f) return;
+    const float inv = 1.0f / det;
+    const V3 s = o - v0;
+    const V3 q = cross(s, e1);
+    const float uu = dot(s, p) * inv, vv = dot(d, q) * inv;
+    if (isfinite(uu) && isfinite(vv)) { u = uu; v = vv; }
+}
+
+// bpt_trace_rays: the same refinement applied to a hit buffer, so stage-level callers see what shading sees.
+__global__ void k_refine_hits(SceneView s, const float4* __restrict__ rays, uint4* __restrict__ hits, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 h = hits[i];
+    if (h.w == BPT_MISS) return;
+    const uint32_t inst = s.xforms ? h.w / s.ntris : 0u;
+    const uint32_t prim = s.xforms ? h.w - inst * s.ntris : h.w;
+    const float* m = s.xforms ? s.xforms + 12 * (size_t)inst : nullptr;
+    const V3 v0 = load_vertex(s, prim, 0, m), v1 = load_vertex(s, prim, 1, m), v2 = load_vertex(s, prim, 2, m);
+    const float4 ro = rays[2 * (size_t)i], rd = rays[2 * (size_t)i + 1];
+    float u, v;
+    barycentrics(V3{ro.x, ro.y, ro.z}, V3{rd.x, rd.y, rd.z}, v0, v1, v2, __uint_as_float(h.y), __uint_as_float(h.z), u, v);
+    h.y = __float_as_uint(u); h.z = __float_as_uint(v);
+    hits[i] = h;
+}
+
 __global__ void k_shade(FrameParams p, SceneView s, uint32_t depth, PathQueue in, const uint4* __restrict__ hits,
                         PathQueue out, uint32_t* counts, float4* frame_sum) {
     const uint32_t n = counts[depth];
@@ -95,7 +127,12 @@ __global__ void k_shade(FrameParams p, SceneView s, uint32_t depth, PathQueue in
             const uint32_t prim = s.xforms ? h.w - inst * s.ntris : h.w;
             const float* m = s.xforms ? s.xforms + 12 * (size_t)inst : nullptr;
             const V3 v0 = load_vertex(s, prim, 0, m), v1 = load_vertex(s, prim, 1, m), v2 = load_vertex(s, prim, 2, m);
-            const float u = __uint_as_float(h.y), v = __uint_as_float(h.z);
+            // The traversal kernel decides WHICH triangle is closest with the Woop form (fast, but its u,v lose
+            // bits on slivers and far origins); the barycentrics that shading consumes are re-derived here from
+            // the original vertices, so the hit position carries no traversal-format error.
+            const float4 ro = in.rays[2 * (size_t)i], rd = in.rays[2 * (size_t)i + 1];
+            float u, v;
+            barycentrics(V3{ro.x, ro.y, ro.z}, V3{rd.x, rd.y, rd.z}, v0, v1, v2, __uint_as_float(h.y), __uint_as_float(h.z), u, v);
             const float b0 = 1.0f - u - v;                           // closesthit.rchit:56
             const V3 pos = v0 * b0 + v1 * u + v2 * v;                // :57
             const V3 nrm = -normalize(cross(v1 - v0, v2 - v0));      // :58, :43-48
@@ -236,6 +273,9 @@ void launch_generate(const FrameParams& p, uint32_t sample_in_frame, PathQueue q
 void launch_shade(const FrameParams& p, const SceneView& s, uint32_t depth, PathQueue in, const uint4* hits,
                   PathQueue out, uint32_t* counts, float4* frame_sum, uint32_t max_paths, cudaStream_t st) {
     k_shade<<<grid_for(max_paths), kBlock, 0, st>>>(p, s, depth, in, hits, out, counts, frame_sum);
+}
+void launch_refine_hits(const SceneView& s, const float4* rays, uint4* hits, uint32_t n, cudaStream_t st) {
+    k_refine_hits<<<grid_for(n), kBlock, 0, st>>>(s, rays, hits, n);
 }
 void launch_accumulate(const FrameParams& p, float4* frame_sum, float4* image, cudaStream_t st) {
     k_accumulate<<<grid_for((uint64_t)tile_local_rows(p) * p.width), kBlock, 0, st>>>(p, frame_sum, image);

@@ -49,6 +49,8 @@ void launch_generate(const FrameParams& p, uint32_t sample_in_frame, PathQueue q
 // and counted in counts[depth+1].
 void launch_shade(const FrameParams& p, const SceneView& s, uint32_t depth, PathQueue in, const uint4* hits,
                   PathQueue out, uint32_t* counts, float4* frame_sum, uint32_t max_paths, cudaStream_t st);
+// re-derives (u,v) of every hit from the original vertices (what k_shade does internally)
+void launch_refine_hits(const SceneView& s, const float4* rays, uint4* hits, uint32_t n, cudaStream_t st);
 void launch_accumulate(const FrameParams& p, float4* frame_sum, float4* image, cudaStream_t st);
 void launch_soup(uint32_t ntris, uint32_t seed, float scale, float* verts, uint32_t* idx, float* faces, cudaStream_t st);
 void launch_image_to_bgra8(const float4* image, uint8_t* bgra, size_t npix, cudaStream_t st);

@@ -23,6 +23,7 @@ class OrcParams(C.Structure):
         ("frame", C.c_int32), ("tile_y0", C.c_uint32), ("tile_rows", C.c_uint32),
         ("cam_origin", C.c_float * 3), ("cam_target", C.c_float * 3), ("sky", C.c_float * 3),
         ("tmin", C.c_float), ("tmax", C.c_float), ("accum_mode", C.c_uint32), ("sampler", C.c_uint32),
+        ("tile_block", C.c_uint32), ("tile_nranks", C.c_uint32), ("tile_rank", C.c_uint32),
     ]
 
 
@@ -36,6 +37,7 @@ def default_params(width=1024, height=1024, spp=32, depth=8, frame=0, **kw):
     p.sky[:] = (0.7, 0.6, 0.5)
     p.tmin, p.tmax = 0.001, 10000.0
     p.accum_mode, p.sampler = 0, 0
+    p.tile_block, p.tile_nranks, p.tile_rank = 0, 0, 0
     for k, v in kw.items():
         if k in ("cam_origin", "cam_target", "sky"):
             getattr(p, k)[:] = v
@@ -137,7 +139,7 @@ class Scene:
 
 
 def generate_rays(p, sample_in_frame=0):
-    rows = p.tile_rows if p.tile_rows else p.height
+    rows = p.height // p.tile_nranks if p.tile_block else (p.tile_rows if p.tile_rows else p.height - p.tile_y0)
     n = rows * p.width
     rays = np.zeros((n, 8), np.float32)
     seeds = np.zeros(n, np.uint32)

@@ -318,6 +318,39 @@ def test_frame_split_and_tile_invariance_gpu(pt_cornell):
     assert O.rel_l2(four, one) < 1e-5
 
 
+def test_interleaved_tiling_gpu(pt_cornell, cornell_oracle):
+    """Multi-GPU tiling on one GPU: the 4 interleaved tiles (8-row blocks dealt round-robin) are disjoint, each equals
+    the same rows of the full image bit for bit, and the BGRA8 view is de-interleaved the same way."""
+    pt_cornell.clear_image()
+    full = pt_cornell.render(bpt.default_params(80, 96, 4, 6), frames=2)
+    acc = np.zeros_like(full)
+    for rank in range(4):
+        tile = dict(tile_block=8, tile_nranks=4, tile_rank=rank)
+        p = bpt.default_params(80, 96, 4, 6, **tile)
+        part = pt_cornell.render(p, frames=2)
+        rows = [y for y in range(96) if (y // 8) % 4 == rank]
+        other = [y for y in range(96) if (y // 8) % 4 != rank]
+        assert np.array_equal(part[rows], full[rows]) and np.all(part[other] == 0)
+        rays, seeds = pt_cornell.generate_rays(p, 1)
+        orays, oseeds = O.generate_rays(O.default_params(80, 96, 4, 6, **tile), 1)
+        assert np.array_equal(seeds, oseeds) and np.array_equal(rays, orays)
+        bgra = pt_cornell.read_image_bgra8(80, 96)
+        assert np.all(bgra[other] == 0) and np.all(bgra[rows][..., 3] == 255)
+        acc += part
+    assert np.array_equal(acc, full)
+    ref = np.zeros((96, 80, 4), np.float32)
+    for f in range(2):
+        cornell_oracle.render(O.default_params(80, 96, 4, 6, f, tile_block=8, tile_nranks=4, tile_rank=2), 32, image=ref)
+    rows = [y for y in range(96) if (y // 8) % 4 == 2]
+    pt_cornell.render(bpt.default_params(80, 96, 4, 6, tile_block=8, tile_nranks=4, tile_rank=2), frames=2)
+    assert O.rel_l2(pt_cornell.read_image(80, 96)[rows], ref[rows]) <= 1e-3
+    with pytest.raises(bpt.BptError):
+        pt_cornell.trace(bpt.default_params(80, 96, 4, 6, tile_block=8, tile_nranks=5, tile_rank=0))   # 96 % 40 != 0
+    with pytest.raises(bpt.BptError):
+        pt_cornell.trace(bpt.default_params(80, 96, 4, 6, tile_block=8, tile_nranks=4, tile_rank=4))
+    pt_cornell.clear_image()
+
+
 def test_determinism(pt_cornell):
     pt_cornell.clear_image()
     a = pt_cornell.render(bpt.default_params(200, 120, 4, 8))
