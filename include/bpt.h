@@ -93,6 +93,15 @@ typedef struct bpt_stats {
     double   build_ms;        /* device time of the last bpt_build_accel                    */
     uint64_t nodes_visited;   /* instrumented builds only (BPT_OPT_COUNT_TRAVERSAL)         */
     uint64_t tris_tested;     /*   "                                                        */
+    /* SIMD efficiency of the traversal loop (instrumented builds only): one loop iteration of a
+     * warp does at most one node step and one triangle test per lane.
+     *   lanes per node step     = nodes_visited / warp_node_steps
+     *   lanes per triangle step = tris_tested   / warp_tri_steps
+     *   live lanes per iteration = lane_iterations / warp_iterations                           */
+    uint64_t warp_iterations;
+    uint64_t warp_node_steps;
+    uint64_t warp_tri_steps;
+    uint64_t lane_iterations;
 } bpt_stats;
 
 /* Sizes of the acceleration structure, for layout/roofline documentation and tests. */

@@ -48,6 +48,8 @@ class Stats(C.Structure):
         ("rays_traced", C.c_uint64), ("paths", C.c_uint64), ("trace_launches", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("trace_kernel_ms", C.c_double), ("frame_ms", C.c_double),
         ("build_ms", C.c_double), ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64),
+        ("warp_iterations", C.c_uint64), ("warp_node_steps", C.c_uint64), ("warp_tri_steps", C.c_uint64),
+        ("lane_iterations", C.c_uint64),
     ]
 
 
@@ -63,7 +65,8 @@ class AccelInfo(C.Structure):
 
 HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4")])
 NODE8_DTYPE = np.dtype([
-    ("p", "<f4", 3), ("e", "u1", 3), ("imask", "u1"), ("child_base", "<u4"), ("tri_base", "<u4"), ("meta", "u1", 8),
+    ("p", "<f4", 3), ("e", "u1", 3), ("pad0", "u1"), ("child_base", "<u4"), ("tri_base", "<u4"), ("valid", "<u4"),
+    ("pad1", "<u4"),
     ("qlox", "u1", 8), ("qloy", "u1", 8), ("qloz", "u1", 8), ("qhix", "u1", 8), ("qhiy", "u1", 8), ("qhiz", "u1", 8)])
 assert NODE8_DTYPE.itemsize == 80
 

@@ -52,7 +52,7 @@ struct bpt_context {
     uint32_t img_w = 0, img_h = 0;
     uint32_t tile_block = 0, tile_nranks = 1, tile_rank = 0;  // tiling of the last bpt_trace
     uint32_t* counters = nullptr;            // counts[kMaxDepth+1] then fetch[kMaxDepth+1]
-    unsigned long long* d_stats = nullptr;   // rays, nodes, tris
+    unsigned long long* d_stats = nullptr;   // BPT_STAT_* (trace.cuh)
 
     // options
     bool profile = false, count = false;
@@ -182,7 +182,8 @@ TraceArgs make_trace_args(bpt_context* c, const float4* rays, uint4* hits, const
     a.woop = reinterpret_cast<const float4*>(c->d_woop);
     a.prim_index = c->blas.prim_index;
     a.top_nodes = c->top_nodes; a.top_tris = c->top_tris;
-    a.stat_rays = c->d_stats; a.stat_nodes = c->d_stats + 1; a.stat_tris = c->d_stats + 2;
+    a.magic = 0x47000000u;
+    a.stat = c->d_stats;
     return a;
 }
 
@@ -248,8 +249,8 @@ int bpt_create(int device, void* stream, bpt_context** out) {
         c->own_stream = true;
     }
     if ((e = cudaMalloc(&c->counters, 2 * (kMaxDepth + 1) * sizeof(uint32_t))) != cudaSuccess ||
-        (e = cudaMalloc(&c->d_stats, 4 * sizeof(unsigned long long))) != cudaSuccess ||
-        (e = cudaMemsetAsync(c->d_stats, 0, 4 * sizeof(unsigned long long), c->stream)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_stats, BPT_STAT_COUNT * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMemsetAsync(c->d_stats, 0, BPT_STAT_COUNT * sizeof(unsigned long long), c->stream)) != cudaSuccess ||
         (e = trace_configure()) != cudaSuccess) {
         int rc = bpt_fail(nullptr, BPT_E_CUDA, "context setup: %s", cudaGetErrorString(e));
         bpt_destroy(c);
@@ -372,7 +373,7 @@ int bpt_build_accel(bpt_context* c) {
     BPT_CUDA_TRY(c, bvh8_build(c->blas, c->stream));
     if (c->blas.num_leaf_slots != c->ntris)
         return bpt_fail(c, BPT_E_STATE, "BVH8 collapse placed %u of %u triangles", c->blas.num_leaf_slots, c->ntris);
-    if (c->blas.depth > (uint32_t)(kTraceSmemStack + 40 - 2))
+    if (c->blas.depth > (uint32_t)kTraceMaxDepth)
         return bpt_fail(c, BPT_E_STATE, "BVH8 depth %u exceeds the traversal stack", c->blas.depth);
     cudaFree(c->d_woop);
     c->d_woop = nullptr;
@@ -515,11 +516,15 @@ int bpt_get_stats(bpt_context* c, bpt_stats* out) {
     if (!c || !out) return BPT_E_INVALID;
     cudaSetDevice(c->device);
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    unsigned long long h[3];
+    unsigned long long h[BPT_STAT_COUNT];
     BPT_CUDA_TRY(c, cudaMemcpy(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
-    c->stats.rays_traced = h[0];
-    c->stats.nodes_visited = h[1];
-    c->stats.tris_tested = h[2];
+    c->stats.rays_traced = h[BPT_STAT_RAYS];
+    c->stats.nodes_visited = h[BPT_STAT_NODES];
+    c->stats.tris_tested = h[BPT_STAT_TRIS];
+    c->stats.warp_iterations = h[BPT_STAT_WARP_ITERS];
+    c->stats.warp_node_steps = h[BPT_STAT_WARP_NODE_STEPS];
+    c->stats.warp_tri_steps = h[BPT_STAT_WARP_TRI_STEPS];
+    c->stats.lane_iterations = h[BPT_STAT_LANE_ITERS];
     for (auto& p : c->frame_events) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, p.first, p.second);
@@ -547,7 +552,7 @@ int bpt_reset_stats(bpt_context* c) {
     double build = c->stats.build_ms;
     c->stats = bpt_stats{};
     c->stats.build_ms = build;
-    BPT_CUDA_TRY(c, cudaMemset(c->d_stats, 0, 4 * sizeof(unsigned long long)));
+    BPT_CUDA_TRY(c, cudaMemset(c->d_stats, 0, BPT_STAT_COUNT * sizeof(unsigned long long)));
     return BPT_OK;
 }
 

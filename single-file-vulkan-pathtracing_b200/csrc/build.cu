@@ -227,11 +227,13 @@ __device__ __forceinline__ float half_area(float4 lo, float4 hi) {
     return dx * dy + dy * dz + dz * dx;
 }
 
+constexpr float kQuantMargin = 0.0078125f;  // 2^-7 of a quantisation step, see k_bvh8_collapse
+
 // exponent e with 2^e * 255 >= ext (with margin), clamped away from denormals
 __device__ __forceinline__ int quant_exponent(float ext) {
     if (!(ext > 0.f)) return -100;
     int k;
-    frexpf(ext * (1.001f / 255.0f), &k);  // value = m * 2^k, m in [0.5,1)  =>  2^k > value
+    frexpf(ext * (1.02f / 255.0f), &k);  // value = m * 2^k, m in [0.5,1)  =>  2^k > value; 2 % = 5 steps of slack
     return max(-100, min(k, 120));
 }
 
@@ -267,7 +269,12 @@ __global__ void k_bvh8_collapse(CollapseArgs a) {
 
     const float4 blo = a.nlo[src], bhi = a.nhi[src];
     const float pad = a.pad;
-    const float px = blo.x - pad, py = blo.y - pad, pz = blo.z - pad;
+    // grid: exponent from the padded extent (with ~5 steps of slack), origin one margin below the padded box
+    const int ex = quant_exponent((bhi.x - blo.x) + 2.f * pad), ey = quant_exponent((bhi.y - blo.y) + 2.f * pad),
+              ez = quant_exponent((bhi.z - blo.z) + 2.f * pad);
+    const float sx = exp2f((float)ex), sy = exp2f((float)ey), sz = exp2f((float)ez);
+    const float isx = exp2f((float)-ex), isy = exp2f((float)-ey), isz = exp2f((float)-ez);
+    const float px = blo.x - pad - kQuantMargin * sx, py = blo.y - pad - kQuantMargin * sy, pz = blo.z - pad - kQuantMargin * sz;
     const float cx = 0.5f * (blo.x + bhi.x), cy = 0.5f * (blo.y + bhi.y), cz = 0.5f * (blo.z + bhi.z);
 
     // slot assignment: slot bit 2/1/0 set = child lies on the +x/+y/+z side of the node centre.
@@ -310,32 +317,29 @@ __global__ void k_bvh8_collapse(CollapseArgs a) {
 
     Node8 nd;
     nd.px = px; nd.py = py; nd.pz = pz;
-    const int ex = quant_exponent((bhi.x + pad) - px), ey = quant_exponent((bhi.y + pad) - py),
-              ez = quant_exponent((bhi.z + pad) - pz);
     nd.ex = (uint8_t)(ex + 127); nd.ey = (uint8_t)(ey + 127); nd.ez = (uint8_t)(ez + 127);
     nd.child_base = child_base;
     nd.tri_base = tri_base;
-    const float sx = exp2f((float)ex), sy = exp2f((float)ey), sz = exp2f((float)ez);
-    const float isx = exp2f((float)-ex), isy = exp2f((float)-ey), isz = exp2f((float)-ez);
-    uint32_t imask = 0, int_rank = 0, leaf_off = 0;
+    uint32_t valid = 0, int_rank = 0, leaf_off = 0;
     for (int s = 0; s < 8; ++s) {
         int c = child_in[s];
         if (c < 0) {
-            nd.meta[s] = 0;
             nd.qlox[s] = nd.qloy[s] = nd.qloz[s] = 255;
             nd.qhix[s] = nd.qhiy[s] = nd.qhiz[s] = 0;
             continue;
         }
-        // conservative quantisation: origin + qlo*scale <= lo - pad, origin + qhi*scale >= hi + pad
+        // conservative quantisation with margin m = kQuantMargin steps:
+        //   origin + qlo*scale <= lo - pad - m*scale,  origin + qhi*scale >= hi + pad + m*scale
+        // (the traversal kernel evaluates the planes with an error below 2^-9 step, trace.cu byte_f)
         auto qlo = [&](float v, float p, float sc, float isc) {
-            float t = v - pad;
+            float t = v - pad - kQuantMargin * sc;
             int q = (int)floorf((t - p) * isc);
             q = max(0, min(q, 255));
             while (q > 0 && p + (float)q * sc > t) --q;
             return (uint8_t)q;
         };
         auto qhi = [&](float v, float p, float sc, float isc) {
-            float t = v + pad;
+            float t = v + pad + kQuantMargin * sc;
             int q = (int)ceilf((t - p) * isc);
             q = max(0, min(q, 255));
             while (q < 255 && p + (float)q * sc < t) ++q;
@@ -345,20 +349,21 @@ __global__ void k_bvh8_collapse(CollapseArgs a) {
         nd.qloy[s] = qlo(clo[c].y, py, sy, isy); nd.qhiy[s] = qhi(chi[c].y, py, sy, isy);
         nd.qloz[s] = qlo(clo[c].z, pz, sz, isz); nd.qhiz[s] = qhi(chi[c].z, pz, sz, isz);
         if (cnt[c] > 3u) {
-            imask |= 1u << s;
-            nd.meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));
+            valid |= 1u << (24 + s);
             a.wide_src[child_base + int_rank] = cand[c];
             ++int_rank;
         } else {
             uint32_t k = cnt[c];
-            nd.meta[s] = (uint8_t)((((1u << k) - 1u) << 5) | leaf_off);
+            valid |= ((1u << k) - 1u) << (3 * s);
             uint32_t f = node_first(a, cand[c]);
             for (uint32_t j = 0; j < k; ++j)
                 a.prim_index[tri_base + leaf_off + j] = (uint32_t)(a.keys[f + j] & 0xffffffffu);
             leaf_off += k;
         }
     }
-    nd.imask = (uint8_t)imask;
+    nd.valid = valid;
+    nd.pad0 = 0;
+    nd.pad1 = 0;
     uint4* dst = reinterpret_cast<uint4*>(a.nodes + w);
     const uint4* srcw = reinterpret_cast<const uint4*>(&nd);
 #pragma unroll

@@ -9,20 +9,27 @@
 #define BPT_NUM_SMS_DEFAULT 148
 
 // ------------------------------------------------------------------ BVH8 node (80 bytes)
-// Compressed 8-wide node after Ylitie, Karras, Laine 2017. Five 16-byte words so a lane fetches
-// it with five 128-bit loads (or a TMA bulk copy moves whole blocks of nodes into shared memory).
-//   w0: px, py, pz (node origin, f32) | ex, ey, ez (u8 biased exponents), imask (u8)
-//   w1: child_base (u32), tri_base (u32), meta[0..3], meta[4..7]
+// Compressed 8-wide node after Ylitie, Karras, Laine 2017, with the per-child meta bytes replaced by
+// one validity word so that the traversal kernel spends one predicated OR per child (trace.cu).
+// Five 16-byte words: a lane fetches a node with five 128-bit loads, and a TMA bulk copy moves whole
+// blocks of nodes into shared memory.
+//   w0: px, py, pz (grid origin, f32) | ex, ey, ez (u8 biased exponents of the grid step), 0
+//   w1: child_base (u32), tri_base (u32), valid (u32), 0
 //   w2: qlo_x[0..7], qlo_y[0..7]
 //   w3: qlo_z[0..7], qhi_x[0..7]
 //   w4: qhi_y[0..7], qhi_z[0..7]
-// meta[i]: 0 = empty; internal child: 0x20 | (24 + slot); leaf: (unary tri count << 5) | first
-// triangle offset relative to tri_base (0..23). Children boxes are origin + q * 2^e.
+// valid: bit 24+s set   = child slot s is an internal node; the internal children of a node are
+//                         consecutive nodes from child_base, in slot order
+//        bits 3s..3s+2  = unary triangle count (001, 011, 111) of leaf child s, 0 if s is internal
+//                         or empty; the triangles of a node are consecutive leaf slots from tri_base
+//                         in (slot, k) order, so bit b of the low 24 is triangle
+//                         tri_base + popc(valid & ((1 << b) - 1) & 0xffffff)
+// Child boxes are origin + q * 2^(e-127) per axis; slot bit 2/1/0 = child on the +x/+y/+z side.
 struct __align__(16) Node8 {
     float px, py, pz;
-    uint8_t ex, ey, ez, imask;
+    uint8_t ex, ey, ez, pad0;
     uint32_t child_base, tri_base;
-    uint8_t meta[8];
+    uint32_t valid, pad1;
     uint8_t qlox[8], qloy[8];
     uint8_t qloz[8], qhix[8];
     uint8_t qhiy[8], qhiz[8];

@@ -70,19 +70,21 @@ __device__ __forceinline__ V3 load_vertex(const SceneView& s, uint32_t prim, int
             m[8] * x + m[9] * y + m[10] * z + m[11]};
 }
 
-// Barycentrics (u,v) of v1,v2 at the ray/triangle intersection, Moeller-Trumbore with one IEEE operation per step
-// (attribs of closesthit.rchit:56). Falls back to the traversal kernel's values on a degenerate determinant.
-__device__ __forceinline__ void barycentrics(V3 o, V3 d, V3 v0, V3 v1, V3 v2, float u_in, float v_in, float& u, float& v) {
+// Barycentrics (u,v) of v1,v2 and the distance t at the ray/triangle intersection, Moeller-Trumbore with one IEEE
+// operation per step (attribs of closesthit.rchit:56). The traversal kernel only decides WHICH triangle is closest
+// (Woop form, fast, but it loses bits on slivers and far origins) and reports its own t; on a degenerate determinant
+// u = v = 0 and that t are kept.
+__device__ __forceinline__ void barycentrics(V3 o, V3 d, V3 v0, V3 v1, V3 v2, float& u, float& v, float& t) {
     const V3 e1 = v1 - v0, e2 = v2 - v0;
     const V3 p = cross(d, e2);
     const float det = dot(e1, p);
-    u = u_in; v = v_in;
+    u = 0.0f; v = 0.0f;
     if (det == 0.0f) return;
     const float inv = 1.0f / det;
     const V3 s = o - v0;
     const V3 q = cross(s, e1);
-    const float uu = dot(s, p) * inv, vv = dot(d, q) * inv;
-    if (isfinite(uu) && isfinite(vv)) { u = uu; v = vv; }
+    const float uu = dot(s, p) * inv, vv = dot(d, q) * inv, tt = dot(e2, q) * inv;
+    if (isfinite(uu) && isfinite(vv) && isfinite(tt)) { u = uu; v = vv; t = tt; }
 }
 
 // bpt_trace_rays: the same refinement applied to a hit buffer, so stage-level callers see what shading sees.
@@ -96,9 +98,9 @@ __global__ void k_refine_hits(SceneView s, const float4* __restrict__ rays, uint
     const float* m = s.xforms ? s.xforms + 12 * (size_t)inst : nullptr;
     const V3 v0 = load_vertex(s, prim, 0, m), v1 = load_vertex(s, prim, 1, m), v2 = load_vertex(s, prim, 2, m);
     const float4 ro = rays[2 * (size_t)i], rd = rays[2 * (size_t)i + 1];
-    float u, v;
-    barycentrics(V3{ro.x, ro.y, ro.z}, V3{rd.x, rd.y, rd.z}, v0, v1, v2, __uint_as_float(h.y), __uint_as_float(h.z), u, v);
-    h.y = __float_as_uint(u); h.z = __float_as_uint(v);
+    float u, v, t = __uint_as_float(h.x);
+    barycentrics(V3{ro.x, ro.y, ro.z}, V3{rd.x, rd.y, rd.z}, v0, v1, v2, u, v, t);
+    h.x = __float_as_uint(t); h.y = __float_as_uint(u); h.z = __float_as_uint(v);
     hits[i] = h;
 }
 
@@ -127,12 +129,11 @@ __global__ void k_shade(FrameParams p, SceneView s, uint32_t depth, PathQueue in
             const uint32_t prim = s.xforms ? h.w - inst * s.ntris : h.w;
             const float* m = s.xforms ? s.xforms + 12 * (size_t)inst : nullptr;
             const V3 v0 = load_vertex(s, prim, 0, m), v1 = load_vertex(s, prim, 1, m), v2 = load_vertex(s, prim, 2, m);
-            // The traversal kernel decides WHICH triangle is closest with the Woop form (fast, but its u,v lose
-            // bits on slivers and far origins); the barycentrics that shading consumes are re-derived here from
-            // the original vertices, so the hit position carries no traversal-format error.
+            // the barycentrics that shading consumes are derived from the original vertices, so the hit position
+            // carries no traversal-format error (the traversal kernel only names the closest triangle)
             const float4 ro = in.rays[2 * (size_t)i], rd = in.rays[2 * (size_t)i + 1];
-            float u, v;
-            barycentrics(V3{ro.x, ro.y, ro.z}, V3{rd.x, rd.y, rd.z}, v0, v1, v2, __uint_as_float(h.y), __uint_as_float(h.z), u, v);
+            float u, v, t = __uint_as_float(h.x);
+            barycentrics(V3{ro.x, ro.y, ro.z}, V3{rd.x, rd.y, rd.z}, v0, v1, v2, u, v, t);
             const float b0 = 1.0f - u - v;                           // closesthit.rchit:56
             const V3 pos = v0 * b0 + v1 * u + v2 * v;                // :57
             const V3 nrm = -normalize(cross(v1 - v0, v2 - v0));      // :58, :43-48

@@ -5,6 +5,14 @@
 constexpr int kTraceBlock = 1024;      // one persistent CTA of 32 warps per SM
 constexpr int kTraceSmemStack = 8;     // per-lane stack entries held in shared memory
 constexpr int kTraceMaxSmem = 227 * 1024;
+constexpr int kTraceSmemFixed = 16 + 2048;  // mbarrier + octant permutation table
+constexpr int kTraceLocalStack = 40;   // overflow entries per lane in local memory
+// every node step pushes at most one sibling group and one parked triangle group
+constexpr int kTraceMaxDepth = (kTraceSmemStack + kTraceLocalStack) / 2 - 1;
+
+// device counters (bpt_stats): rays always; the rest only from the instrumented kernel
+enum { BPT_STAT_RAYS = 0, BPT_STAT_NODES, BPT_STAT_TRIS, BPT_STAT_WARP_ITERS, BPT_STAT_WARP_NODE_STEPS,
+       BPT_STAT_WARP_TRI_STEPS, BPT_STAT_LANE_ITERS, BPT_STAT_COUNT };
 
 struct TraceArgs {
     const float4* rays;            // 2 per ray: {o, tmin} {d, tmax}
@@ -16,9 +24,8 @@ struct TraceArgs {
     const uint32_t* prim_index;    // leaf slot -> primitive id
     uint32_t top_nodes;            // BFS prefix staged into shared memory
     uint32_t top_tris;             // leading triangles staged into shared memory
-    unsigned long long* stat_rays; // += ray count (may be null)
-    unsigned long long* stat_nodes;
-    unsigned long long* stat_tris;
+    uint32_t magic;                // 0x47000000 (float 32768): byte->float permute constant, see trace.cu byte_f
+    unsigned long long* stat;      // BPT_STAT_* counters (may be null when not counting: only [RAYS] is touched)
 };
 
 size_t trace_smem_bytes(uint32_t top_nodes, uint32_t top_tris);

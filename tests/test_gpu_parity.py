@@ -37,9 +37,13 @@ def compare_hits(gpu, ref, tris_world, max_mismatch=2e-4, tol=2e-4):
     frac = 1.0 - same.mean()
     assert frac <= max_mismatch, f"{(~same).sum()} of {len(ref)} rays disagree on the primitive"
     hit = same & (ref["prim"] != O.MISS)
-    np.testing.assert_allclose(gpu["t"][hit], ref["t"][hit], rtol=tol, atol=tol)
-    np.testing.assert_allclose(gpu["u"][hit], ref["u"][hit], atol=tol)
-    np.testing.assert_allclose(gpu["v"][hit], ref["v"][hit], atol=tol)
+    # f32 Moeller-Trumbore against the f64 oracle: a ray that grazes its triangle (|d.n| tiny) amplifies the f32
+    # rounding of the determinant, so up to 1e-4 of the hits may exceed `tol`, and none may exceed 10 * tol
+    for name, rtol in (("t", tol), ("u", 0.0), ("v", 0.0)):
+        g, r = gpu[name][hit].astype(np.float64), ref[name][hit].astype(np.float64)
+        err = np.abs(g - r) - rtol * np.abs(r)
+        assert (err > tol).mean() <= 1e-4, (name, (err > tol).sum(), len(err))
+        assert err.max() <= 10 * tol, (name, err.max())
     return frac
 
 
@@ -120,30 +124,33 @@ def check_build_invariants(pt, verts, idx):
             scale = np.ldexp(np.float64(1.0), nd["e"].astype(np.int32) - 127)
             p = nd["p"].astype(np.float64)
             rank = 0
+            valid = int(nd["valid"])
+            leaf_rank = 0  # triangles of a node are dense in (slot, k) order from tri_base
             for s in range(8):
-                m = int(nd["meta"][s])
-                if m == 0:
+                inner = (valid >> (24 + s)) & 1
+                unary = (valid >> (3 * s)) & 7
+                if not inner and not unary:
                     continue
+                assert not (inner and unary) and unary in (0, 1, 3, 7)
                 qlo = np.array([nd["qlox"][s], nd["qloy"][s], nd["qloz"][s]], np.float64)
                 qhi = np.array([nd["qhix"][s], nd["qhiy"][s], nd["qhiz"][s]], np.float64)
                 blo, bhi = p + qlo * scale, p + qhi * scale
                 if plo is not None:  # both boxes are conservative supersets of the same exact box, each on its own
                     # node's grid, so they nest only up to one quantisation step of this node (+ the padding)
                     assert np.all(blo >= plo - scale - 1e-4) and np.all(bhi <= phi + scale + 1e-4)
-                if (m & 0x1F) >= 24 and (m >> 5) == 1:
-                    assert (nd["imask"] >> s) & 1 and (m & 0x1F) == 24 + s
+                if inner:
                     nxt.append((int(nd["child_base"]) + rank, blo, bhi))
                     rank += 1
                 else:
-                    assert not (nd["imask"] >> s) & 1
-                    cnt = {1: 1, 3: 2, 7: 3}[m >> 5]
-                    off = m & 0x1F
+                    cnt = {1: 1, 3: 2, 7: 3}[unary]
                     for j in range(cnt):
-                        slot = int(nd["tri_base"]) + off + j
+                        slot = int(nd["tri_base"]) + leaf_rank + j
                         prim = tri_index[slot]
                         tri_seen[prim] += 1
-                        assert np.all(blo <= lo[prim]) and np.all(bhi >= hi[prim])  # quantised box contains the triangle
-            assert rank == bin(int(nd["imask"])).count("1")
+                        # quantised box contains the triangle with the margin the traversal kernel relies on
+                        assert np.all(blo <= lo[prim] - scale / 256) and np.all(bhi >= hi[prim] + scale / 256)
+                    leaf_rank += cnt
+            assert rank == bin(valid >> 24).count("1")
         level = nxt
     assert np.all(visited_nodes == 1) and np.all(tri_seen == 1)
     assert depth == info.max_depth8
