@@ -108,12 +108,13 @@ typedef struct bpt_stats {
 typedef struct bpt_accel_info {
     uint32_t num_tris;        /* triangles in the bottom-level structure                    */
     uint32_t num_instances;
-    uint32_t num_nodes8;      /* BVH8 nodes (80 B each)                                     */
+    uint32_t num_nodes8;      /* BVH8 nodes (96 B each)                                     */
     uint32_t num_binary_nodes;/* LBVH internal nodes (N-1)                                  */
-    uint32_t top_nodes_smem;  /* nodes of the BFS prefix staged into shared memory by TMA   */
+    uint32_t top_nodes_smem;  /* nodes staged into shared memory by TMA: all of them for a
+                                 scene small enough (with its triangles), else 0            */
     uint32_t max_depth8;      /* depth of the BVH8                                          */
-    uint64_t bytes_nodes;     /* num_nodes8 * 80                                            */
-    uint64_t bytes_tris;      /* num_tris * 48 (Woop)                                       */
+    uint64_t bytes_nodes;     /* num_nodes8 * 96                                            */
+    uint64_t bytes_tris;      /* num_tris * 64 (Woop rows + primitive id)                   */
     uint32_t num_tlas_nodes8; /* two-level builds: nodes in the instance BVH8               */
     uint32_t reserved;
 } bpt_accel_info;
@@ -121,10 +122,13 @@ typedef struct bpt_accel_info {
 /* options for bpt_set_option */
 #define BPT_OPT_PROFILE          1 /* 1: bracket every traversal launch with CUDA events     */
 #define BPT_OPT_COUNT_TRAVERSAL  2 /* 1: use the instrumented traversal kernel (nodes/tris)  */
-#define BPT_OPT_SMEM_TOP_NODES   3 /* max BVH8 nodes staged into shared memory (0 = none)    */
+#define BPT_OPT_SMEM_TOP_NODES   3 /* stage the whole BVH in shared memory when it has at most
+                                      this many nodes and fits (0 = never stage)             */
 #define BPT_OPT_TRACE_CTAS_PER_SM 4 /* persistent grid = 148 * this                          */
 #define BPT_OPT_SORT_RAYS        5 /* reserved                                               */
 #define BPT_OPT_USE_GRAPH        6 /* 1: replay a captured CUDA graph per sample pass        */
+#define BPT_OPT_TRACE_REFILL_BELOW 8     /* traversal: refill a warp when fewer lanes than this are live */
+#define BPT_OPT_TRACE_STEPS_PER_REFILL 9 /* traversal: loop iterations between two refill votes           */
 
 /* ---- lifecycle: replaces Context ctor/dtor (main.cpp:74-267) ------------------------- */
 int  bpt_abi_version(void);
@@ -198,8 +202,8 @@ int bpt_generate_rays(bpt_context* ctx, const bpt_params* p, uint32_t sample_in_
                       float* rays, uint32_t* seeds);
 
 /* ---- BVH introspection for the build-invariant tests (copies device -> host) --------- */
-/* nodes8: num_nodes8 * 80 bytes; tri_index: num_tris uint32 (leaf order -> primitive);
- * woop: num_tris*12 floats. Any pointer may be NULL. */
+/* nodes8: num_nodes8 * 96 bytes; tri_index: num_tris uint32 (leaf order -> primitive);
+ * woop: num_tris * 64 bytes (12 floats of Woop rows, the primitive id, 3 pad words). Any pointer may be NULL. */
 int bpt_download_accel(bpt_context* ctx, void* nodes8, uint32_t* tri_index, float* woop);
 /* the uploaded (or device-generated) mesh, as bpt_upload_mesh would have received it. */
 int bpt_download_mesh(bpt_context* ctx, float* verts, uint32_t* indices, float* faces);

@@ -22,6 +22,7 @@ MISS = 0xFFFFFFFF
 ACCUM_FLOAT4, ACCUM_RGBA8 = 0, 1
 SAMPLER_UNIFORM, SAMPLER_COSINE = 0, 1
 OPT_PROFILE, OPT_COUNT_TRAVERSAL, OPT_SMEM_TOP_NODES, OPT_TRACE_CTAS_PER_SM = 1, 2, 3, 4
+OPT_TRACE_REFILL_BELOW, OPT_TRACE_STEPS_PER_REFILL = 8, 9
 NCCL_UNIQUE_ID_BYTES = 128
 
 
@@ -65,10 +66,11 @@ class AccelInfo(C.Structure):
 
 HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4")])
 NODE8_DTYPE = np.dtype([
-    ("p", "<f4", 3), ("e", "u1", 3), ("pad0", "u1"), ("child_base", "<u4"), ("tri_base", "<u4"), ("valid", "<u4"),
-    ("pad1", "<u4"),
-    ("qlox", "u1", 8), ("qloy", "u1", 8), ("qloz", "u1", 8), ("qhix", "u1", 8), ("qhiy", "u1", 8), ("qhiz", "u1", 8)])
-assert NODE8_DTYPE.itemsize == 80
+    ("p", "<f4", 3), ("s", "<f4", 3), ("child_base", "<u4"), ("tri_base", "<u4"), ("valid", "<u4"), ("pad0", "<u4"),
+    ("qlox", "u1", 8), ("qloy", "u1", 8), ("qloz", "u1", 8), ("qhix", "u1", 8), ("qhiy", "u1", 8), ("qhiz", "u1", 8),
+    ("pad1", "<u4", 2)])
+WOOP_DTYPE = np.dtype([("rows", "<f4", (3, 4)), ("prim", "<u4"), ("pad", "<u4", 3)])
+assert NODE8_DTYPE.itemsize == 96 and WOOP_DTYPE.itemsize == 64
 
 # every symbol include/bpt.h declares: (restype, argtypes)
 _vp, _u32, _i32, _sz = C.c_void_p, C.c_uint32, C.c_int, C.c_size_t
@@ -265,7 +267,7 @@ class PathTracer:
         info = self.accel_info()
         nodes = np.zeros(info.num_nodes8, NODE8_DTYPE)
         tri_index = np.zeros(info.num_tris, np.uint32)
-        woop = np.zeros((info.num_tris, 3, 4), np.float32)
+        woop = np.zeros(info.num_tris, WOOP_DTYPE)
         self._check(self._L.bpt_download_accel(self._h, _ptr(nodes), _ptr(tri_index), _ptr(woop)))
         return nodes, tri_index, woop
 

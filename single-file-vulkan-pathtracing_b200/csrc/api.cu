@@ -39,8 +39,8 @@ struct bpt_context {
     // acceleration structure
     Bvh8 blas;
     WoopTri* d_woop = nullptr;
-    bool built = false;
-    uint32_t top_nodes = 0, top_tris = 0;
+    bool built = false, built_nodes_ok = false;
+    bool staged = false;  // the traversal kernel instance that holds the whole BVH in shared memory is in use
 
     // wavefront buffers
     size_t cap_paths = 0;
@@ -56,8 +56,9 @@ struct bpt_context {
 
     // options
     bool profile = false, count = false;
-    int64_t opt_top_nodes = 584;  // 1 + 8 + 64 + 511: about four full levels (46 KB)
+    int64_t opt_stage_max_nodes = 1 << 20;  // BPT_OPT_SMEM_TOP_NODES: 0 disables shared-memory staging
     int ctas_per_sm = 1;
+    int refill_below = 24, steps_per_refill = 4;
 
     // statistics
     bpt_stats stats{};
@@ -178,10 +179,10 @@ int row_major_image(bpt_context* c, const float4** out) {
 TraceArgs make_trace_args(bpt_context* c, const float4* rays, uint4* hits, const uint32_t* count, uint32_t* fetch) {
     TraceArgs a;
     a.rays = rays; a.hits = hits; a.count_ptr = count; a.fetch_ctr = fetch;
-    a.nodes = reinterpret_cast<const uint4*>(c->blas.nodes);
-    a.woop = reinterpret_cast<const float4*>(c->d_woop);
-    a.prim_index = c->blas.prim_index;
-    a.top_nodes = c->top_nodes; a.top_tris = c->top_tris;
+    a.nodes = c->blas.nodes;
+    a.tris = c->d_woop;
+    a.num_nodes = c->blas.num_nodes; a.num_tris = c->ntris;
+    a.refill_below = c->refill_below; a.steps_per_refill = c->steps_per_refill;
     a.magic = 0x47000000u;
     a.stat = c->d_stats;
     return a;
@@ -193,13 +194,19 @@ void launch_trace(bpt_context* c, const TraceArgs& a) {
         e0 = get_event(c); e1 = get_event(c);
         cudaEventRecord(e0, c->stream);
     }
-    trace_launch(a, (unsigned)(c->num_sms * c->ctas_per_sm), c->count, c->stream);
+    trace_launch(a, (unsigned)(c->num_sms * c->ctas_per_sm), c->staged, c->count, c->stream);
     if (c->profile) {
         cudaEventRecord(e1, c->stream);
         c->trace_events.emplace_back(e0, e1);
     }
     c->stats.trace_launches++;
     c->stats.kernel_launches++;
+}
+
+// Small scenes run the traversal instance that keeps the whole BVH in shared memory (TMA-staged once per CTA).
+void plan_staging(bpt_context* c) {
+    c->staged = c->built_nodes_ok && c->blas.num_nodes <= (uint64_t)c->opt_stage_max_nodes &&
+                trace_smem_bytes(c->blas.num_nodes, c->ntris) <= (size_t)kTraceMaxSmem;
 }
 
 }  // namespace
@@ -284,12 +291,17 @@ int bpt_set_option(bpt_context* c, int option, int64_t value) {
         case BPT_OPT_PROFILE: c->profile = value != 0; return BPT_OK;
         case BPT_OPT_COUNT_TRAVERSAL: c->count = value != 0; return BPT_OK;
         case BPT_OPT_SMEM_TOP_NODES:
-            if (value < 0) return bpt_fail(c, BPT_E_INVALID, "top node count must be >= 0");
-            c->opt_top_nodes = value;
-            if (c->built) {
-                uint32_t cap = (uint32_t)((kTraceMaxSmem - trace_smem_bytes(0, c->top_tris)) / 80);
-                c->top_nodes = (uint32_t)std::min<int64_t>(std::min<int64_t>(value, c->blas.num_nodes), cap);
-            }
+            if (value < 0) return bpt_fail(c, BPT_E_INVALID, "node count must be >= 0");
+            c->opt_stage_max_nodes = value;
+            if (c->built) plan_staging(c);
+            return BPT_OK;
+        case BPT_OPT_TRACE_REFILL_BELOW:
+            if (value < 1 || value > 32) return bpt_fail(c, BPT_E_INVALID, "refill threshold must be in [1,32]");
+            c->refill_below = (int)value;
+            return BPT_OK;
+        case BPT_OPT_TRACE_STEPS_PER_REFILL:
+            if (value < 1 || value > 64) return bpt_fail(c, BPT_E_INVALID, "steps per refill must be in [1,64]");
+            c->steps_per_refill = (int)value;
             return BPT_OK;
         case BPT_OPT_TRACE_CTAS_PER_SM:
             if (value != 1) return bpt_fail(c, BPT_E_INVALID, "the traversal kernel runs one 1024-thread CTA per SM");
@@ -365,7 +377,7 @@ int bpt_build_accel(bpt_context* c) {
     if (!c) return BPT_E_INVALID;
     if (c->ntris == 0) return bpt_fail(c, BPT_E_STATE, "bpt_build_accel before bpt_upload_mesh");
     cudaSetDevice(c->device);
-    c->built = false;
+    c->built = false; c->built_nodes_ok = false; c->staged = false;
     cudaEvent_t e0 = get_event(c), e1 = get_event(c);
     cudaEventRecord(e0, c->stream);
     BPT_CUDA_TRY(c, bvh8_alloc(c->blas, c->ntris));
@@ -377,7 +389,7 @@ int bpt_build_accel(bpt_context* c) {
         return bpt_fail(c, BPT_E_STATE, "BVH8 depth %u exceeds the traversal stack", c->blas.depth);
     cudaFree(c->d_woop);
     c->d_woop = nullptr;
-    BPT_CUDA_TRY(c, cudaMalloc(&c->d_woop, (size_t)c->ntris * sizeof(WoopTri) + 16));
+    BPT_CUDA_TRY(c, cudaMalloc(&c->d_woop, (size_t)c->ntris * sizeof(WoopTri) + 32));
     bvh8_launch_woop(c->blas, c->d_verts, c->d_idx, c->d_woop, c->stream);
     cudaEventRecord(e1, c->stream);
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -386,10 +398,8 @@ int bpt_build_accel(bpt_context* c) {
     cudaEventElapsedTime(&ms, e0, e1);
     c->stats.build_ms = ms;
     c->event_pool.push_back(e0); c->event_pool.push_back(e1);
-    // staging plan: whole triangle array if it is tiny, then the BFS prefix of the nodes
-    c->top_tris = (size_t)c->ntris * 48 <= 32768 ? c->ntris : 0;
-    uint32_t cap = (uint32_t)((kTraceMaxSmem - trace_smem_bytes(0, c->top_tris)) / 80);
-    c->top_nodes = (uint32_t)std::min<int64_t>(std::min<int64_t>(c->opt_top_nodes, c->blas.num_nodes), cap);
+    c->built_nodes_ok = true;
+    plan_staging(c);
     c->built = true;
     return BPT_OK;
 }
@@ -402,10 +412,10 @@ int bpt_accel_info_get(bpt_context* c, bpt_accel_info* out) {
     out->num_instances = c->ninst;
     out->num_nodes8 = c->blas.num_nodes;
     out->num_binary_nodes = c->ntris - 1;
-    out->top_nodes_smem = c->top_nodes;
+    out->top_nodes_smem = c->staged ? c->blas.num_nodes : 0;
     out->max_depth8 = c->blas.depth;
-    out->bytes_nodes = (uint64_t)c->blas.num_nodes * 80;
-    out->bytes_tris = (uint64_t)c->ntris * 48;
+    out->bytes_nodes = (uint64_t)c->blas.num_nodes * BPT_NODE_BYTES;
+    out->bytes_tris = (uint64_t)c->ntris * BPT_TRI_BYTES;
     return BPT_OK;
 }
 
@@ -601,9 +611,9 @@ int bpt_download_accel(bpt_context* c, void* nodes8, uint32_t* tri_index, float*
     if (!c->built) return bpt_fail(c, BPT_E_STATE, "no acceleration structure built");
     cudaSetDevice(c->device);
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    if (nodes8) BPT_CUDA_TRY(c, cudaMemcpy(nodes8, c->blas.nodes, (size_t)c->blas.num_nodes * 80, cudaMemcpyDeviceToHost));
+    if (nodes8) BPT_CUDA_TRY(c, cudaMemcpy(nodes8, c->blas.nodes, (size_t)c->blas.num_nodes * BPT_NODE_BYTES, cudaMemcpyDeviceToHost));
     if (tri_index) BPT_CUDA_TRY(c, cudaMemcpy(tri_index, c->blas.prim_index, (size_t)c->ntris * 4, cudaMemcpyDeviceToHost));
-    if (woop) BPT_CUDA_TRY(c, cudaMemcpy(woop, c->d_woop, (size_t)c->ntris * 48, cudaMemcpyDeviceToHost));
+    if (woop) BPT_CUDA_TRY(c, cudaMemcpy(woop, c->d_woop, (size_t)c->ntris * BPT_TRI_BYTES, cudaMemcpyDeviceToHost));
     return BPT_OK;
 }
 

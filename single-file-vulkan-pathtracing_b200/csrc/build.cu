@@ -8,8 +8,8 @@
 //   K4  lbvh_hierarchy   Karras 2012: one thread per internal node, clz on key XOR
 //   K5  lbvh_refit       bottom-up AABBs with per-node arrival counters
 //   K6  bvh8_collapse    binary -> 8-wide, greedy largest-area opening, octant slot assignment,
-//                        quantisation to the 80-byte Node8 (level-synchronous, BFS node order)
-//   K7  woop_transform   48-byte unit-triangle transforms in leaf order
+//                        quantisation to the 96-byte Node8 (level-synchronous, BFS node order)
+//   K7  woop_transform   64-byte records (unit-triangle transform + primitive id) in leaf order
 // Everything is generic over "primitives with an AABB" so the same code builds the instance-level
 // BVH8 of two-level scenes.
 #include <cfloat>
@@ -317,7 +317,7 @@ __global__ void k_bvh8_collapse(CollapseArgs a) {
 
     Node8 nd;
     nd.px = px; nd.py = py; nd.pz = pz;
-    nd.ex = (uint8_t)(ex + 127); nd.ey = (uint8_t)(ey + 127); nd.ez = (uint8_t)(ez + 127);
+    nd.sx = sx; nd.sy = sy; nd.sz = sz;
     nd.child_base = child_base;
     nd.tri_base = tri_base;
     uint32_t valid = 0, int_rank = 0, leaf_off = 0;
@@ -362,12 +362,11 @@ __global__ void k_bvh8_collapse(CollapseArgs a) {
         }
     }
     nd.valid = valid;
-    nd.pad0 = 0;
-    nd.pad1 = 0;
+    nd.pad0 = nd.pad1 = nd.pad2 = 0;
     uint4* dst = reinterpret_cast<uint4*>(a.nodes + w);
     const uint4* srcw = reinterpret_cast<const uint4*>(&nd);
 #pragma unroll
-    for (int q = 0; q < 5; ++q) dst[q] = srcw[q];
+    for (int q = 0; q < 6; ++q) dst[q] = srcw[q];
 }
 
 // K7: Woop transform of the triangle in leaf slot s. Rows are computed in double and rounded once.
@@ -387,6 +386,7 @@ __global__ void k_woop(const float* __restrict__ verts, const uint32_t* __restri
     double nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
     double det = nx * nx + ny * ny + nz * nz;  // det [e1 e2 n]
     WoopTri w;
+    w.prim = prim; w.pad0 = w.pad1 = w.pad2 = 0;
     if (!(det > 0.0) || !isfinite(det)) {
         w.ru = w.rv = w.rw = make_float4(0.f, 0.f, 0.f, 0.f);  // degenerate: d'.z == 0 -> never hit
     } else {

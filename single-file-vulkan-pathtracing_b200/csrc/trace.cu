@@ -7,38 +7,44 @@
 // Design (B200):
 //   * one persistent CTA per SM (grid = #SMs * ctas_per_sm); warps pull rays from a global counter
 //     and refill idle lanes (ballot + popc prefix) whenever fewer than kRefillBelow lanes are live
-//   * the BFS prefix of the node array (top of the tree) and the first triangles are staged once
-//     per CTA into shared memory with TMA bulk copies (cp.async.bulk + mbarrier complete_tx);
-//     deeper nodes / triangles are read with 128-bit loads through L1/L2
+//   * small scenes are staged once per CTA into shared memory with TMA bulk copies (cp.async.bulk +
+//     mbarrier complete_tx); big scenes read nodes / triangles with 256-bit loads through L1/L2
 //   * per-lane traversal stack: kSmemStack 8-byte entries in shared memory (thread-interleaved,
 //     conflict-free), overflow in local memory
 //   * rays are 2 x float4, hits 1 x uint4 -> all record traffic is 128-bit
 //   * traversal order: octant-permuted slot priority (Ylitie et al. 2017), node groups and
 //     triangle groups share one 64-bit stack entry format
 //
-// Instruction budget. The kernel is issue-bound (profiles/r1a_*: 72 % issue-active, ~0 DRAM
-// stall), and on sm_100 the ALU pipe (PRMT/LOP3/FMNMX/SEL) runs at half the rate of the FMA pipe,
-// so the node step is written to spend as few ALU-pipe instructions as possible:
-//   * a quantised plane byte q becomes the float 32768+q with ONE byte-permute (magic word from the
-//     constant bank, selector immediate); the 32768 bias is folded into the per-axis offset with one
-//     FMA per axis instead of one subtraction per plane (the fold costs <= 2^-9 of a quantisation
-//     step; the builder quantises with a 2^-7-step margin, build.cu)
-//   * a child that passes the slab test ORs one immediate into the hit word (its internal-child bit
-//     and its three triangle bits); one AND with the node's `valid` word then yields the internal
-//     hits (top byte, slot order) and the triangle hits (low 24 bits) — no per-child meta decoding
-//   * the octant permutation of the internal hits (bit p <- slot p ^ oct) is one byte lookup in a
-//     2 KB shared-memory table (LSU pipe) instead of three conditional bit-swap stages
-//   * triangles are software-pipelined: every loop iteration does at most ONE node step and ONE
-//     triangle test per lane; a lane keeps descending (and popping node groups) while its triangle
-//     group drains, so the triangle test runs once per iteration with every lane that has a
-//     pending triangle instead of a divergent inner loop that ran at 2/32 lanes
+// What bounds it. The kernel moves almost no DRAM bytes (L2 hit rate 76-85 %); it is bound by instruction issue and
+// by L1 wavefronts (profiles/: l1tex throughput 77 %, issue 68 %, ALU pipe 56 %), and on sm_100 the ALU pipe
+// (PRMT/LOP3/FMNMX/SEL) runs at half the rate of the FMA pipe. Hence:
+//   * nodes are 96 bytes = three 256-bit loads, triangles 64 bytes = two (LDG.E.256): every lane walks its own
+//     node, so a load instruction costs one L1 wavefront per lane whatever its width
+//   * a quantised plane byte q becomes the float 32768+q with ONE byte-permute (magic word from the constant bank,
+//     selector immediate); the 32768 bias is folded into the per-axis offset with one FMA per axis instead of one
+//     subtraction per plane (the fold costs <= 2^-9 of a quantisation step; the builder quantises with a 2^-7-step
+//     margin, build.cu)
+//   * a child that passes the slab test ORs one immediate into the hit word (its internal-child bit and its three
+//     triangle bits); one AND with the node's `valid` word then yields the internal hits (top byte, slot order) and
+//     the triangle hits (low 24 bits) — no per-child meta decoding
+//   * the octant permutation of the internal hits (bit p <- slot p ^ oct) is one 64-bit lookup in a 2 KB
+//     shared-memory table (LSU pipe; the row of a hit byte holds its 8 permutations, so lanes with equal hit bytes
+//     broadcast) instead of three conditional bit-swap stages
+//   * triangles are software-pipelined: every loop iteration does at most ONE node step and ONE triangle test per
+//     lane; a lane keeps descending (and popping node groups) while its triangle group drains, so the triangle test
+//     runs once per iteration with every lane that has a pending triangle instead of a divergent inner loop that
+//     ran at 2/32 lanes
+//   * the whole warp runs every phase of the loop behind a __syncwarp(): without it the lanes that popped and the
+//     lanes that did not reach the node step as two groups and the node step runs twice per iteration at 12/32 lanes
+//   * small scenes (Cornell box: every node and triangle fits) run the STAGED instance: the BVH is copied into
+//     shared memory once per CTA by TMA bulk copies (cp.async.bulk + mbarrier) and never touched in global memory
+//     again; big scenes run the global instance (staging only the top of the tree bought nothing measurable: its
+//     nodes are L1-resident anyway, and the dual shared/global path cost issue slots)
 #include "trace.cuh"
 
 namespace {
 
-constexpr int kRefillBelow = 24;   // refill when fewer live lanes than this (>= 9 rays per atomic)
 constexpr int kLocalStack = kTraceLocalStack;
-constexpr int kStepsPerRefill = 4; // traversal iterations between two refill votes
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---------------------------------------------------------------- TMA / mbarrier (PTX)
@@ -70,6 +76,37 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// Shared memory through 32-bit shared-window addresses: with C++ pointers into the dynamic array ptxas rebuilds the
+// generic window base (S2R SR_CgaCtaId + LEA) in front of every access of the traversal loop.
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// 256-bit read-only global load (LDG.E.256, sm_100+): p is 32-byte aligned
+struct U8 { uint4 lo, hi; };
+__device__ __forceinline__ U8 ldg256(const void* p) {
+    U8 v;
+    asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"  // volatile: issue where written
+        : "=r"(v.lo.x), "=r"(v.lo.y), "=r"(v.lo.z), "=r"(v.lo.w), "=r"(v.hi.x), "=r"(v.hi.y), "=r"(v.hi.z), "=r"(v.hi.w)
+        : "l"(p));
+    return v;
+}
+__device__ __forceinline__ U8 lds256(uint32_t addr) { return U8{lds128(addr), lds128(addr + 16u)}; }
+
 // Byte J of w as the float 32768 + byte (exact): bytes {0, w.bJ, 0, 0x47}. `magic` (0x47000000) arrives as a kernel
 // argument so that it stays a constant-bank operand and the selector is the instruction's immediate — when both are
 // compile-time constants ptxas keeps the magic as the immediate and burns a register move per selector.
@@ -83,7 +120,7 @@ constexpr float kByteBias = 32768.0f;
 
 struct RayState {
     float ox, oy, oz, dx, dy, dz, idx, idy, idz, tmin, tbest;
-    uint32_t htri;    // leaf slot of the closest hit, BPT_MISS if none
+    uint32_t hprim;   // primitive of the closest hit, BPT_MISS if none
     uint32_t oct;     // dx>=0?4:0 | dy>=0?2:0 | dz>=0?1:0: slot s is visited with priority s ^ oct
 };
 
@@ -108,71 +145,75 @@ __device__ __forceinline__ uint32_t test_quad(uint32_t xn, uint32_t yn, uint32_t
     return hit;
 }
 
-template <int BLOCK, int SSTACK, bool COUNT>
+template <int BLOCK, int SSTACK, bool STAGED, bool COUNT>
 __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    uint8_t* slut = smem_raw + 16;  // slut[oct * 256 + b]: bit p = bit (p ^ oct) of b
+    uint2* slut = reinterpret_cast<uint2*>(smem_raw + 16);  // byte o of slut[b]: bit p = bit (p ^ o) of b
     uint2* sstack = reinterpret_cast<uint2*>(smem_raw + kTraceSmemFixed);
-    uint4* snodes = reinterpret_cast<uint4*>(smem_raw + kTraceSmemFixed + (size_t)SSTACK * BLOCK * sizeof(uint2));
-    float4* stris = reinterpret_cast<float4*>(snodes + 5 * (size_t)a.top_nodes);
+    unsigned char* snodes = smem_raw + kTraceSmemFixed + (size_t)SSTACK * BLOCK * sizeof(uint2);  // STAGED only
+    unsigned char* stris = snodes + (size_t)a.num_nodes * BPT_NODE_BYTES;
 
     const uint32_t nrays = *a.count_ptr;
     if (nrays == 0u) return;  // uniform across the grid: an exhausted bounce costs one launch and nothing else
 
-    // ---- stage the top of the tree into shared memory with TMA bulk copies
-    const uint32_t node_bytes = a.top_nodes * 80u, tri_bytes = a.top_tris * 48u;
-    if (node_bytes + tri_bytes) {
+    // ---- STAGED: the whole BVH (nodes, then triangles) moves into shared memory with TMA bulk copies
+    if (STAGED) {
+        const uint32_t node_bytes = a.num_nodes * BPT_NODE_BYTES, tri_bytes = a.num_tris * BPT_TRI_BYTES;
         if (threadIdx.x == 0) mbar_init(bar, 1);
         __syncthreads();
         if (threadIdx.x == 0) {
             mbar_expect_tx(bar, node_bytes + tri_bytes);
             constexpr uint32_t kChunk = 32768u;
             for (uint32_t off = 0; off < node_bytes; off += kChunk)
-                tma_bulk_g2s(reinterpret_cast<unsigned char*>(snodes) + off,
-                             reinterpret_cast<const unsigned char*>(a.nodes) + off, min(kChunk, node_bytes - off), bar);
+                tma_bulk_g2s(snodes + off, reinterpret_cast<const unsigned char*>(a.nodes) + off, min(kChunk, node_bytes - off), bar);
             for (uint32_t off = 0; off < tri_bytes; off += kChunk)
-                tma_bulk_g2s(reinterpret_cast<unsigned char*>(stris) + off,
-                             reinterpret_cast<const unsigned char*>(a.woop) + off, min(kChunk, tri_bytes - off), bar);
+                tma_bulk_g2s(stris + off, reinterpret_cast<const unsigned char*>(a.tris) + off, min(kChunk, tri_bytes - off), bar);
         }
         mbar_wait(bar, 0);
     }
-
-    for (uint32_t i = threadIdx.x; i < 2048u; i += BLOCK) {
-        const uint32_t oct = i >> 8, b = i & 0xffu;
-        uint32_t p = 0;
+    for (uint32_t b = threadIdx.x; b < 256u; b += BLOCK) {
+        uint32_t w[2] = {0u, 0u};
 #pragma unroll
-        for (uint32_t k = 0; k < 8; ++k) p |= ((b >> (k ^ oct)) & 1u) << k;
-        slut[i] = (uint8_t)p;
+        for (uint32_t o = 0; o < 8; ++o) {
+            uint32_t p = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < 8; ++k) p |= ((b >> (k ^ o)) & 1u) << k;
+            w[o >> 2] |= p << (8 * (o & 3));
+        }
+        slut[b] = make_uint2(w[0], w[1]);
     }
     __syncthreads();
 
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.stat) atomicAdd(a.stat + BPT_STAT_RAYS, (unsigned long long)nrays);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
-    uint2* mystack = sstack + threadIdx.x;
+    const uint32_t stack_a = smem_u32(sstack + threadIdx.x);  // entry i of this lane: stack_a + i * BLOCK * 8
+    const uint32_t snodes_a = smem_u32(snodes), stris_a = smem_u32(stris), slut_a = smem_u32(slut);
     uint2 lstack[kLocalStack];
     const uint32_t magic = a.magic;
+    const int refill_below = a.refill_below, steps_per_refill = a.steps_per_refill;
 
     RayState r;
     uint2 G = make_uint2(0u, 0u);  // node group: x = first internal child, y = hits by priority << 24 | internal mask
     uint2 T = make_uint2(0u, 0u);  // triangle group: x = node the triangles belong to, y = hit bits (valid layout)
     uint32_t Tb = 0u, Tv = 0u;     // tri_base and valid word of node T.x
+    uint32_t octsel = 0u;          // byte-permute selector that picks byte `oct` of a slut row into byte 3
     int sp = 0;
     uint32_t ray_idx = 0;
     bool active = false, exhausted = false;
     unsigned long long cnt_nodes = 0, cnt_tris = 0, cnt_witer = 0, cnt_wnode = 0, cnt_wtri = 0, cnt_liter = 0;
 
-#define BPT_PUSH(E)                                                               \
-    {                                                                             \
-        if (sp < SSTACK) mystack[sp * BLOCK] = (E); else lstack[sp - SSTACK] = (E); \
-        ++sp;                                                                     \
+#define BPT_PUSH(E)                                                                               \
+    {                                                                                             \
+        if (sp < SSTACK) sts64(stack_a + sp * (BLOCK * 8), (E)); else lstack[sp - SSTACK] = (E);  \
+        ++sp;                                                                                     \
     }
 #define BPT_LEADER() ((__activemask() & lt) == 0u)
 
     for (;;) {
         unsigned actmask = __ballot_sync(FULL, active);
-        if (!exhausted && __popc(actmask) < kRefillBelow) {
+        if (!exhausted && __popc(actmask) < refill_below) {
             const unsigned idle = ~actmask;
             const int nidle = __popc(idle);
             uint32_t base = 0;
@@ -191,7 +232,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                     r.idy = 1.0f / (fabsf(rd.y) > eps ? rd.y : copysignf(eps, rd.y));
                     r.idz = 1.0f / (fabsf(rd.z) > eps ? rd.z : copysignf(eps, rd.z));
                     r.oct = (rd.x >= 0.f ? 4u : 0u) | (rd.y >= 0.f ? 2u : 0u) | (rd.z >= 0.f ? 1u : 0u);
-                    r.htri = BPT_MISS;
+                    octsel = r.oct << 12;
+                    r.hprim = BPT_MISS;
                     G = make_uint2(0u, 0x80000000u);  // root: node 0 through priority bit 31, internal mask 0
                     T = make_uint2(0u, 0u);
                     sp = 0;
@@ -204,115 +246,117 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
         if (actmask == 0u) break;
 
         // Every lane of the warp runs the loop below, live or not (an idle lane has no node bits, no triangle bits and
-        // an empty stack), and the warp reconverges with __syncwarp() in front of every phase: without it the lanes
-        // that popped and the lanes that did not reach the node step as two separate groups, and the ~270-instruction
-        // node step runs twice per iteration at 12/32 lanes (measured; profiles/).
-        {
+        // an empty stack), and the warp reconverges with __syncwarp() in front of every phase.
 #pragma unroll 1
-            for (int it = 0; it < kStepsPerRefill; ++it) {
-                if (COUNT) {
-                    const unsigned m = __ballot_sync(FULL, active);
-                    if (lane == 0 && m) ++cnt_witer;
-                    if (active) ++cnt_liter;
-                }
-                // ---------------- pop when out of node work: a node group always, a parked triangle group only when
-                //                  none is draining (it stays on the stack until then)
-                if (active && !(G.y & 0xff000000u) && sp > 0) {
-                    const uint2 e = sp <= SSTACK ? mystack[(sp - 1) * BLOCK] : lstack[sp - 1 - SSTACK];
-                    if (e.y & 0xff000000u) { G = e; --sp; }
-                    else if (T.y == 0u) {
-                        T = e; --sp;
-                        const uint4 w1 = e.x < a.top_nodes ? snodes[5 * (size_t)e.x + 1] : __ldg(a.nodes + 5 * (size_t)e.x + 1);
-                        Tb = w1.y; Tv = w1.z;
+        for (int it = 0; it < steps_per_refill; ++it) {
+            if (COUNT) {
+                const unsigned m = __ballot_sync(FULL, active);
+                if (lane == 0 && m) ++cnt_witer;
+                if (active) ++cnt_liter;
+            }
+            // ---------------- pop when out of node work: a node group always, a parked triangle group only when
+            //                  none is draining (it stays on the stack until then)
+            if (active && !(G.y & 0xff000000u) && sp > 0) {
+                const uint2 e = sp <= SSTACK ? lds64(stack_a + (sp - 1) * (BLOCK * 8)) : lstack[sp - 1 - SSTACK];
+                if (e.y & 0xff000000u) { G = e; --sp; }
+                else if (T.y == 0u) {
+                    T = e; --sp;
+                    if (STAGED) { Tb = lds32(snodes_a + e.x * BPT_NODE_BYTES + 28u); Tv = lds32(snodes_a + e.x * BPT_NODE_BYTES + 32u); }
+                    else {
+                        const unsigned char* np = reinterpret_cast<const unsigned char*>(a.nodes) + (size_t)e.x * BPT_NODE_BYTES;
+                        Tb = __ldg(reinterpret_cast<const uint32_t*>(np + 28));
+                        Tv = __ldg(reinterpret_cast<const uint32_t*>(np + 32));
                     }
                 }
-                // ---------------- node step
-                __syncwarp();
-                if (G.y & 0xff000000u) {
-                    if (COUNT) { if (BPT_LEADER()) ++cnt_wnode; ++cnt_nodes; }
-                    const uint32_t bit = 31u - __clz(G.y);
-                    G.y &= ~(1u << bit);
-                    if (G.y & 0xff000000u) BPT_PUSH(G)  // siblings still pending
-                    const uint32_t slot = (bit - 24u) ^ r.oct;
-                    const uint32_t rel = __popc(G.y & ~(0xffffffffu << slot) & 0xffu);
-                    const uint32_t node = G.x + rel;
-                    uint4 n0, n1, n2, n3, n4;
-                    if (node < a.top_nodes) {  // staged prefix: shared memory
-                        const uint4* np = snodes + 5 * (size_t)node;
-                        n0 = np[0]; n1 = np[1]; n2 = np[2]; n3 = np[3]; n4 = np[4];
-                    } else {
-                        const uint4* np = a.nodes + 5 * (size_t)node;
-                        n0 = __ldg(np); n1 = __ldg(np + 1); n2 = __ldg(np + 2); n3 = __ldg(np + 3); n4 = __ldg(np + 4);
-                    }
-                    const float adx = __uint_as_float((n0.w & 0xffu) << 23) * r.idx;
-                    const float ady = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * r.idy;
-                    const float adz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23) * r.idz;
-                    const float bx = fmaf(adx, -kByteBias, (__uint_as_float(n0.x) - r.ox) * r.idx);
-                    const float by = fmaf(ady, -kByteBias, (__uint_as_float(n0.y) - r.oy) * r.idy);
-                    const float bz = fmaf(adz, -kByteBias, (__uint_as_float(n0.z) - r.oz) * r.idz);
-                    // near / far plane bytes by direction sign
-                    const bool nx = r.idx < 0.f, ny = r.idy < 0.f, nz = r.idz < 0.f;
-                    const uint32_t xn0 = nx ? n3.z : n2.x, xn1 = nx ? n3.w : n2.y, xf0 = nx ? n2.x : n3.z, xf1 = nx ? n2.y : n3.w;
-                    const uint32_t yn0 = ny ? n4.x : n2.z, yn1 = ny ? n4.y : n2.w, yf0 = ny ? n2.z : n4.x, yf1 = ny ? n2.w : n4.y;
-                    const uint32_t zn0 = nz ? n4.z : n3.x, zn1 = nz ? n4.w : n3.y, zf0 = nz ? n3.x : n4.z, zf1 = nz ? n3.y : n4.w;
-                    uint32_t hit = test_quad<0>(xn0, yn0, zn0, xf0, yf0, zf0, adx, ady, adz, bx, by, bz, r.tmin, r.tbest, magic);
-                    hit |= test_quad<1>(xn1, yn1, zn1, xf1, yf1, zf1, adx, ady, adz, bx, by, bz, r.tmin, r.tbest, magic);
-                    hit &= n1.z;  // valid: internal children in the top byte, triangles in the low 24 bits
-                    // internal hits in visiting priority (bit p <- slot p ^ oct), internal mask in the low byte
-                    const uint32_t prio = slut[(r.oct << 8) + (hit >> 24)];
-                    G.x = n1.x;
-                    G.y = __byte_perm(prio, n1.z, 0x0217);
-                    if (hit & 0x00ffffffu) {
-                        if (T.y) BPT_PUSH(T)  // a group is still draining: park it, it is popped like any other entry
-                        T.x = node;
-                        T.y = hit & 0x00ffffffu;
-                        Tb = n1.y; Tv = n1.z;
+            }
+            // ---------------- node step
+            __syncwarp();
+            if (G.y & 0xff000000u) {
+                if (COUNT) { if (BPT_LEADER()) ++cnt_wnode; ++cnt_nodes; }
+                const uint32_t bit = 31u - __clz(G.y);
+                G.y &= ~(1u << bit);
+                if (G.y & 0xff000000u) BPT_PUSH(G)  // siblings still pending
+                const uint32_t slot = (bit - 24u) ^ r.oct;
+                const uint32_t rel = __popc(G.y & ~(0xffffffffu << slot) & 0xffu);
+                const uint32_t node = G.x + rel;
+                U8 v0, v1, v2;
+                if (STAGED) {
+                    const uint32_t np = snodes_a + node * BPT_NODE_BYTES;
+                    v0 = lds256(np); v1 = lds256(np + 32u); v2.lo = lds128(np + 64u); v2.hi = make_uint4(lds32(np + 80u), lds32(np + 84u), 0u, 0u);
+                } else {
+                    const unsigned char* np = reinterpret_cast<const unsigned char*>(a.nodes) + (size_t)node * BPT_NODE_BYTES;
+                    v0 = ldg256(np); v1 = ldg256(np + 32); v2 = ldg256(np + 64);
+                }
+                // v0: px py pz sx | sy sz child_base tri_base   v1: valid - qlox qlox | qloy qloy qloz qloz
+                // v2: qhix qhix qhiy qhiy | qhiz qhiz - -
+                const float adx = __uint_as_float(v0.lo.w) * r.idx;
+                const float ady = __uint_as_float(v0.hi.x) * r.idy;
+                const float adz = __uint_as_float(v0.hi.y) * r.idz;
+                const float bx = fmaf(adx, -kByteBias, (__uint_as_float(v0.lo.x) - r.ox) * r.idx);
+                const float by = fmaf(ady, -kByteBias, (__uint_as_float(v0.lo.y) - r.oy) * r.idy);
+                const float bz = fmaf(adz, -kByteBias, (__uint_as_float(v0.lo.z) - r.oz) * r.idz);
+                // near / far plane bytes by direction sign
+                const bool nx = r.idx < 0.f, ny = r.idy < 0.f, nz = r.idz < 0.f;
+                const uint32_t xn0 = nx ? v2.lo.x : v1.lo.z, xn1 = nx ? v2.lo.y : v1.lo.w, xf0 = nx ? v1.lo.z : v2.lo.x, xf1 = nx ? v1.lo.w : v2.lo.y;
+                const uint32_t yn0 = ny ? v2.lo.z : v1.hi.x, yn1 = ny ? v2.lo.w : v1.hi.y, yf0 = ny ? v1.hi.x : v2.lo.z, yf1 = ny ? v1.hi.y : v2.lo.w;
+                const uint32_t zn0 = nz ? v2.hi.x : v1.hi.z, zn1 = nz ? v2.hi.y : v1.hi.w, zf0 = nz ? v1.hi.z : v2.hi.x, zf1 = nz ? v1.hi.w : v2.hi.y;
+                uint32_t hit = test_quad<0>(xn0, yn0, zn0, xf0, yf0, zf0, adx, ady, adz, bx, by, bz, r.tmin, r.tbest, magic);
+                hit |= test_quad<1>(xn1, yn1, zn1, xf1, yf1, zf1, adx, ady, adz, bx, by, bz, r.tmin, r.tbest, magic);
+                const uint32_t valid = v1.lo.x;
+                hit &= valid;  // internal children in the top byte, triangles in the low 24 bits
+                // internal hits in visiting priority (bit p <- slot p ^ oct) into byte 3, internal mask into byte 0
+                const uint2 row = lds64(slut_a + ((hit >> 24) << 3));
+                const uint32_t prio = __byte_perm(row.x, row.y, octsel);  // byte 3 = row byte `oct`, bytes 0-2 = row byte 0
+                G.x = v0.hi.z;
+                G.y = (prio & 0xff000000u) | (valid >> 24);
+                if (hit & 0x00ffffffu) {
+                    if (T.y) BPT_PUSH(T)  // a group is still draining: park it, it is popped like any other entry
+                    T.x = node;
+                    T.y = hit & 0x00ffffffu;
+                    Tb = v0.hi.w; Tv = valid;
+                }
+            }
+            // ---------------- triangle step: one triangle of the lane's pending group
+            __syncwarp();
+            if (T.y) {
+                if (COUNT) { if (BPT_LEADER()) ++cnt_wtri; ++cnt_tris; }
+                const uint32_t k = 31u - __clz(T.y);
+                T.y &= ~(1u << k);
+                const uint32_t tri = Tb + __popc(Tv & ~(0xffffffffu << k));  // k < 24: internal bits never counted
+                U8 w0, w1;  // w0: ru rv   w1: rw | prim - - -
+                if (STAGED) {
+                    const uint32_t tp = stris_a + tri * BPT_TRI_BYTES;
+                    w0 = lds256(tp); w1.lo = lds128(tp + 32u); w1.hi = make_uint4(lds32(tp + 48u), 0u, 0u, 0u);
+                } else {
+                    const unsigned char* tp = reinterpret_cast<const unsigned char*>(a.tris) + (size_t)tri * BPT_TRI_BYTES;
+                    w0 = ldg256(tp); w1 = ldg256(tp + 32);
+                }
+                const float rwx = __uint_as_float(w1.lo.x), rwy = __uint_as_float(w1.lo.y), rwz = __uint_as_float(w1.lo.z);
+                const float oz = __uint_as_float(w1.lo.w) + r.ox * rwx + r.oy * rwy + r.oz * rwz;
+                const float dz = r.dx * rwx + r.dy * rwy + r.dz * rwz;
+                const float t = __fdividef(-oz, dz);
+                if (t >= r.tmin && t <= r.tbest) {
+                    const float rux = __uint_as_float(w0.lo.x), ruy = __uint_as_float(w0.lo.y), ruz = __uint_as_float(w0.lo.z);
+                    const float rvx = __uint_as_float(w0.hi.x), rvy = __uint_as_float(w0.hi.y), rvz = __uint_as_float(w0.hi.z);
+                    const float ou = __uint_as_float(w0.lo.w) + r.ox * rux + r.oy * ruy + r.oz * ruz;
+                    const float du = r.dx * rux + r.dy * ruy + r.dz * ruz;
+                    const float u = ou + t * du;
+                    const float ov = __uint_as_float(w0.hi.w) + r.ox * rvx + r.oy * rvy + r.oz * rvz;
+                    const float dv = r.dx * rvx + r.dy * rvy + r.dz * rvz;
+                    const float v = ov + t * dv;
+                    // equal distance (exact duplicate triangles): lowest primitive id wins
+                    if (u >= 0.f && v >= 0.f && u + v <= 1.f && (t < r.tbest || w1.hi.x < r.hprim)) {
+                        r.tbest = t;
+                        r.hprim = w1.hi.x;
                     }
                 }
-                // ---------------- triangle step: one triangle of the lane's pending group
-                __syncwarp();
-                if (T.y) {
-                    if (COUNT) { if (BPT_LEADER()) ++cnt_wtri; ++cnt_tris; }
-                    const uint32_t k = 31u - __clz(T.y);
-                    T.y &= ~(1u << k);
-                    const uint32_t tri = Tb + __popc(Tv & ~(0xffffffffu << k));  // k < 24: internal bits never counted
-                    float4 ru, rv, rw;
-                    if (tri < a.top_tris) {
-                        const float4* tp = stris + 3 * (size_t)tri;
-                        ru = tp[0]; rv = tp[1]; rw = tp[2];
-                    } else {
-                        const float4* tp = a.woop + 3 * (size_t)tri;
-                        ru = __ldg(tp); rv = __ldg(tp + 1); rw = __ldg(tp + 2);
-                    }
-                    const float oz = rw.w + r.ox * rw.x + r.oy * rw.y + r.oz * rw.z;
-                    const float dz = r.dx * rw.x + r.dy * rw.y + r.dz * rw.z;
-                    const float t = __fdividef(-oz, dz);
-                    if (t >= r.tmin && t <= r.tbest) {
-                        const float ou = ru.w + r.ox * ru.x + r.oy * ru.y + r.oz * ru.z;
-                        const float du = r.dx * ru.x + r.dy * ru.y + r.dz * ru.z;
-                        const float u = ou + t * du;
-                        const float ov = rv.w + r.ox * rv.x + r.oy * rv.y + r.oz * rv.z;
-                        const float dv = r.dx * rv.x + r.dy * rv.y + r.dz * rv.z;
-                        const float v = ov + t * dv;
-                        if (u >= 0.f && v >= 0.f && u + v <= 1.f) {
-                            // equal distance (exact duplicate triangles): lowest primitive id wins
-                            bool take = t < r.tbest || r.htri == BPT_MISS;
-                            if (!take) take = __ldg(&a.prim_index[tri]) < __ldg(&a.prim_index[r.htri]);
-                            if (take) { r.tbest = t; r.htri = tri; }
-                        }
-                    }
-                }
-                // ---------------- terminate
-                __syncwarp();
-                if (active && !(G.y & 0xff000000u) && T.y == 0u && sp == 0) {
-                    uint4 h;  // u, v are re-derived from the original vertices by the consumer (shade.cu barycentrics)
-                    h.x = __float_as_uint(r.tbest);
-                    h.y = 0u;
-                    h.z = 0u;
-                    h.w = r.htri == BPT_MISS ? BPT_MISS : __ldg(&a.prim_index[r.htri]);
-                    a.hits[ray_idx] = h;
-                    active = false;
-                }
+            }
+            // ---------------- terminate
+            __syncwarp();
+            if (active && !(G.y & 0xff000000u) && T.y == 0u && sp == 0) {
+                // {t, -, -, prim}: u, v are re-derived from the original vertices by the consumer (shade.cu)
+                a.hits[ray_idx] = make_uint4(__float_as_uint(r.tbest), 0u, 0u, r.hprim);
+                active = false;
             }
         }
     }
@@ -331,21 +375,30 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
 
 }  // namespace
 
-// shared memory the traversal kernel needs for a given staging configuration
-size_t trace_smem_bytes(uint32_t top_nodes, uint32_t top_tris) {
-    return kTraceSmemFixed + (size_t)kTraceSmemStack * kTraceBlock * sizeof(uint2) + (size_t)top_nodes * 80 + (size_t)top_tris * 48;
+// shared memory the traversal kernel needs; staged_* = 0 for the global instance
+size_t trace_smem_bytes(uint32_t staged_nodes, uint32_t staged_tris) {
+    return kTraceSmemFixed + (size_t)kTraceSmemStack * kTraceBlock * sizeof(uint2) + (size_t)staged_nodes * BPT_NODE_BYTES +
+           (size_t)staged_tris * BPT_TRI_BYTES;
 }
 
 cudaError_t trace_configure() {
-    cudaError_t e = cudaFuncSetAttribute(k_trace<kTraceBlock, kTraceSmemStack, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kTraceMaxSmem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_trace<kTraceBlock, kTraceSmemStack, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                kTraceMaxSmem);
+    cudaError_t e;
+#define CFG(S, C)                                                                                                     \
+    if ((e = cudaFuncSetAttribute(k_trace<kTraceBlock, kTraceSmemStack, S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  kTraceMaxSmem)) != cudaSuccess)                                                     \
+        return e;
+    CFG(false, false) CFG(false, true) CFG(true, false) CFG(true, true)
+#undef CFG
+    return cudaSuccess;
 }
 
-void trace_launch(const TraceArgs& a, unsigned grid, bool count, cudaStream_t st) {
-    size_t smem = trace_smem_bytes(a.top_nodes, a.top_tris);
-    if (count) k_trace<kTraceBlock, kTraceSmemStack, true><<<grid, kTraceBlock, smem, st>>>(a);
-    else k_trace<kTraceBlock, kTraceSmemStack, false><<<grid, kTraceBlock, smem, st>>>(a);
+void trace_launch(const TraceArgs& a, unsigned grid, bool staged, bool count, cudaStream_t st) {
+    const size_t smem = staged ? trace_smem_bytes(a.num_nodes, a.num_tris) : trace_smem_bytes(0, 0);
+    if (staged) {
+        if (count) k_trace<kTraceBlock, kTraceSmemStack, true, true><<<grid, kTraceBlock, smem, st>>>(a);
+        else k_trace<kTraceBlock, kTraceSmemStack, true, false><<<grid, kTraceBlock, smem, st>>>(a);
+    } else {
+        if (count) k_trace<kTraceBlock, kTraceSmemStack, false, true><<<grid, kTraceBlock, smem, st>>>(a);
+        else k_trace<kTraceBlock, kTraceSmemStack, false, false><<<grid, kTraceBlock, smem, st>>>(a);
+    }
 }

@@ -16,18 +16,18 @@ enum { BPT_STAT_RAYS = 0, BPT_STAT_NODES, BPT_STAT_TRIS, BPT_STAT_WARP_ITERS, BP
 
 struct TraceArgs {
     const float4* rays;            // 2 per ray: {o, tmin} {d, tmax}
-    uint4* hits;                   // {t, u, v, prim}
+    uint4* hits;                   // {t, -, -, prim or BPT_MISS}
     const uint32_t* count_ptr;     // number of rays (device)
     uint32_t* fetch_ctr;           // global ray fetch counter (zeroed before launch)
-    const uint4* nodes;            // BVH8 nodes, 5 x uint4 each, BFS order
-    const float4* woop;            // 3 x float4 per triangle, leaf order
-    const uint32_t* prim_index;    // leaf slot -> primitive id
-    uint32_t top_nodes;            // BFS prefix staged into shared memory
-    uint32_t top_tris;             // leading triangles staged into shared memory
+    const Node8* nodes;            // BVH8 nodes, BFS order
+    const WoopTri* tris;           // triangle records, leaf order
+    uint32_t num_nodes, num_tris;  // sizes (the STAGED instance copies all of them into shared memory)
+    int refill_below;              // refill a warp's idle lanes when fewer than this many are live
+    int steps_per_refill;          // traversal iterations between two refill votes
     uint32_t magic;                // 0x47000000 (float 32768): byte->float permute constant, see trace.cu byte_f
     unsigned long long* stat;      // BPT_STAT_* counters (may be null when not counting: only [RAYS] is touched)
 };
 
-size_t trace_smem_bytes(uint32_t top_nodes, uint32_t top_tris);
+size_t trace_smem_bytes(uint32_t staged_nodes, uint32_t staged_tris);
 cudaError_t trace_configure();
-void trace_launch(const TraceArgs& a, unsigned grid, bool count, cudaStream_t st);
+void trace_launch(const TraceArgs& a, unsigned grid, bool staged, bool count, cudaStream_t st);

@@ -121,7 +121,8 @@ def check_build_invariants(pt, verts, idx):
         for (ni, plo, phi) in level:
             nd = nodes[ni]
             visited_nodes[ni] += 1
-            scale = np.ldexp(np.float64(1.0), nd["e"].astype(np.int32) - 127)
+            scale = nd["s"].astype(np.float64)
+            assert np.all(np.frexp(scale)[0] == 0.5)  # grid steps are powers of two
             p = nd["p"].astype(np.float64)
             rank = 0
             valid = int(nd["valid"])
@@ -158,7 +159,8 @@ def check_build_invariants(pt, verts, idx):
     t = tri[tri_index].astype(np.float64)
     area = np.linalg.norm(np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0]), axis=1)
     ok = area > 1e-12
-    M, c = woop[:, :, :3].astype(np.float64), woop[:, :, 3].astype(np.float64)
+    assert np.array_equal(woop["prim"], tri_index)
+    M, c = woop["rows"][:, :, :3].astype(np.float64), woop["rows"][:, :, 3].astype(np.float64)
     # the rows are rounded once to f32, so the residual is bounded by a few f32 ulps of the magnitudes summed
     # (slivers have large rows: an absolute tolerance would measure the triangle's conditioning, not the kernel)
     eps = float(np.finfo(np.float32).eps)
