@@ -59,6 +59,7 @@ def parse_args(argv=None):
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--backend", default="nccl", help="torch.distributed backend (tests use gloo)")
+    ap.add_argument("--opt", action="append", default=[], help="developer knob: OPTION_ID=VALUE for bpt_set_option (recorded in config)")
     return ap.parse_args(argv)
 
 
@@ -272,6 +273,9 @@ def run_ours(args):
     torch.cuda.set_device(d.local_rank)
     stream = torch.cuda.Stream(device=d.local_rank)
     pt = bpt.PathTracer(d.local_rank, stream.cuda_stream)
+    for o in args.opt:
+        k, v = o.split("=")
+        pt.set_option(int(k), int(v))
     W, H, K, WU = w["width"], w["height"], args.steps, args.warmup
     tile = tile_kwargs(H, d.world, d.rank)
 
@@ -407,7 +411,8 @@ def run_ours(args):
                           "tiling": (f"{tile['tile_block']}-row blocks round-robin over {d.world} GPUs + 1 NCCL all-gather"
                                      if tile else "single tile"),
                           "l2": "working set per step (path queues + BVH) is far larger than the 126 MB L2; no flush needed",
-                          "bvh8_nodes": info.num_nodes8, "bvh_bytes": int(info.bytes_nodes + info.bytes_tris)},
+                          "bvh8_nodes": info.num_nodes8, "bvh_bytes": int(info.bytes_nodes + info.bytes_tris),
+                          **({"options": args.opt} if args.opt else {})},
                "samples_per_s": paths / (ms * 1e-3), "rays": int(rays), "paths": int(paths), "build_ms": build_ms,
                "gpu_launches": int(st.kernel_launches), "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
         print(json.dumps(out), flush=True)

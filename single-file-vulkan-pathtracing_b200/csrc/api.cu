@@ -46,7 +46,9 @@ struct bpt_context {
     size_t cap_paths = 0;
     PathQueue q[2] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     uint4* hits = nullptr;
-    float4* frame_sum = nullptr;
+    float4* path_color = nullptr;    // per path of the running pass: its sample's colour so far
+    float4* frame_sum = nullptr;     // per tile pixel: sum of the finished samples of the frame
+    size_t cap_pixels = 0;
     float4* image = nullptr;         // accumulation target; rank-major under interleaved tiling (bpt.h)
     float4* image_linear = nullptr;  // row-major copy produced on demand under interleaved tiling
     uint32_t img_w = 0, img_h = 0;
@@ -59,6 +61,7 @@ struct bpt_context {
     int64_t opt_stage_max_nodes = 1 << 20;  // BPT_OPT_SMEM_TOP_NODES: 0 disables shared-memory staging
     int ctas_per_sm = 1;
     int refill_below = 24, steps_per_refill = 4;
+    int64_t pass_paths = 1ll << 27;  // BPT_OPT_PASS_PATHS: target number of paths per sample pass
 
     // statistics
     bpt_stats stats{};
@@ -108,8 +111,8 @@ void free_paths(bpt_context* c) {
         cudaFree(q.rays); cudaFree(q.state); cudaFree(q.pixel);
         q = PathQueue{nullptr, nullptr, nullptr};
     }
-    cudaFree(c->hits); cudaFree(c->frame_sum);
-    c->hits = nullptr; c->frame_sum = nullptr;
+    cudaFree(c->hits); cudaFree(c->path_color);
+    c->hits = nullptr; c->path_color = nullptr;
     c->cap_paths = 0;
 }
 
@@ -122,9 +125,20 @@ int ensure_paths(bpt_context* c, size_t n) {
         BPT_CUDA_TRY(c, cudaMalloc(&q.pixel, n * sizeof(uint32_t)));
     }
     BPT_CUDA_TRY(c, cudaMalloc(&c->hits, n * sizeof(uint4)));
-    BPT_CUDA_TRY(c, cudaMalloc(&c->frame_sum, n * sizeof(float4)));
-    BPT_CUDA_TRY(c, cudaMemsetAsync(c->frame_sum, 0, n * sizeof(float4), c->stream));
+    BPT_CUDA_TRY(c, cudaMalloc(&c->path_color, n * sizeof(float4)));
+    BPT_CUDA_TRY(c, cudaMemsetAsync(c->path_color, 0, n * sizeof(float4), c->stream));
     c->cap_paths = n;
+    return BPT_OK;
+}
+
+int ensure_frame_sum(bpt_context* c, size_t npix) {
+    if (npix <= c->cap_pixels) return BPT_OK;
+    cudaFree(c->frame_sum);
+    c->frame_sum = nullptr;
+    c->cap_pixels = 0;
+    BPT_CUDA_TRY(c, cudaMalloc(&c->frame_sum, npix * sizeof(float4)));
+    BPT_CUDA_TRY(c, cudaMemsetAsync(c->frame_sum, 0, npix * sizeof(float4), c->stream));
+    c->cap_pixels = npix;
     return BPT_OK;
 }
 
@@ -275,6 +289,7 @@ void bpt_destroy(bpt_context* c) {
     free_scene(c);
     free_paths(c);
     bvh8_free(c->blas);
+    cudaFree(c->frame_sum);
     cudaFree(c->d_woop); cudaFree(c->image); cudaFree(c->image_linear); cudaFree(c->counters); cudaFree(c->d_stats);
     for (auto& p : c->frame_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto& p : c->trace_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
@@ -306,6 +321,10 @@ int bpt_set_option(bpt_context* c, int option, int64_t value) {
         case BPT_OPT_TRACE_CTAS_PER_SM:
             if (value != 1) return bpt_fail(c, BPT_E_INVALID, "the traversal kernel runs one 1024-thread CTA per SM");
             c->ctas_per_sm = 1;
+            return BPT_OK;
+        case BPT_OPT_PASS_PATHS:
+            if (value < 1) return bpt_fail(c, BPT_E_INVALID, "paths per pass must be >= 1");
+            c->pass_paths = value;
             return BPT_OK;
         case BPT_OPT_SORT_RAYS:
         case BPT_OPT_USE_GRAPH: return bpt_fail(c, BPT_E_INVALID, "option %d is reserved", option);
@@ -427,7 +446,12 @@ int bpt_trace(bpt_context* c, const bpt_params* p) {
     cudaSetDevice(c->device);
     FrameParams f = to_frame(p);
     const uint32_t npix = tile_local_rows(f) * f.width;
-    if ((rc = ensure_paths(c, npix)) != BPT_OK) return rc;
+    // samples per pass: enough paths in flight to keep the persistent traversal launches long (their tail and the
+    // per-launch fixed costs do not shrink with the tile), whatever the tile size of this GPU
+    uint32_t ns = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(f.spp_per_frame, c->pass_paths / npix));
+    if ((uint64_t)npix * ns > 0x7fffffffull) ns = 0x7fffffffu / npix;
+    if ((rc = ensure_paths(c, (size_t)npix * ns)) != BPT_OK) return rc;
+    if ((rc = ensure_frame_sum(c, npix)) != BPT_OK) return rc;
     if ((rc = ensure_image(c, f.width, f.height)) != BPT_OK) return rc;
     if (f.tile_block != c->tile_block || (f.tile_block && (f.tile_nranks != c->tile_nranks || f.tile_rank != c->tile_rank))) {
         // the storage layout of the image buffer changes with the tiling: start from a fresh image
@@ -442,16 +466,19 @@ int bpt_trace(bpt_context* c, const bpt_params* p) {
 
     cudaEvent_t e0 = get_event(c), e1 = get_event(c);
     cudaEventRecord(e0, c->stream);
-    for (uint32_t s = 0; s < f.spp_per_frame; ++s) {
-        launch_generate(f, s, c->q[0], counts, fetch, f.max_depth + 1, c->stream);
+    for (uint32_t s0 = 0; s0 < f.spp_per_frame; s0 += ns) {
+        const uint32_t n = std::min(ns, f.spp_per_frame - s0);
+        launch_generate(f, s0, n, c->q[0], counts, fetch, f.max_depth + 1, c->stream);
         c->stats.kernel_launches++;
         int cur = 0;
         for (uint32_t d = 0; d < f.max_depth; ++d) {
             launch_trace(c, make_trace_args(c, c->q[cur].rays, c->hits, counts + d, fetch + d));
-            launch_shade(f, sv, d, c->q[cur], c->hits, c->q[cur ^ 1], counts, c->frame_sum, npix, c->stream);
+            launch_shade(f, sv, d, c->q[cur], c->hits, c->q[cur ^ 1], counts, c->path_color, npix * n, c->stream);
             c->stats.kernel_launches++;
             cur ^= 1;
         }
+        launch_gather_pass(npix, n, c->path_color, c->frame_sum, c->stream);
+        c->stats.kernel_launches++;
     }
     launch_accumulate(f, c->frame_sum, c->image, c->stream);
     c->stats.kernel_launches++;
@@ -518,7 +545,7 @@ int bpt_clear_image(bpt_context* c) {
     if (!c) return BPT_E_INVALID;
     cudaSetDevice(c->device);
     if (c->image) BPT_CUDA_TRY(c, cudaMemsetAsync(c->image, 0, (size_t)c->img_w * c->img_h * sizeof(float4), c->stream));
-    if (c->frame_sum) BPT_CUDA_TRY(c, cudaMemsetAsync(c->frame_sum, 0, c->cap_paths * sizeof(float4), c->stream));
+    if (c->frame_sum) BPT_CUDA_TRY(c, cudaMemsetAsync(c->frame_sum, 0, c->cap_pixels * sizeof(float4), c->stream));
     return BPT_OK;
 }
 
@@ -597,7 +624,7 @@ int bpt_generate_rays(bpt_context* c, const bpt_params* p, uint32_t sample_in_fr
     if ((rc = ensure_paths(c, npix)) != BPT_OK) return rc;
     uint32_t* counts = c->counters;
     uint32_t* fetch = c->counters + (kMaxDepth + 1);
-    launch_generate(f, sample_in_frame, c->q[0], counts, fetch, f.max_depth + 1, c->stream);
+    launch_generate(f, sample_in_frame, 1, c->q[0], counts, fetch, f.max_depth + 1, c->stream);
     std::vector<float4> st(npix);
     BPT_CUDA_TRY(c, cudaMemcpyAsync(rays, c->q[0].rays, (size_t)npix * 32, cudaMemcpyDeviceToHost, c->stream));
     BPT_CUDA_TRY(c, cudaMemcpyAsync(st.data(), c->q[0].state, (size_t)npix * 16, cudaMemcpyDeviceToHost, c->stream));

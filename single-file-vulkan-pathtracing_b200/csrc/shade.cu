@@ -33,17 +33,19 @@ __device__ __forceinline__ V3 normalize(V3 a) { return a / sqrtf(dot(a, a)); }
 constexpr float kTwoPi = 6.2831855f, kPi = 3.1415927f, kPdf = 0.15915494f;
 
 // ---------------------------------------------------------------- K9
-__global__ void k_generate(FrameParams p, uint32_t sample_in_frame, PathQueue q, uint32_t* counts, uint32_t* fetch,
+__global__ void k_generate(FrameParams p, uint32_t s0, uint32_t ns, PathQueue q, uint32_t* counts, uint32_t* fetch,
                            uint32_t ncounters) {
     const uint32_t npix = tile_local_rows(p) * p.width;
+    const uint32_t npaths = npix * ns;  // one pass carries samples s0 .. s0+ns-1 of every tile pixel
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < ncounters) {  // queue lengths and fetch counters of this sample pass
-        counts[i] = i == 0 ? npix : 0u;
+        counts[i] = i == 0 ? npaths : 0u;
         fetch[i] = 0u;
     }
-    if (i >= npix) return;
-    const uint32_t px = i % p.width, py = tile_global_row(p, i / p.width);
-    const uint32_t k = sample_in_frame + p.spp_per_frame * (uint32_t)p.frame + 1u;  // raygen.rgen:47
+    if (i >= npaths) return;
+    const uint32_t slot = i / npix, pl = i - slot * npix;
+    const uint32_t px = pl % p.width, py = tile_global_row(p, pl / p.width);
+    const uint32_t k = (s0 + slot) + p.spp_per_frame * (uint32_t)p.frame + 1u;  // raygen.rgen:47
     uint32_t sx = px * k, sy = py * k;
     bpt_pcg2d(sx, sy);
     uint32_t seed = sx + sy;
@@ -58,7 +60,7 @@ __global__ void k_generate(FrameParams p, uint32_t sample_in_frame, PathQueue q,
     q.rays[2 * (size_t)i] = make_float4(o.x, o.y, o.z, p.tmin);
     q.rays[2 * (size_t)i + 1] = make_float4(d.x, d.y, d.z, p.tmax);
     q.state[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
-    q.pixel[i] = i;
+    q.pixel[i] = i;  // path id of the pass: slot * npix + tile-local pixel
 }
 
 // ---------------------------------------------------------------- K11
@@ -104,8 +106,10 @@ __global__ void k_refine_hits(SceneView s, const float4* __restrict__ rays, uint
     hits[i] = h;
 }
 
+// path_color[path id] collects `color` of one sample (raygen.rgen:76); k_gather_pass folds the samples of a pass into
+// the frame sum in sample order, so the result does not depend on how many samples a pass carries.
 __global__ void k_shade(FrameParams p, SceneView s, uint32_t depth, PathQueue in, const uint4* __restrict__ hits,
-                        PathQueue out, uint32_t* counts, float4* frame_sum) {
+                        PathQueue out, uint32_t* counts, float4* path_color) {
     const uint32_t n = counts[depth];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
@@ -121,9 +125,9 @@ __global__ void k_shade(FrameParams p, SceneView s, uint32_t depth, PathQueue in
         if (h.w == BPT_MISS) {
             // miss.rmiss:10-11 then raygen.rgen:76 and the break at :81
             const V3 c = w * V3{p.sky[0], p.sky[1], p.sky[2]};
-            float4 acc = frame_sum[pix];
+            float4 acc = path_color[pix];
             acc.x += c.x; acc.y += c.y; acc.z += c.z;
-            frame_sum[pix] = acc;
+            path_color[pix] = acc;
         } else {
             const uint32_t inst = s.xforms ? h.w / s.ntris : 0u;
             const uint32_t prim = s.xforms ? h.w - inst * s.ntris : h.w;
@@ -141,9 +145,9 @@ __global__ void k_shade(FrameParams p, SceneView s, uint32_t depth, PathQueue in
             const V3 kd{__ldg(f), __ldg(f + 1), __ldg(f + 2)}, ke{__ldg(f + 3), __ldg(f + 4), __ldg(f + 5)};
             if (ke.x != 0.0f || ke.y != 0.0f || ke.z != 0.0f) {      // raygen.rgen:76 (adding 0 is exact)
                 const V3 c = w * ke;
-                float4 acc = frame_sum[pix];
+                float4 acc = path_color[pix];
                 acc.x += c.x; acc.y += c.y; acc.z += c.z;
-                frame_sum[pix] = acc;
+                path_color[pix] = acc;
             }
             if (depth + 1u < p.max_depth) {                          // the next segment will be traced
                 const V3 brdf = kd / kPi;                            // closesthit.rchit:61
@@ -185,6 +189,19 @@ __global__ void k_shade(FrameParams p, SceneView s, uint32_t depth, PathQueue in
             out.pixel[j] = pix;
         }
     }
+}
+
+// frame_sum[pixel] += color of samples s0..s0+ns-1, in sample order (raygen.rgen:76 adds into one `color` per pixel)
+__global__ void k_gather_pass(uint32_t npix, uint32_t ns, float4* __restrict__ path_color, float4* __restrict__ frame_sum) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    float4 acc = frame_sum[i];
+    for (uint32_t s = 0; s < ns; ++s) {
+        const float4 c = path_color[(size_t)s * npix + i];
+        path_color[(size_t)s * npix + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        acc.x += c.x; acc.y += c.y; acc.z += c.z;
+    }
+    frame_sum[i] = acc;
 }
 
 // ---------------------------------------------------------------- K12
@@ -266,14 +283,17 @@ inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kBlock - 1) / kBlo
 
 }  // namespace
 
-void launch_generate(const FrameParams& p, uint32_t sample_in_frame, PathQueue q, uint32_t* counts, uint32_t* fetch,
+void launch_generate(const FrameParams& p, uint32_t s0, uint32_t ns, PathQueue q, uint32_t* counts, uint32_t* fetch,
                      uint32_t ncounters, cudaStream_t st) {
-    const uint64_t threads = std::max<uint64_t>((uint64_t)tile_local_rows(p) * p.width, ncounters);  // the first threads also reset the counters
-    k_generate<<<grid_for(threads), kBlock, 0, st>>>(p, sample_in_frame, q, counts, fetch, ncounters);
+    const uint64_t threads = std::max<uint64_t>((uint64_t)tile_local_rows(p) * p.width * ns, ncounters);  // the first threads also reset the counters
+    k_generate<<<grid_for(threads), kBlock, 0, st>>>(p, s0, ns, q, counts, fetch, ncounters);
+}
+void launch_gather_pass(uint32_t npix, uint32_t ns, float4* path_color, float4* frame_sum, cudaStream_t st) {
+    k_gather_pass<<<grid_for(npix), kBlock, 0, st>>>(npix, ns, path_color, frame_sum);
 }
 void launch_shade(const FrameParams& p, const SceneView& s, uint32_t depth, PathQueue in, const uint4* hits,
-                  PathQueue out, uint32_t* counts, float4* frame_sum, uint32_t max_paths, cudaStream_t st) {
-    k_shade<<<grid_for(max_paths), kBlock, 0, st>>>(p, s, depth, in, hits, out, counts, frame_sum);
+                  PathQueue out, uint32_t* counts, float4* path_color, uint32_t max_paths, cudaStream_t st) {
+    k_shade<<<grid_for(max_paths), kBlock, 0, st>>>(p, s, depth, in, hits, out, counts, path_color);
 }
 void launch_refine_hits(const SceneView& s, const float4* rays, uint4* hits, uint32_t n, cudaStream_t st) {
     k_refine_hits<<<grid_for(n), kBlock, 0, st>>>(s, rays, hits, n);

@@ -36,19 +36,22 @@ struct SceneView {
     uint32_t ntris;
 };
 
-// One wavefront queue (SoA): ray 2 x float4, state float4 {w.rgb, seed bits}, pixel u32.
+// One wavefront queue (SoA): ray 2 x float4, state float4 {w.rgb, seed bits}, pixel u32 (= path id of the pass).
 struct PathQueue {
     float4* rays;
     float4* state;
     uint32_t* pixel;
 };
 
-void launch_generate(const FrameParams& p, uint32_t sample_in_frame, PathQueue q, uint32_t* counts, uint32_t* fetch,
+// one pass = samples s0..s0+ns-1 of every tile pixel; path id = slot * tile_pixels + tile-local pixel
+void launch_generate(const FrameParams& p, uint32_t s0, uint32_t ns, PathQueue q, uint32_t* counts, uint32_t* fetch,
                      uint32_t ncounters, cudaStream_t st);
+// folds the per-sample colours of a finished pass into the frame sum (sample order) and clears them
+void launch_gather_pass(uint32_t npix, uint32_t ns, float4* path_color, float4* frame_sum, cudaStream_t st);
 // depth: index of the bounce being shaded; counts[depth] paths in `in`, survivors appended to `out`
-// and counted in counts[depth+1].
+// and counted in counts[depth+1]. path_color: per-path radiance of the pass (indexed by path id).
 void launch_shade(const FrameParams& p, const SceneView& s, uint32_t depth, PathQueue in, const uint4* hits,
-                  PathQueue out, uint32_t* counts, float4* frame_sum, uint32_t max_paths, cudaStream_t st);
+                  PathQueue out, uint32_t* counts, float4* path_color, uint32_t max_paths, cudaStream_t st);
 // re-derives (u,v) of every hit from the original vertices (what k_shade does internally)
 void launch_refine_hits(const SceneView& s, const float4* rays, uint4* hits, uint32_t n, cudaStream_t st);
 void launch_accumulate(const FrameParams& p, float4* frame_sum, float4* image, cudaStream_t st);
