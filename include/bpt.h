@@ -156,8 +156,13 @@ int bpt_upload_mesh_device(bpt_context* ctx,
                            const void* d_verts, uint32_t nverts,
                            const void* d_indices, uint32_t nindices,
                            const void* d_faces, uint32_t nfaces);
-/* Instance transforms: n row-major 3x4 float matrices (VkTransformMatrixKHR,
- * main.cpp:515-520). Default after upload: one identity instance. */
+/* Instance transforms: n row-major 3x4 float matrices (VkTransformMatrixKHR, main.cpp:515-520), object -> world.
+ * Call after bpt_upload_mesh (which resets the scene to one identity instance) and before bpt_build_accel: the
+ * build then adds an instance-level BVH8 over the instances' world boxes (the reference's TLAS, main.cpp:538) and
+ * the traversal kernel runs two-level. Hit primitive ids are instance * ntris + primitive. Shading transforms the
+ * triangle's vertices by the instance matrix and applies the reference's formulas to them (the reference shader
+ * itself ignores instance transforms, which is only correct for its single identity instance).
+ * Fails on a singular or non-finite matrix. */
 int bpt_set_instances(bpt_context* ctx, const float* xforms3x4, uint32_t n);
 
 /* Synthetic triangle soup generated on the device (no reference equivalent —

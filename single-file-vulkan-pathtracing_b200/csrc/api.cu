@@ -33,12 +33,16 @@ struct bpt_context {
     float* d_verts = nullptr;
     uint32_t* d_idx = nullptr;
     float* d_faces = nullptr;
-    float* d_xforms = nullptr;  // null: one identity instance
+    float* d_xforms = nullptr;      // null: one identity instance
+    float* d_xforms_inv = nullptr;  // inverse 3x4 of every instance (two-level scenes)
     uint32_t nverts = 0, nidx = 0, nfaces = 0, ntris = 0, ninst = 1;
 
     // acceleration structure
-    Bvh8 blas;
-    WoopTri* d_woop = nullptr;
+    Bvh8 blas;                      // over the mesh triangles
+    Bvh8 tlas;                      // over the instances (two-level scenes only)
+    WoopTri* d_woop = nullptr;      // [triangle records | instance records]
+    Node8* d_nodes_all = nullptr;   // two-level scenes: [mesh nodes | instance nodes]
+    bool two_level = false;
     bool built = false, built_nodes_ok = false;
     bool staged = false;  // the traversal kernel instance that holds the whole BVH in shared memory is in use
 
@@ -100,8 +104,8 @@ cudaEvent_t get_event(bpt_context* c) {
 }
 
 void free_scene(bpt_context* c) {
-    cudaFree(c->d_verts); cudaFree(c->d_idx); cudaFree(c->d_faces); cudaFree(c->d_xforms);
-    c->d_verts = nullptr; c->d_idx = nullptr; c->d_faces = nullptr; c->d_xforms = nullptr;
+    cudaFree(c->d_verts); cudaFree(c->d_idx); cudaFree(c->d_faces); cudaFree(c->d_xforms); cudaFree(c->d_xforms_inv);
+    c->d_verts = nullptr; c->d_idx = nullptr; c->d_faces = nullptr; c->d_xforms = nullptr; c->d_xforms_inv = nullptr;
     c->nverts = c->nidx = c->nfaces = c->ntris = 0;
     c->ninst = 1;
     c->built = false;
@@ -193,9 +197,12 @@ int row_major_image(bpt_context* c, const float4** out) {
 TraceArgs make_trace_args(bpt_context* c, const float4* rays, uint4* hits, const uint32_t* count, uint32_t* fetch) {
     TraceArgs a;
     a.rays = rays; a.hits = hits; a.count_ptr = count; a.fetch_ctr = fetch;
-    a.nodes = c->blas.nodes;
+    a.nodes = c->two_level ? c->d_nodes_all : c->blas.nodes;
     a.tris = c->d_woop;
-    a.num_nodes = c->blas.num_nodes; a.num_tris = c->ntris;
+    a.num_nodes = c->blas.num_nodes + (c->two_level ? c->tlas.num_nodes : 0u);
+    a.num_tris = c->ntris + (c->two_level ? c->ninst : 0u);
+    a.root = c->two_level ? c->blas.num_nodes : 0u;
+    a.num_mesh_tris = c->ntris;
     a.refill_below = c->refill_below; a.steps_per_refill = c->steps_per_refill;
     a.magic = 0x47000000u;
     a.stat = c->d_stats;
@@ -208,7 +215,7 @@ void launch_trace(bpt_context* c, const TraceArgs& a) {
         e0 = get_event(c); e1 = get_event(c);
         cudaEventRecord(e0, c->stream);
     }
-    trace_launch(a, (unsigned)(c->num_sms * c->ctas_per_sm), c->staged, c->count, c->stream);
+    trace_launch(a, (unsigned)(c->num_sms * c->ctas_per_sm), c->staged, c->two_level, c->count, c->stream);
     if (c->profile) {
         cudaEventRecord(e1, c->stream);
         c->trace_events.emplace_back(e0, e1);
@@ -219,8 +226,29 @@ void launch_trace(bpt_context* c, const TraceArgs& a) {
 
 // Small scenes run the traversal instance that keeps the whole BVH in shared memory (TMA-staged once per CTA).
 void plan_staging(bpt_context* c) {
-    c->staged = c->built_nodes_ok && c->blas.num_nodes <= (uint64_t)c->opt_stage_max_nodes &&
-                trace_smem_bytes(c->blas.num_nodes, c->ntris) <= (size_t)kTraceMaxSmem;
+    const uint64_t nodes = (uint64_t)c->blas.num_nodes + (c->two_level ? c->tlas.num_nodes : 0u);
+    const uint64_t recs = (uint64_t)c->ntris + (c->two_level ? c->ninst : 0u);
+    c->staged = c->built_nodes_ok && nodes <= (uint64_t)c->opt_stage_max_nodes &&
+                trace_smem_bytes((uint32_t)nodes, (uint32_t)recs) <= (size_t)kTraceMaxSmem;
+}
+
+// inverse of a row-major 3x4 affine transform, in double; false if singular
+bool invert3x4(const float* m, float* out) {
+    const double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    if (!(std::fabs(det) > 0.0) || !std::isfinite(det)) return false;
+    const double r = 1.0 / det;
+    const double n[9] = {(e * i - f * h) * r, (c * h - b * i) * r, (b * f - c * e) * r,
+                         (f * g - d * i) * r, (a * i - c * g) * r, (c * d - a * f) * r,
+                         (d * h - e * g) * r, (b * g - a * h) * r, (a * e - b * d) * r};
+    const double t[3] = {m[3], m[7], m[11]};
+    for (int row = 0; row < 3; ++row) {
+        for (int col = 0; col < 3; ++col) out[4 * row + col] = (float)n[3 * row + col];
+        out[4 * row + 3] = (float)-(n[3 * row] * t[0] + n[3 * row + 1] * t[1] + n[3 * row + 2] * t[2]);
+    }
+    for (int k = 0; k < 12; ++k)
+        if (!std::isfinite(out[k])) return false;
+    return true;
 }
 
 }  // namespace
@@ -288,8 +316,8 @@ void bpt_destroy(bpt_context* c) {
     if (c->nccl_comm) bpt_nccl_comm_destroy(c->nccl_comm);
     free_scene(c);
     free_paths(c);
-    bvh8_free(c->blas);
-    cudaFree(c->frame_sum);
+    bvh8_free(c->blas); bvh8_free(c->tlas);
+    cudaFree(c->d_nodes_all); cudaFree(c->frame_sum);
     cudaFree(c->d_woop); cudaFree(c->image); cudaFree(c->image_linear); cudaFree(c->counters); cudaFree(c->d_stats);
     for (auto& p : c->frame_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto& p : c->trace_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
@@ -389,7 +417,23 @@ int bpt_upload_soup(bpt_context* c, uint32_t ntris, uint32_t seed) {
 int bpt_set_instances(bpt_context* c, const float* xforms3x4, uint32_t n) {
     if (!c) return BPT_E_INVALID;
     if (n == 0 || !xforms3x4) return bpt_fail(c, BPT_E_INVALID, "need at least one instance transform");
-    return bpt_fail(c, BPT_E_INVALID, "multi-instance (two-level) scenes are not implemented yet");
+    if (c->ntris == 0) return bpt_fail(c, BPT_E_STATE, "bpt_set_instances before bpt_upload_mesh");
+    if ((uint64_t)n * c->ntris > 0xfffffffeull) return bpt_fail(c, BPT_E_INVALID, "%u instances x %u triangles overflow the 32-bit primitive id", n, c->ntris);
+    std::vector<float> inv(12 * (size_t)n);
+    for (uint32_t i = 0; i < n; ++i)
+        if (!invert3x4(xforms3x4 + 12 * (size_t)i, inv.data() + 12 * (size_t)i))
+            return bpt_fail(c, BPT_E_INVALID, "instance %u has a singular or non-finite transform", i);
+    cudaSetDevice(c->device);
+    cudaFree(c->d_xforms); cudaFree(c->d_xforms_inv);
+    c->d_xforms = nullptr; c->d_xforms_inv = nullptr;
+    c->built = false;
+    BPT_CUDA_TRY(c, cudaMalloc(&c->d_xforms, 48 * (size_t)n));
+    BPT_CUDA_TRY(c, cudaMalloc(&c->d_xforms_inv, 48 * (size_t)n));
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(c->d_xforms, xforms3x4, 48 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(c->d_xforms_inv, inv.data(), 48 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // inv is a local
+    c->ninst = n;
+    return BPT_OK;
 }
 
 int bpt_build_accel(bpt_context* c) {
@@ -404,12 +448,31 @@ int bpt_build_accel(bpt_context* c) {
     BPT_CUDA_TRY(c, bvh8_build(c->blas, c->stream));
     if (c->blas.num_leaf_slots != c->ntris)
         return bpt_fail(c, BPT_E_STATE, "BVH8 collapse placed %u of %u triangles", c->blas.num_leaf_slots, c->ntris);
-    if (c->blas.depth > (uint32_t)kTraceMaxDepth)
-        return bpt_fail(c, BPT_E_STATE, "BVH8 depth %u exceeds the traversal stack", c->blas.depth);
-    cudaFree(c->d_woop);
-    c->d_woop = nullptr;
-    BPT_CUDA_TRY(c, cudaMalloc(&c->d_woop, (size_t)c->ntris * sizeof(WoopTri) + 32));
+    c->two_level = c->d_xforms != nullptr;
+    const uint32_t nrec = c->ntris + (c->two_level ? c->ninst : 0u);
+    cudaFree(c->d_woop); cudaFree(c->d_nodes_all);
+    c->d_woop = nullptr; c->d_nodes_all = nullptr;
+    BPT_CUDA_TRY(c, cudaMalloc(&c->d_woop, (size_t)nrec * sizeof(WoopTri) + 32));
     bvh8_launch_woop(c->blas, c->d_verts, c->d_idx, c->d_woop, c->stream);
+    uint32_t depth = c->blas.depth;
+    if (c->two_level) {
+        // K8: the same builder over the instances' world boxes (main.cpp:514-538), then one node array [mesh | instances]
+        BPT_CUDA_TRY(c, bvh8_alloc(c->tlas, c->ninst));
+        bvh8_launch_instance_bounds(c->tlas, c->d_xforms, c->blas.scene_lo, c->blas.scene_hi, c->stream);
+        BPT_CUDA_TRY(c, bvh8_build(c->tlas, c->stream));
+        if (c->tlas.num_leaf_slots != c->ninst)
+            return bpt_fail(c, BPT_E_STATE, "instance BVH8 collapse placed %u of %u instances", c->tlas.num_leaf_slots, c->ninst);
+        bvh8_launch_instance_records(c->tlas, c->d_xforms_inv, c->d_woop + c->ntris, c->stream);
+        const uint32_t nb = c->blas.num_nodes, nt = c->tlas.num_nodes;
+        BPT_CUDA_TRY(c, cudaMalloc(&c->d_nodes_all, (size_t)(nb + nt) * sizeof(Node8)));
+        BPT_CUDA_TRY(c, cudaMemcpyAsync(c->d_nodes_all, c->blas.nodes, (size_t)nb * sizeof(Node8), cudaMemcpyDeviceToDevice, c->stream));
+        bvh8_launch_append_nodes(c->tlas.nodes, nt, nb, c->ntris, c->d_nodes_all + nb, c->stream);
+        depth += c->tlas.depth + 1;  // + the sentinel
+    } else {
+        bvh8_free(c->tlas);
+    }
+    if (depth > (uint32_t)kTraceMaxDepth)
+        return bpt_fail(c, BPT_E_STATE, "BVH8 depth %u exceeds the traversal stack", depth);
     cudaEventRecord(e1, c->stream);
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     BPT_CUDA_TRY(c, cudaGetLastError());
@@ -433,6 +496,7 @@ int bpt_accel_info_get(bpt_context* c, bpt_accel_info* out) {
     out->num_binary_nodes = c->ntris - 1;
     out->top_nodes_smem = c->staged ? c->blas.num_nodes : 0;
     out->max_depth8 = c->blas.depth;
+    out->num_tlas_nodes8 = c->two_level ? c->tlas.num_nodes : 0;
     out->bytes_nodes = (uint64_t)c->blas.num_nodes * BPT_NODE_BYTES;
     out->bytes_tris = (uint64_t)c->ntris * BPT_TRI_BYTES;
     return BPT_OK;

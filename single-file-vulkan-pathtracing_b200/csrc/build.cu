@@ -405,6 +405,32 @@ __global__ void k_woop(const float* __restrict__ verts, const uint32_t* __restri
     out[s] = w;
 }
 
+// K8: record of the instance in leaf slot s of the instance-level BVH8: rows of the inverse 3x4 transform + instance id
+__global__ void k_instance_records(const float* __restrict__ inv, const uint32_t* __restrict__ prim_index, uint32_t n,
+                                   WoopTri* __restrict__ out) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t inst = prim_index[s];
+    const float* m = inv + 12 * (size_t)inst;
+    WoopTri w;
+    w.ru = make_float4(m[0], m[1], m[2], m[3]);
+    w.rv = make_float4(m[4], m[5], m[6], m[7]);
+    w.rw = make_float4(m[8], m[9], m[10], m[11]);
+    w.prim = inst; w.pad0 = w.pad1 = w.pad2 = 0;
+    out[s] = w;
+}
+
+// K8: copies the instance-level nodes behind the mesh nodes, rebasing their child and record indices
+__global__ void k_append_nodes(const Node8* __restrict__ src, uint32_t n, uint32_t node_off, uint32_t rec_off,
+                               Node8* __restrict__ dst) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Node8 nd = src[i];
+    nd.child_base += node_off;
+    nd.tri_base += rec_off;
+    dst[i] = nd;
+}
+
 template <class T>
 cudaError_t dalloc(T** p, size_t count) {
     return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T) + 16);
@@ -510,4 +536,11 @@ cudaError_t bvh8_build(Bvh8& b, cudaStream_t st) {
 
 void bvh8_launch_woop(const Bvh8& b, const float* verts, const uint32_t* idx, WoopTri* out, cudaStream_t st) {
     k_woop<<<grid_for(b.n), kBlock, 0, st>>>(verts, idx, b.prim_index, b.n, out);
+}
+
+void bvh8_launch_instance_records(const Bvh8& tlas, const float* inv_xforms, WoopTri* out, cudaStream_t st) {
+    k_instance_records<<<grid_for(tlas.n), kBlock, 0, st>>>(inv_xforms, tlas.prim_index, tlas.n, out);
+}
+void bvh8_launch_append_nodes(const Node8* src, uint32_t n, uint32_t node_off, uint32_t rec_off, Node8* dst, cudaStream_t st) {
+    k_append_nodes<<<grid_for(n), kBlock, 0, st>>>(src, n, node_off, rec_off, dst);
 }

@@ -33,6 +33,10 @@ void bvh8_launch_instance_bounds(Bvh8& b, const float* xforms, const float mesh_
 cudaError_t bvh8_build(Bvh8& b, cudaStream_t st);
 void bvh8_launch_woop(const Bvh8& b, const float* verts, const uint32_t* idx, WoopTri* out, cudaStream_t st);
 
+// two-level scenes: instance leaf records (inverse transforms) and the merged node array [mesh | instances]
+void bvh8_launch_instance_records(const Bvh8& tlas, const float* inv_xforms, WoopTri* out, cudaStream_t st);
+void bvh8_launch_append_nodes(const Node8* src, uint32_t n, uint32_t node_off, uint32_t rec_off, Node8* dst, cudaStream_t st);
+
 // radix_sort.cu — stable LSD radix sort of 64-bit keys on bits [begin_bit, end_bit).
 // Returns the buffer (keys or tmp) that holds the sorted result.
 size_t radix_sort_u64_temp_bytes(uint32_t n);

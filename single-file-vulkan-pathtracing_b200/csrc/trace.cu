@@ -145,7 +145,11 @@ __device__ __forceinline__ uint32_t test_quad(uint32_t xn, uint32_t yn, uint32_t
     return hit;
 }
 
-template <int BLOCK, int SSTACK, bool STAGED, bool COUNT>
+// TWO_LEVEL (instanced scenes, main.cpp:515-538): nodes = [mesh BVH8 | instance BVH8], records = [triangles | instances];
+// an instance record holds the rows of the inverse 3x4 transform. Hitting one pushes what is left of the instance-level
+// state plus a sentinel, moves the ray into object space (d is NOT renormalised, so t is the same in both spaces) and
+// descends from the mesh root (node 0); popping the sentinel reloads the world-space ray.
+template <int BLOCK, int SSTACK, bool STAGED, bool TWO_LEVEL, bool COUNT>
 __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -199,6 +203,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
     uint2 T = make_uint2(0u, 0u);  // triangle group: x = node the triangles belong to, y = hit bits (valid layout)
     uint32_t Tb = 0u, Tv = 0u;     // tri_base and valid word of node T.x
     uint32_t octsel = 0u;          // byte-permute selector that picks byte `oct` of a slut row into byte 3
+    uint32_t inst_base = 0u;       // TWO_LEVEL: instance * mesh triangles while inside an instance
     int sp = 0;
     uint32_t ray_idx = 0;
     bool active = false, exhausted = false;
@@ -234,7 +239,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                     r.oct = (rd.x >= 0.f ? 4u : 0u) | (rd.y >= 0.f ? 2u : 0u) | (rd.z >= 0.f ? 1u : 0u);
                     octsel = r.oct << 12;
                     r.hprim = BPT_MISS;
-                    G = make_uint2(0u, 0x80000000u);  // root: node 0 through priority bit 31, internal mask 0
+                    inst_base = 0u;
+                    G = make_uint2(a.root, 0x80000000u);  // root through priority bit 31, internal mask 0
                     T = make_uint2(0u, 0u);
                     sp = 0;
                     active = true;
@@ -259,6 +265,22 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
             if (active && !(G.y & 0xff000000u) && sp > 0) {
                 const uint2 e = sp <= SSTACK ? lds64(stack_a + (sp - 1) * (BLOCK * 8)) : lstack[sp - 1 - SSTACK];
                 if (e.y & 0xff000000u) { G = e; --sp; }
+                else if (TWO_LEVEL && e.y == 0u) {
+                    if (T.y == 0u) {  // sentinel: the instance is done (its triangles too) -> back to world space
+                        --sp;
+                        const float4 ro = __ldg(&a.rays[2 * (size_t)ray_idx]);
+                        const float4 rd = __ldg(&a.rays[2 * (size_t)ray_idx + 1]);
+                        r.ox = ro.x; r.oy = ro.y; r.oz = ro.z;
+                        r.dx = rd.x; r.dy = rd.y; r.dz = rd.z;
+                        const float eps = 1e-30f;
+                        r.idx = 1.0f / (fabsf(rd.x) > eps ? rd.x : copysignf(eps, rd.x));
+                        r.idy = 1.0f / (fabsf(rd.y) > eps ? rd.y : copysignf(eps, rd.y));
+                        r.idz = 1.0f / (fabsf(rd.z) > eps ? rd.z : copysignf(eps, rd.z));
+                        r.oct = (rd.x >= 0.f ? 4u : 0u) | (rd.y >= 0.f ? 2u : 0u) | (rd.z >= 0.f ? 1u : 0u);
+                        octsel = r.oct << 12;
+                        inst_base = 0u;
+                    }
+                }
                 else if (T.y == 0u) {
                     T = e; --sp;
                     if (STAGED) { Tb = lds32(snodes_a + e.x * BPT_NODE_BYTES + 28u); Tv = lds32(snodes_a + e.x * BPT_NODE_BYTES + 32u); }
@@ -331,6 +353,29 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                     const unsigned char* tp = reinterpret_cast<const unsigned char*>(a.tris) + (size_t)tri * BPT_TRI_BYTES;
                     w0 = ldg256(tp); w1 = ldg256(tp + 32);
                 }
+                if (TWO_LEVEL && tri >= a.num_mesh_tris) {
+                    // instance record: w0 = rows 0,1 and w1.lo = row 2 of the inverse transform, w1.hi.x = instance
+                    if (G.y & 0xff000000u) BPT_PUSH(G)
+                    if (T.y) BPT_PUSH(T)
+                    BPT_PUSH(make_uint2(0u, 0u))
+                    const float m00 = __uint_as_float(w0.lo.x), m01 = __uint_as_float(w0.lo.y), m02 = __uint_as_float(w0.lo.z), m03 = __uint_as_float(w0.lo.w);
+                    const float m10 = __uint_as_float(w0.hi.x), m11 = __uint_as_float(w0.hi.y), m12 = __uint_as_float(w0.hi.z), m13 = __uint_as_float(w0.hi.w);
+                    const float m20 = __uint_as_float(w1.lo.x), m21 = __uint_as_float(w1.lo.y), m22 = __uint_as_float(w1.lo.z), m23 = __uint_as_float(w1.lo.w);
+                    const float ox = m00 * r.ox + m01 * r.oy + m02 * r.oz + m03, oy = m10 * r.ox + m11 * r.oy + m12 * r.oz + m13,
+                                oz = m20 * r.ox + m21 * r.oy + m22 * r.oz + m23;
+                    const float dx = m00 * r.dx + m01 * r.dy + m02 * r.dz, dy = m10 * r.dx + m11 * r.dy + m12 * r.dz,
+                                dz = m20 * r.dx + m21 * r.dy + m22 * r.dz;
+                    r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
+                    const float eps = 1e-30f;
+                    r.idx = 1.0f / (fabsf(dx) > eps ? dx : copysignf(eps, dx));
+                    r.idy = 1.0f / (fabsf(dy) > eps ? dy : copysignf(eps, dy));
+                    r.idz = 1.0f / (fabsf(dz) > eps ? dz : copysignf(eps, dz));
+                    r.oct = (dx >= 0.f ? 4u : 0u) | (dy >= 0.f ? 2u : 0u) | (dz >= 0.f ? 1u : 0u);
+                    octsel = r.oct << 12;
+                    inst_base = w1.hi.x * a.num_mesh_tris;
+                    G = make_uint2(0u, 0x80000000u);  // mesh root
+                    T = make_uint2(0u, 0u);
+                } else {
                 const float rwx = __uint_as_float(w1.lo.x), rwy = __uint_as_float(w1.lo.y), rwz = __uint_as_float(w1.lo.z);
                 const float oz = __uint_as_float(w1.lo.w) + r.ox * rwx + r.oy * rwy + r.oz * rwz;
                 const float dz = r.dx * rwx + r.dy * rwy + r.dz * rwz;
@@ -345,10 +390,12 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                     const float dv = r.dx * rvx + r.dy * rvy + r.dz * rvz;
                     const float v = ov + t * dv;
                     // equal distance (exact duplicate triangles): lowest primitive id wins
-                    if (u >= 0.f && v >= 0.f && u + v <= 1.f && (t < r.tbest || w1.hi.x < r.hprim)) {
+                    const uint32_t prim = inst_base + w1.hi.x;
+                    if (u >= 0.f && v >= 0.f && u + v <= 1.f && (t < r.tbest || prim < r.hprim)) {
                         r.tbest = t;
-                        r.hprim = w1.hi.x;
+                        r.hprim = prim;
                     }
+                }
                 }
             }
             // ---------------- terminate
@@ -383,22 +430,25 @@ size_t trace_smem_bytes(uint32_t staged_nodes, uint32_t staged_tris) {
 
 cudaError_t trace_configure() {
     cudaError_t e;
-#define CFG(S, C)                                                                                                     \
-    if ((e = cudaFuncSetAttribute(k_trace<kTraceBlock, kTraceSmemStack, S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  kTraceMaxSmem)) != cudaSuccess)                                                     \
+#define CFG(S, L, C)                                                                                 \
+    if ((e = cudaFuncSetAttribute(k_trace<kTraceBlock, kTraceSmemStack, S, L, C>,                     \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kTraceMaxSmem)) != cudaSuccess) \
         return e;
-    CFG(false, false) CFG(false, true) CFG(true, false) CFG(true, true)
+    CFG(false, false, false) CFG(false, false, true) CFG(true, false, false) CFG(true, false, true)
+    CFG(false, true, false) CFG(false, true, true) CFG(true, true, false) CFG(true, true, true)
 #undef CFG
     return cudaSuccess;
 }
 
-void trace_launch(const TraceArgs& a, unsigned grid, bool staged, bool count, cudaStream_t st) {
+void trace_launch(const TraceArgs& a, unsigned grid, bool staged, bool two_level, bool count, cudaStream_t st) {
     const size_t smem = staged ? trace_smem_bytes(a.num_nodes, a.num_tris) : trace_smem_bytes(0, 0);
+#define GO(S, L, C) k_trace<kTraceBlock, kTraceSmemStack, S, L, C><<<grid, kTraceBlock, smem, st>>>(a)
     if (staged) {
-        if (count) k_trace<kTraceBlock, kTraceSmemStack, true, true><<<grid, kTraceBlock, smem, st>>>(a);
-        else k_trace<kTraceBlock, kTraceSmemStack, true, false><<<grid, kTraceBlock, smem, st>>>(a);
+        if (two_level) { if (count) GO(true, true, true); else GO(true, true, false); }
+        else { if (count) GO(true, false, true); else GO(true, false, false); }
     } else {
-        if (count) k_trace<kTraceBlock, kTraceSmemStack, false, true><<<grid, kTraceBlock, smem, st>>>(a);
-        else k_trace<kTraceBlock, kTraceSmemStack, false, false><<<grid, kTraceBlock, smem, st>>>(a);
+        if (two_level) { if (count) GO(false, true, true); else GO(false, true, false); }
+        else { if (count) GO(false, false, true); else GO(false, false, false); }
     }
+#undef GO
 }

@@ -21,7 +21,9 @@ struct TraceArgs {
     uint32_t* fetch_ctr;           // global ray fetch counter (zeroed before launch)
     const Node8* nodes;            // BVH8 nodes, BFS order
     const WoopTri* tris;           // triangle records, leaf order
-    uint32_t num_nodes, num_tris;  // sizes (the STAGED instance copies all of them into shared memory)
+    uint32_t num_nodes, num_tris;  // array sizes (the STAGED instance copies all of them into shared memory)
+    uint32_t root;                 // node the traversal starts from (0, or the instance-level root)
+    uint32_t num_mesh_tris;        // TWO_LEVEL: records from this index on are instances
     int refill_below;              // refill a warp's idle lanes when fewer than this many are live
     int steps_per_refill;          // traversal iterations between two refill votes
     uint32_t magic;                // 0x47000000 (float 32768): byte->float permute constant, see trace.cu byte_f
@@ -30,4 +32,4 @@ struct TraceArgs {
 
 size_t trace_smem_bytes(uint32_t staged_nodes, uint32_t staged_tris);
 cudaError_t trace_configure();
-void trace_launch(const TraceArgs& a, unsigned grid, bool staged, bool count, cudaStream_t st);
+void trace_launch(const TraceArgs& a, unsigned grid, bool staged, bool two_level, bool count, cudaStream_t st);

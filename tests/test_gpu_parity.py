@@ -397,6 +397,105 @@ def test_soup_image_parity(soup20k):
     assert abs(rays_gpu - rays) <= 1e-4 * rays
 
 
+# ------------------------------------------------------------------------------------------ K8: instanced scenes
+def instance_grid(n_side=3, spacing=2.5, jitter=True, seed=3):
+    """n_side^3 instance transforms (3x4 row-major): translations on a grid, plus a rotation about z and a uniform
+    scale per instance when `jitter` (BASELINE config 5 is the plain grid)."""
+    rng = np.random.default_rng(seed)
+    xf = []
+    c = 0.5 * (n_side - 1) * spacing
+    for ix in range(n_side):
+        for iy in range(n_side):
+            for iz in range(n_side):
+                a = rng.uniform(0, 2 * np.pi) if jitter else 0.0
+                sc = rng.uniform(0.6, 1.3) if jitter else 1.0
+                R = sc * np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+                t = np.array([ix * spacing - c, iy * spacing - c - 1.0, iz * spacing - c])
+                xf.append(np.concatenate([R, t[:, None]], 1).reshape(12))
+    return np.asarray(xf, np.float32)
+
+
+@pytest.fixture(scope="module")
+def pt_instanced(cornell):
+    xf = instance_grid()
+    pt = bpt.PathTracer(0)
+    pt.upload_mesh(*cornell)
+    pt.set_instances(xf)
+    info = pt.build_accel()
+    assert info.num_instances == len(xf) and info.num_tlas_nodes8 >= 1
+    yield pt, xf, O.Scene(*cornell, xforms=xf)
+    pt.close()
+
+
+def test_instanced_trace_rays(pt_instanced, cornell):
+    pt, xf, scene = pt_instanced
+    ntris = len(cornell[1]) // 3
+    rays = random_rays(200_000, 11, lo=(-5, -6, -5), hi=(5, 4, 5))
+    gpu = pt.trace_rays(rays)
+    ref = scene.intersect(rays, 64)
+    assert (ref["prim"] != O.MISS).mean() > 0.3 and ref["prim"][ref["prim"] != O.MISS].max() >= 26 * ntris
+    # the Cornell asset holds exact duplicate triangles: compare modulo the duplicates (T9)
+    dup = {20: 16, 21: 17, 32: 30, 33: 31}
+    def canon(p):
+        q = p.copy()
+        hit = q != O.MISS
+        inst, tri = q[hit] // ntris, q[hit] % ntris
+        for a, b in dup.items():
+            tri[tri == a] = b
+        q[hit] = inst * ntris + tri
+        return q
+    g2, r2 = gpu.copy(), ref.copy()
+    g2["prim"], r2["prim"] = canon(gpu["prim"]), canon(ref["prim"])
+    compare_hits(g2, r2, None, max_mismatch=5e-4)
+    # staged (whole BVH in shared memory) and global instances of the kernel agree bit for bit
+    pt.set_option(bpt.OPT_SMEM_TOP_NODES, 0)
+    assert pt.accel_info().top_nodes_smem == 0
+    assert np.array_equal(pt.trace_rays(rays), gpu)
+    pt.set_option(bpt.OPT_SMEM_TOP_NODES, 1 << 20)
+    assert pt.accel_info().top_nodes_smem > 0
+
+
+def test_instanced_image_parity(pt_instanced):
+    pt, xf, scene = pt_instanced
+    kw = dict(cam_origin=(0.0, -1.0, 14.0), cam_target=(0.0, -1.0, 11.0))
+    pt.clear_image()
+    img = pt.render(bpt.default_params(160, 160, 4, 6, **kw))
+    ref, rays = scene.render(O.default_params(160, 160, 4, 6, **kw), 32)
+    assert O.rel_l2(img, ref) <= 1e-3
+    assert (ref[..., :3] != np.array([0.7, 0.6, 0.5], np.float32)).any(axis=-1).mean() > 0.2  # the grid is in frame
+
+
+def test_single_transformed_instance_matches_transformed_mesh(cornell):
+    """One instance with a non-identity transform == the mesh with that transform baked into its vertices."""
+    verts, idx, faces = cornell
+    M = np.array([[0.8, 0, 0.6, 0.3], [0, 1, 0, -0.2], [-0.6, 0, 0.8, 0.1]], np.float32)
+    baked = np.stack([M[r, 0] * verts[:, 0] + M[r, 1] * verts[:, 1] + M[r, 2] * verts[:, 2] + M[r, 3] for r in range(3)], 1).astype(np.float32)
+    rays = random_rays(50_000, 12)
+    with bpt.PathTracer(0) as a, bpt.PathTracer(0) as b:
+        a.upload_mesh(verts, idx, faces); a.set_instances(M.reshape(1, 12)); a.build_accel()
+        b.upload_mesh(baked, idx, faces); b.build_accel()
+        ha, hb = a.trace_rays(rays), b.trace_rays(rays)
+        same = ha["prim"] == hb["prim"]
+        assert 1.0 - same.mean() <= 5e-4
+        np.testing.assert_allclose(ha["t"][same], hb["t"][same], rtol=2e-4, atol=2e-4)
+        pa, pb = bpt.default_params(96, 96, 2, 4), bpt.default_params(96, 96, 2, 4)
+        assert O.rel_l2(a.render(pa), b.render(pb)) <= 1e-3
+
+
+def test_instance_errors(cornell):
+    with bpt.PathTracer(0) as pt:
+        with pytest.raises(bpt.BptError):
+            pt.set_instances(np.eye(3, 4, dtype=np.float32).reshape(1, 12))   # before upload
+        pt.upload_mesh(*cornell)
+        with pytest.raises(bpt.BptError):
+            pt.set_instances(np.zeros((1, 12), np.float32))                      # singular
+        pt.set_instances(np.eye(3, 4, dtype=np.float32).reshape(1, 12))
+        with pytest.raises(bpt.BptError):
+            pt.trace(bpt.default_params(8, 8, 1, 1))                             # instances invalidate the build
+        pt.build_accel()
+        pt.trace(bpt.default_params(8, 8, 1, 1))
+
+
 def test_error_paths(cornell):
     verts, idx, faces = cornell
     with bpt.PathTracer(0) as pt:
