@@ -39,10 +39,15 @@ WORKLOADS = {
                    config="configs[2]: synthetic 1 M triangle soup, 1920x1080, 64 spp (8 steps of 8 spp), depth 8"),
     "cornell": dict(tris=0, seed=0, width=1024, height=1024, spp=32, depth=8, full_spp=256,
                     config="configs[1]: CornellBox-Original.obj, 1024x1024, 256 spp (8 steps of 32 spp), depth 8"),
+    "cornell1000": dict(tris=0, seed=0, width=2048, height=2048, spp=32, depth=8, full_spp=512, instances=10,
+                        cam_origin=(0.0, -1.0, 55.0), cam_target=(0.0, -1.0, 52.0),
+                        config="configs[4]: Cornell box x1000 instances (10x10x10 grid, pitch 2.5, two-level BVH), 2048x2048, "
+                               "512 spp (16 steps of 32 spp), depth 8, camera pulled back to z=55"),
 }
 METRIC = "Mray/s"
 TILE_BLOCK = 8          # rows per interleaved block
-CPU_SAMPLE_ROWS = 64    # rows of the image the CPU baseline renders (spread uniformly), 1 spp
+CPU_SAMPLE_ROWS = 128   # rows of the image the CPU baseline renders per step (spread uniformly over the image)
+CPU_SAMPLE_SPP = 4      # samples per pixel of those rows: ~10 s of work on 16 cores for the 10 M soup
 
 
 def parse_args(argv=None):
@@ -202,15 +207,29 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU legs (oracle)
+def instance_grid(n, pitch=2.5):
+    """n^3 translations (3x4 row-major) on a grid centred on the box centre (0,-1,0): BASELINE config 5."""
+    c = 0.5 * (n - 1) * pitch
+    xf = np.zeros((n * n * n, 3, 4), np.float32)
+    xf[:, 0, 0] = xf[:, 1, 1] = xf[:, 2, 2] = 1.0
+    g = np.stack(np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij"), -1).reshape(-1, 3)
+    xf[:, :, 3] = g * pitch - c
+    return xf.reshape(-1, 12)
+
+
+def camera_kwargs(w):
+    return {k: w[k] for k in ("cam_origin", "cam_target") if k in w}
+
+
 def oracle_scene(w):
     """The workload's scene in the oracle (CPU restatement of the reference). Checker / baseline only."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     if w["tris"]:
         verts, idx, faces = O.soup(w["tris"], w["seed"])
-    else:
-        verts, idx, faces, _ = O.load_cornell_golden()
-    return O, O.Scene(verts, idx, faces)
+        return O, O.Scene(verts, idx, faces)
+    verts, idx, faces, _ = O.load_cornell_golden()
+    return O, O.Scene(verts, idx, faces, xforms=instance_grid(w["instances"]) if w.get("instances") else None)
 
 
 def cpu_sample_params(O, w, frame):
@@ -218,12 +237,12 @@ def cpu_sample_params(O, w, frame):
     while w["height"] % rows:
         rows -= 1
     # `rows` single rows spread uniformly over the image: the interleaved tiling with 1-row blocks, rank 0
-    return O.default_params(w["width"], w["height"], 1, w["depth"], frame, tile_block=1, tile_nranks=w["height"] // rows,
-                            tile_rank=0), rows
+    return O.default_params(w["width"], w["height"], CPU_SAMPLE_SPP, w["depth"], frame, tile_block=1,
+                            tile_nranks=w["height"] // rows, tile_rank=0, **camera_kwargs(w)), rows
 
 
 def cpu_baseline(w, steps=1, warmup=0):
-    """Oracle on all host cores over a bounded sample: CPU_SAMPLE_ROWS rows x full width x 1 spp per step."""
+    """Oracle on all host cores over a bounded sample: CPU_SAMPLE_ROWS rows x full width x CPU_SAMPLE_SPP spp per step."""
     O, scene = oracle_scene(w)
     cores = int(O.lib().orc_hardware_threads())
     img = np.zeros((w["height"], w["width"], 4), np.float32)
@@ -237,7 +256,7 @@ def cpu_baseline(w, steps=1, warmup=0):
             rays_total += rays
             secs += dt
     return {"value": rays_total / secs / 1e6, "unit": METRIC, "cores": cores, "kind": "port",
-            "sample": f"{rows} rows spread uniformly over the {w['width']}x{w['height']} image x 1 spp x depth "
+            "sample": f"{rows} rows spread uniformly over the {w['width']}x{w['height']} image x {CPU_SAMPLE_SPP} spp x depth "
                       f"{w['depth']} per step, {steps} step(s): {rays_total} rays in {secs:.2f} s (oracle's own median-split BVH)"}, \
         rays_total, secs
 
@@ -280,7 +299,7 @@ def run_ours(args):
     tile = tile_kwargs(H, d.world, d.rank)
 
     def params(frame):
-        return bpt.default_params(W, H, w["spp"], w["depth"], frame, **tile)
+        return bpt.default_params(W, H, w["spp"], w["depth"], frame, **tile, **camera_kwargs(w))
 
     # ---- scene + build (once per job; reported, not part of `value`)
     if w["tris"]:
@@ -290,6 +309,8 @@ def run_ours(args):
         import oracle_lib as O  # fixture loader only (tests/golden/cornell_scene.json)
         verts, idx, faces, _ = O.load_cornell_golden()
         pt.upload_mesh(verts, idx, faces)
+        if w.get("instances"):
+            pt.set_instances(instance_grid(w["instances"]))
     info = pt.build_accel()
     build_ms = pt.stats().build_ms
     if d.active:
@@ -381,6 +402,8 @@ def run_ours(args):
         tw0 = time.perf_counter()
         e0.record(stream)
         pt.upload_mesh(hv, hi, hf)                   # H2D: 72 B per triangle
+        if w.get("instances"):
+            pt.set_instances(instance_grid(w["instances"]))
         pt.build_accel()
         for s in range(K):
             pt.trace(params(s))
@@ -406,7 +429,7 @@ def run_ours(args):
         out = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": d.world, "steps": K, "warmup": WU,
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic",
-               "config": {"workload": w["name"], "baseline_config": w["config"], "tris": info.num_tris, "width": W, "height": H,
+               "config": {"workload": w["name"], "baseline_config": w["config"], "tris": info.num_tris, "instances": info.num_instances, "width": W, "height": H,
                           "spp_per_step": w["spp"], "depth": w["depth"], "sampler": "uniform hemisphere (reference)",
                           "tiling": (f"{tile['tile_block']}-row blocks round-robin over {d.world} GPUs + 1 NCCL all-gather"
                                      if tile else "single tile"),
