@@ -129,6 +129,7 @@ typedef struct bpt_accel_info {
 #define BPT_OPT_USE_GRAPH        6 /* 1: replay a captured CUDA graph per sample pass        */
 #define BPT_OPT_PASS_PATHS       10 /* target paths per sample pass: a pass carries min(spp, this / tile pixels)
                                       samples of every tile pixel (default 2^27); results do not depend on it */
+#define BPT_OPT_TOP_NODES        11 /* big scenes: BVH8 nodes of the BFS prefix (top of the tree) staged in shared memory */
 #define BPT_OPT_TRACE_REFILL_BELOW 8     /* traversal: refill a warp when fewer lanes than this are live */
 #define BPT_OPT_TRACE_STEPS_PER_REFILL 9 /* traversal: loop iterations between two refill votes           */
 

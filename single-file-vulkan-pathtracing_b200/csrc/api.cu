@@ -45,6 +45,8 @@ struct bpt_context {
     bool two_level = false;
     bool built = false, built_nodes_ok = false;
     bool staged = false;  // the traversal kernel instance that holds the whole BVH in shared memory is in use
+    uint32_t top_nodes = 0;  // else: BFS prefix staged in shared memory
+    int64_t opt_top_nodes = 600;  // BPT_OPT_TOP_NODES
 
     // wavefront buffers
     size_t cap_paths = 0;
@@ -202,6 +204,7 @@ TraceArgs make_trace_args(bpt_context* c, const float4* rays, uint4* hits, const
     a.num_nodes = c->blas.num_nodes + (c->two_level ? c->tlas.num_nodes : 0u);
     a.num_tris = c->ntris + (c->two_level ? c->ninst : 0u);
     a.root = c->two_level ? c->blas.num_nodes : 0u;
+    a.top_nodes = c->staged ? 0u : c->top_nodes;
     a.num_mesh_tris = c->ntris;
     a.refill_below = c->refill_below; a.steps_per_refill = c->steps_per_refill;
     a.magic = 0x47000000u;
@@ -230,6 +233,10 @@ void plan_staging(bpt_context* c) {
     const uint64_t recs = (uint64_t)c->ntris + (c->two_level ? c->ninst : 0u);
     c->staged = c->built_nodes_ok && nodes <= (uint64_t)c->opt_stage_max_nodes &&
                 trace_smem_bytes((uint32_t)nodes, (uint32_t)recs) <= (size_t)kTraceMaxSmem;
+    // the BFS prefix only makes sense for a single-level array (node 0 = root)
+    const uint64_t cap = (kTraceMaxSmem - trace_smem_bytes(0, 0)) / BPT_NODE_BYTES;
+    c->top_nodes = (c->staged || c->two_level || c->opt_stage_max_nodes == 0) ? 0u
+                   : (uint32_t)std::min<uint64_t>(std::min<uint64_t>((uint64_t)c->opt_top_nodes, nodes), cap);
 }
 
 // inverse of a row-major 3x4 affine transform, in double; false if singular
@@ -336,6 +343,11 @@ int bpt_set_option(bpt_context* c, int option, int64_t value) {
         case BPT_OPT_SMEM_TOP_NODES:
             if (value < 0) return bpt_fail(c, BPT_E_INVALID, "node count must be >= 0");
             c->opt_stage_max_nodes = value;
+            if (c->built) plan_staging(c);
+            return BPT_OK;
+        case BPT_OPT_TOP_NODES:
+            if (value < 0) return bpt_fail(c, BPT_E_INVALID, "node count must be >= 0");
+            c->opt_top_nodes = value;
             if (c->built) plan_staging(c);
             return BPT_OK;
         case BPT_OPT_TRACE_REFILL_BELOW:
@@ -494,7 +506,7 @@ int bpt_accel_info_get(bpt_context* c, bpt_accel_info* out) {
     out->num_instances = c->ninst;
     out->num_nodes8 = c->blas.num_nodes;
     out->num_binary_nodes = c->ntris - 1;
-    out->top_nodes_smem = c->staged ? c->blas.num_nodes : 0;
+    out->top_nodes_smem = c->staged ? c->blas.num_nodes + (c->two_level ? c->tlas.num_nodes : 0u) : c->top_nodes;
     out->max_depth8 = c->blas.depth;
     out->num_tlas_nodes8 = c->two_level ? c->tlas.num_nodes : 0;
     out->bytes_nodes = (uint64_t)c->blas.num_nodes * BPT_NODE_BYTES;

@@ -38,8 +38,8 @@
 //     lanes that did not reach the node step as two groups and the node step runs twice per iteration at 12/32 lanes
 //   * small scenes (Cornell box: every node and triangle fits) run the STAGED instance: the BVH is copied into
 //     shared memory once per CTA by TMA bulk copies (cp.async.bulk + mbarrier) and never touched in global memory
-//     again; big scenes run the global instance (staging only the top of the tree bought nothing measurable: its
-//     nodes are L1-resident anyway, and the dual shared/global path cost issue slots)
+//     again; big scenes run the global instance, which stages the BFS prefix of the node array (the top of the
+//     tree, 600 nodes by default) the same way — worth +1 % on the 10 M soup; more than ~1000 nodes starves L1
 #include "trace.cuh"
 
 namespace {
@@ -156,14 +156,16 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
     uint2* slut = reinterpret_cast<uint2*>(smem_raw + 16);  // byte o of slut[b]: bit p = bit (p ^ o) of b
     uint2* sstack = reinterpret_cast<uint2*>(smem_raw + kTraceSmemFixed);
     unsigned char* snodes = smem_raw + kTraceSmemFixed + (size_t)SSTACK * BLOCK * sizeof(uint2);  // STAGED only
-    unsigned char* stris = snodes + (size_t)a.num_nodes * BPT_NODE_BYTES;
+    unsigned char* stris = snodes + (size_t)a.num_nodes * BPT_NODE_BYTES;  // STAGED only
 
     const uint32_t nrays = *a.count_ptr;
     if (nrays == 0u) return;  // uniform across the grid: an exhausted bounce costs one launch and nothing else
 
-    // ---- STAGED: the whole BVH (nodes, then triangles) moves into shared memory with TMA bulk copies
-    if (STAGED) {
-        const uint32_t node_bytes = a.num_nodes * BPT_NODE_BYTES, tri_bytes = a.num_tris * BPT_TRI_BYTES;
+    // ---- STAGED: the whole BVH (nodes, then triangles) moves into shared memory with TMA bulk copies;
+    //      otherwise the BFS prefix of a.top_nodes nodes (the top of the tree) does
+    if (STAGED || a.top_nodes) {
+        const uint32_t node_bytes = (STAGED ? a.num_nodes : a.top_nodes) * BPT_NODE_BYTES;
+        const uint32_t tri_bytes = a.num_tris * BPT_TRI_BYTES * (STAGED ? 1u : 0u);  // triangles only in the STAGED instance
         if (threadIdx.x == 0) mbar_init(bar, 1);
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -171,8 +173,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
             constexpr uint32_t kChunk = 32768u;
             for (uint32_t off = 0; off < node_bytes; off += kChunk)
                 tma_bulk_g2s(snodes + off, reinterpret_cast<const unsigned char*>(a.nodes) + off, min(kChunk, node_bytes - off), bar);
-            for (uint32_t off = 0; off < tri_bytes; off += kChunk)
-                tma_bulk_g2s(stris + off, reinterpret_cast<const unsigned char*>(a.tris) + off, min(kChunk, tri_bytes - off), bar);
+            if (STAGED)
+                for (uint32_t off = 0; off < tri_bytes; off += kChunk)
+                    tma_bulk_g2s(stris + off, reinterpret_cast<const unsigned char*>(a.tris) + off, min(kChunk, tri_bytes - off), bar);
         }
         mbar_wait(bar, 0);
     }
@@ -303,6 +306,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                 const uint32_t node = G.x + rel;
                 U8 v0, v1, v2;
                 if (STAGED) {
+                    const uint32_t np = snodes_a + node * BPT_NODE_BYTES;
+                    v0 = lds256(np); v1 = lds256(np + 32u); v2.lo = lds128(np + 64u); v2.hi = make_uint4(lds32(np + 80u), lds32(np + 84u), 0u, 0u);
+                } else if (node < a.top_nodes) {  // staged top of the tree: no miss-path traffic for the hottest levels
                     const uint32_t np = snodes_a + node * BPT_NODE_BYTES;
                     v0 = lds256(np); v1 = lds256(np + 32u); v2.lo = lds128(np + 64u); v2.hi = make_uint4(lds32(np + 80u), lds32(np + 84u), 0u, 0u);
                 } else {
@@ -441,7 +447,7 @@ cudaError_t trace_configure() {
 }
 
 void trace_launch(const TraceArgs& a, unsigned grid, bool staged, bool two_level, bool count, cudaStream_t st) {
-    const size_t smem = staged ? trace_smem_bytes(a.num_nodes, a.num_tris) : trace_smem_bytes(0, 0);
+    const size_t smem = staged ? trace_smem_bytes(a.num_nodes, a.num_tris) : trace_smem_bytes(a.top_nodes, 0);
 #define GO(S, L, C) k_trace<kTraceBlock, kTraceSmemStack, S, L, C><<<grid, kTraceBlock, smem, st>>>(a)
     if (staged) {
         if (two_level) { if (count) GO(true, true, true); else GO(true, true, false); }

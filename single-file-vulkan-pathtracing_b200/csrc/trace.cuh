@@ -22,6 +22,7 @@ struct TraceArgs {
     const Node8* nodes;            // BVH8 nodes, BFS order
     const WoopTri* tris;           // triangle records, leaf order
     uint32_t num_nodes, num_tris;  // array sizes (the STAGED instance copies all of them into shared memory)
+    uint32_t top_nodes;            // global instance: BFS prefix of the node array staged in shared memory
     uint32_t root;                 // node the traversal starts from (0, or the instance-level root)
     uint32_t num_mesh_tris;        // TWO_LEVEL: records from this index on are instances
     int refill_below;              // refill a warp's idle lanes when fewer than this many are live

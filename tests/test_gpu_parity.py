@@ -235,13 +235,15 @@ def test_soup_build_and_trace(soup20k):
         gpu = pt.trace_rays(rays)
         ref = scene.intersect(rays, 64)
         compare_hits(gpu, ref, None, max_mismatch=5e-4)
-        # staging on/off must not change a single hit
-        pt.set_option(bpt.OPT_SMEM_TOP_NODES, 0)
-        gpu0 = pt.trace_rays(rays)
-        assert np.array_equal(gpu0, gpu)
-        pt.set_option(bpt.OPT_SMEM_TOP_NODES, 2000)
-        gpu1 = pt.trace_rays(rays)
-        assert np.array_equal(gpu1, gpu)
+        # staging must not change a single hit: default BFS prefix, no prefix, the largest prefix that fits, and the
+        # whole-BVH instance switched off
+        assert 0 < pt.accel_info().top_nodes_smem <= 600
+        for opt, val in ((bpt.OPT_TOP_NODES, 0), (bpt.OPT_TOP_NODES, 1 << 20), (bpt.OPT_SMEM_TOP_NODES, 0)):
+            pt.set_option(opt, val)
+            assert np.array_equal(pt.trace_rays(rays), gpu), (opt, val)
+        assert pt.accel_info().top_nodes_smem == 0
+        pt.set_option(bpt.OPT_SMEM_TOP_NODES, 1 << 20)
+        pt.set_option(bpt.OPT_TOP_NODES, 600)
         # instrumented kernel: same hits, plausible counters
         pt.set_option(bpt.OPT_COUNT_TRAVERSAL, 1)
         pt.reset_stats()
