@@ -42,6 +42,7 @@ struct bpt_context {
     Bvh8 tlas;                      // over the instances (two-level scenes only)
     WoopTri* d_woop = nullptr;      // [triangle records | instance records]
     Node8* d_nodes_all = nullptr;   // two-level scenes: [mesh nodes | instance nodes]
+    float4* d_srec = nullptr;       // shading records, 64 B per primitive (shade.cuh)
     bool two_level = false;
     bool built = false, built_nodes_ok = false;
     bool staged = false;  // the traversal kernel instance that holds the whole BVH in shared memory is in use
@@ -324,7 +325,7 @@ void bpt_destroy(bpt_context* c) {
     free_scene(c);
     free_paths(c);
     bvh8_free(c->blas); bvh8_free(c->tlas);
-    cudaFree(c->d_nodes_all); cudaFree(c->frame_sum);
+    cudaFree(c->d_nodes_all); cudaFree(c->d_srec); cudaFree(c->frame_sum);
     cudaFree(c->d_woop); cudaFree(c->image); cudaFree(c->image_linear); cudaFree(c->counters); cudaFree(c->d_stats);
     for (auto& p : c->frame_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto& p : c->trace_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
@@ -466,6 +467,10 @@ int bpt_build_accel(bpt_context* c) {
     c->d_woop = nullptr; c->d_nodes_all = nullptr;
     BPT_CUDA_TRY(c, cudaMalloc(&c->d_woop, (size_t)nrec * sizeof(WoopTri) + 32));
     bvh8_launch_woop(c->blas, c->d_verts, c->d_idx, c->d_woop, c->stream);
+    cudaFree(c->d_srec);
+    c->d_srec = nullptr;
+    BPT_CUDA_TRY(c, cudaMalloc(&c->d_srec, (size_t)c->ntris * 64));
+    launch_shade_records(c->d_verts, c->d_idx, c->d_faces, c->ntris, c->d_srec, c->stream);
     uint32_t depth = c->blas.depth;
     if (c->two_level) {
         // K8: the same builder over the instances' world boxes (main.cpp:514-538), then one node array [mesh | instances]
@@ -536,7 +541,7 @@ int bpt_trace(bpt_context* c, const bpt_params* p) {
         c->tile_nranks = f.tile_block ? f.tile_nranks : 1;
         c->tile_rank = f.tile_block ? f.tile_rank : 0;
     }
-    SceneView sv{c->d_verts, c->d_idx, c->d_faces, c->d_xforms, c->ntris};
+    SceneView sv{c->d_srec, c->d_xforms, c->ntris};
     uint32_t* counts = c->counters;
     uint32_t* fetch = c->counters + (kMaxDepth + 1);
 
@@ -683,7 +688,7 @@ int bpt_trace_rays(bpt_context* c, const float* rays, uint32_t n, void* hits) {
     BPT_CUDA_TRY(c, cudaMemcpyAsync(counts, &init[0], 4, cudaMemcpyHostToDevice, c->stream));
     BPT_CUDA_TRY(c, cudaMemcpyAsync(fetch, &init[1], 4, cudaMemcpyHostToDevice, c->stream));
     launch_trace(c, make_trace_args(c, c->q[0].rays, c->hits, counts, fetch));
-    launch_refine_hits(SceneView{c->d_verts, c->d_idx, c->d_faces, c->d_xforms, c->ntris}, c->q[0].rays, c->hits, n, c->stream);
+    launch_refine_hits(SceneView{c->d_srec, c->d_xforms, c->ntris}, c->q[0].rays, c->hits, n, c->stream);
     BPT_CUDA_TRY(c, cudaMemcpyAsync(hits, c->hits, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     BPT_CUDA_TRY(c, cudaGetLastError());

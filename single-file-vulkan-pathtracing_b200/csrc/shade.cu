@@ -64,12 +64,36 @@ __global__ void k_generate(FrameParams p, uint32_t s0, uint32_t ns, PathQueue q,
 }
 
 // ---------------------------------------------------------------- K11
-__device__ __forceinline__ V3 load_vertex(const SceneView& s, uint32_t prim, int c, const float* m) {
-    const float* v = s.verts + 3 * (size_t)__ldg(&s.indices[3 * (size_t)prim + c]);
-    const float x = __ldg(v), y = __ldg(v + 1), z = __ldg(v + 2);
-    if (!m) return {x, y, z};
-    return {m[0] * x + m[1] * y + m[2] * z + m[3], m[4] * x + m[5] * y + m[6] * z + m[7],
-            m[8] * x + m[9] * y + m[10] * z + m[11]};
+// Shading record of a primitive (64 bytes, 32-byte aligned, built once by k_shade_records): the three vertices the
+// index buffer names (closesthit.rchit:52-54) and its Face {Kd, Ke} (:60-62), so that shading gathers two sectors
+// instead of an index triple, three vertices and a face record.
+struct ShadeRec { V3 v0, v1, v2, kd, ke; };
+__device__ __forceinline__ V3 xform(const float* m, V3 p) {
+    if (!m) return p;
+    return {m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7],
+            m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]};
+}
+__device__ __forceinline__ ShadeRec load_rec(const SceneView& s, uint32_t prim, const float* m) {
+    const float4* r = s.srec + 4 * (size_t)prim;
+    const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), d = __ldg(r + 3);
+    return {xform(m, V3{a.x, a.y, a.z}), xform(m, V3{a.w, b.x, b.y}), xform(m, V3{b.z, b.w, c.x}), V3{c.y, c.z, c.w},
+            V3{d.x, d.y, d.z}};
+}
+__global__ void k_shade_records(const float* __restrict__ verts, const uint32_t* __restrict__ idx,
+                                const float* __restrict__ faces, uint32_t n, float4* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float f[16];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* v = verts + 3 * (size_t)idx[3 * (size_t)i + c];
+        f[3 * c] = v[0]; f[3 * c + 1] = v[1]; f[3 * c + 2] = v[2];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) f[9 + k] = faces[6 * (size_t)i + k];
+    f[15] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) out[4 * (size_t)i + q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
 }
 
 // Barycentrics (u,v) of v1,v2 and the distance t at the ray/triangle intersection, Moeller-Trumbore with one IEEE
@@ -98,7 +122,8 @@ __global__ void k_refine_hits(SceneView s, const float4* __restrict__ rays, uint
     const uint32_t inst = s.xforms ? h.w / s.ntris : 0u;
     const uint32_t prim = s.xforms ? h.w - inst * s.ntris : h.w;
     const float* m = s.xforms ? s.xforms + 12 * (size_t)inst : nullptr;
-    const V3 v0 = load_vertex(s, prim, 0, m), v1 = load_vertex(s, prim, 1, m), v2 = load_vertex(s, prim, 2, m);
+    const ShadeRec sr = load_rec(s, prim, m);
+    const V3 v0 = sr.v0, v1 = sr.v1, v2 = sr.v2;
     const float4 ro = rays[2 * (size_t)i], rd = rays[2 * (size_t)i + 1];
     float u, v, t = __uint_as_float(h.x);
     barycentrics(V3{ro.x, ro.y, ro.z}, V3{rd.x, rd.y, rd.z}, v0, v1, v2, u, v, t);
@@ -132,7 +157,8 @@ __global__ void k_shade(FrameParams p, SceneView s, uint32_t depth, PathQueue in
             const uint32_t inst = s.xforms ? h.w / s.ntris : 0u;
             const uint32_t prim = s.xforms ? h.w - inst * s.ntris : h.w;
             const float* m = s.xforms ? s.xforms + 12 * (size_t)inst : nullptr;
-            const V3 v0 = load_vertex(s, prim, 0, m), v1 = load_vertex(s, prim, 1, m), v2 = load_vertex(s, prim, 2, m);
+            const ShadeRec sr = load_rec(s, prim, m);
+            const V3 v0 = sr.v0, v1 = sr.v1, v2 = sr.v2;
             // the barycentrics that shading consumes are derived from the original vertices, so the hit position
             // carries no traversal-format error (the traversal kernel only names the closest triangle)
             const float4 ro = in.rays[2 * (size_t)i], rd = in.rays[2 * (size_t)i + 1];
@@ -141,8 +167,7 @@ __global__ void k_shade(FrameParams p, SceneView s, uint32_t depth, PathQueue in
             const float b0 = 1.0f - u - v;                           // closesthit.rchit:56
             const V3 pos = v0 * b0 + v1 * u + v2 * v;                // :57
             const V3 nrm = -normalize(cross(v1 - v0, v2 - v0));      // :58, :43-48
-            const float* f = s.faces + 6 * (size_t)prim;
-            const V3 kd{__ldg(f), __ldg(f + 1), __ldg(f + 2)}, ke{__ldg(f + 3), __ldg(f + 4), __ldg(f + 5)};
+            const V3 kd = sr.kd, ke = sr.ke;
             if (ke.x != 0.0f || ke.y != 0.0f || ke.z != 0.0f) {      // raygen.rgen:76 (adding 0 is exact)
                 const V3 c = w * ke;
                 float4 acc = path_color[pix];
@@ -294,6 +319,9 @@ void launch_gather_pass(uint32_t npix, uint32_t ns, float4* path_color, float4* 
 void launch_shade(const FrameParams& p, const SceneView& s, uint32_t depth, PathQueue in, const uint4* hits,
                   PathQueue out, uint32_t* counts, float4* path_color, uint32_t max_paths, cudaStream_t st) {
     k_shade<<<grid_for(max_paths), kBlock, 0, st>>>(p, s, depth, in, hits, out, counts, path_color);
+}
+void launch_shade_records(const float* verts, const uint32_t* idx, const float* faces, uint32_t ntris, float4* out, cudaStream_t st) {
+    k_shade_records<<<grid_for(ntris), kBlock, 0, st>>>(verts, idx, faces, ntris, out);
 }
 void launch_refine_hits(const SceneView& s, const float4* rays, uint4* hits, uint32_t n, cudaStream_t st) {
     k_refine_hits<<<grid_for(n), kBlock, 0, st>>>(s, rays, hits, n);

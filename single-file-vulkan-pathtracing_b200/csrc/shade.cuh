@@ -29,12 +29,12 @@ __host__ __device__ __forceinline__ uint32_t tile_store_row(const FrameParams& p
 }
 
 struct SceneView {
-    const float* verts;       // xyz triples (Vertex, main.cpp:19-21)
-    const uint32_t* indices;  // 3 per triangle
-    const float* faces;       // Kd.rgb Ke.rgb per triangle (Face, main.cpp:23-26)
+    const float4* srec;       // 4 x float4 per primitive: v0 v1 v2 Kd Ke - (built from the three arrays of
+                              // main.cpp:492-494 by launch_shade_records)
     const float* xforms;      // 3x4 row-major per instance, or null (single identity instance)
     uint32_t ntris;
 };
+void launch_shade_records(const float* verts, const uint32_t* idx, const float* faces, uint32_t ntris, float4* out, cudaStream_t st);
 
 // One wavefront queue (SoA): ray 2 x float4, state float4 {w.rgb, seed bits}, pixel u32 (= path id of the pass).
 struct PathQueue {
