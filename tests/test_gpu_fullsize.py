@@ -1,0 +1,107 @@
+"""BASELINE.json full sizes on the GPU, checked through size-independent properties (the oracle cannot render them in
+seconds): closest hits against the oracle on a sample of rays through the full 10 M-triangle BVH, tile / pass-grouping /
+staging invariance at 4096 x 4096, conservation of paths, and the instanced Cfg5 scene at full instance count."""
+import importlib
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+bpt = importlib.import_module("single-file-vulkan-pathtracing_b200")
+
+
+@pytest.fixture(scope="module")
+def pt_soup10m():
+    pt = bpt.PathTracer(0)
+    pt.upload_soup(10_000_000, 0x5EED0002)
+    info = pt.build_accel()
+    assert info.num_tris == 10_000_000 and info.num_nodes8 > 1_000_000
+    yield pt
+    pt.close()
+
+
+def test_soup10m_closest_hits_match_the_oracle(pt_soup10m):
+    rng = np.random.default_rng(7)
+    n = 100_000
+    o = rng.uniform((-1.1, -2.1, -1.1), (1.1, 0.1, 1.1), (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, np.full((n, 1), 1e-3, np.float32), d, np.full((n, 1), 1e4, np.float32)], 1)
+    gpu = pt_soup10m.trace_rays(rays)
+    verts, idx, faces = O.soup(10_000_000, 0x5EED0002)
+    ref = O.Scene(verts, idx, faces).intersect(rays, 64)
+    same = gpu["prim"] == ref["prim"]
+    assert 1.0 - same.mean() <= 5e-4
+    hit = same & (ref["prim"] != O.MISS)
+    assert hit.mean() > 0.5
+    err = np.abs(gpu["t"][hit].astype(np.float64) - ref["t"][hit]) - 2e-4 * np.abs(ref["t"][hit])
+    assert (err > 2e-4).mean() <= 1e-4 and err.max() <= 2e-3
+
+
+def test_soup10m_4096_invariances(pt_soup10m):
+    """One 4096 x 4096 frame of 2 spp: the image does not depend on how many samples a pass carries, on the staged
+    BFS prefix, or on rendering it as 4 interleaved tiles (the multi-GPU decomposition); rays are conserved."""
+    pt = pt_soup10m
+    W = H = 4096
+    p = bpt.default_params(W, H, 2, 8)
+    pt.clear_image(); pt.reset_stats()
+    full = pt.render(p)
+    st = pt.stats()
+    assert st.paths == W * H * 2 and W * H * 2 < st.rays_traced <= W * H * 2 * 8
+    sky = np.array([0.7, 0.6, 0.5], np.float32)
+    assert np.array_equal(full[0, 0, :3], sky) and np.array_equal(full[-1, -1, :3], sky)   # corners see the sky (KAT-2)
+    assert np.isfinite(full).all() and (full[H // 2 - 200:H // 2 + 200, W // 2 - 200:W // 2 + 200, :3] != sky).any()
+    for opt, val, back in ((bpt.OPT_PASS_PATHS, 1, 1 << 27), (bpt.OPT_TOP_NODES, 0, 600)):
+        pt.set_option(opt, val)
+        pt.clear_image(); pt.reset_stats()
+        assert np.array_equal(pt.render(p), full), opt
+        assert pt.stats().rays_traced == st.rays_traced
+        pt.set_option(opt, back)
+    acc = np.zeros_like(full)
+    for rank in range(4):
+        pt.clear_image()
+        acc += pt.render(bpt.default_params(W, H, 2, 8, tile_block=8, tile_nranks=4, tile_rank=rank))
+    assert np.array_equal(acc, full)
+    pt.clear_image()
+
+
+def test_cornell1000_instances_full_count(cornell):
+    """Cfg5 geometry: 10 x 10 x 10 instances, pitch 2.5. Closest hits against the oracle's world-space expansion, and
+    the staged (whole BVH in shared memory) and global kernel instances agree."""
+    n = 10
+    c = 0.5 * (n - 1) * 2.5
+    g = np.stack(np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij"), -1).reshape(-1, 3)
+    xf = np.zeros((n ** 3, 3, 4), np.float32)
+    xf[:, 0, 0] = xf[:, 1, 1] = xf[:, 2, 2] = 1.0
+    xf[:, :, 3] = g * 2.5 - c
+    xf = xf.reshape(-1, 12)
+    rng = np.random.default_rng(9)
+    m = 200_000
+    o = rng.uniform(-14, 14, (m, 3)).astype(np.float32)
+    d = rng.normal(size=(m, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, np.full((m, 1), 1e-3, np.float32), d, np.full((m, 1), 1e4, np.float32)], 1)
+    with bpt.PathTracer(0) as pt:
+        pt.upload_mesh(*cornell)
+        pt.set_instances(xf)
+        info = pt.build_accel()
+        assert info.num_instances == 1000 and info.top_nodes_smem > 0
+        gpu = pt.trace_rays(rays)
+        pt.set_option(bpt.OPT_SMEM_TOP_NODES, 0)
+        assert np.array_equal(pt.trace_rays(rays), gpu)
+    ref = O.Scene(*cornell, xforms=xf).intersect(rays, 64)
+    ntris = len(cornell[1]) // 3
+    dup = {20: 16, 21: 17, 32: 30, 33: 31}   # exact duplicate triangles of the asset (T9)
+
+    def canon(p):
+        q = p.copy()
+        h = q != O.MISS
+        inst, tri = q[h] // ntris, q[h] % ntris
+        for a, b in dup.items():
+            tri[tri == a] = b
+        q[h] = inst * ntris + tri
+        return q
+    same = canon(gpu["prim"]) == canon(ref["prim"])
+    assert 1.0 - same.mean() <= 5e-4 and (ref["prim"] != O.MISS).mean() > 0.3
