@@ -67,7 +67,7 @@ struct bpt_context {
     bool profile = false, count = false;
     int64_t opt_stage_max_nodes = 1 << 20;  // BPT_OPT_SMEM_TOP_NODES: 0 disables shared-memory staging
     int ctas_per_sm = 1;
-    int refill_below = 24, steps_per_refill = 4;
+    int refill_below = 30, steps_per_refill = 2;
     int64_t pass_paths = 1ll << 27;  // BPT_OPT_PASS_PATHS: target number of paths per sample pass
 
     // statistics

@@ -5,8 +5,9 @@
 // ray/triangle test of the driver's acceleration structure.
 //
 // Design (B200):
-//   * one persistent CTA per SM (grid = #SMs * ctas_per_sm); warps pull rays from a global counter
-//     and refill idle lanes (ballot + popc prefix) whenever fewer than kRefillBelow lanes are live
+//   * one persistent CTA per SM (grid = #SMs * ctas_per_sm); every warp keeps a pool of 32 rays in shared memory
+//     (one atomic on the global counter + two coalesced 128-bit loads per lane per pool) and tops its idle lanes
+//     up from it (ballot + popc prefix) whenever fewer than `refill_below` lanes are live
 //   * small scenes are staged once per CTA into shared memory with TMA bulk copies (cp.async.bulk +
 //     mbarrier complete_tx); big scenes read nodes / triangles with 256-bit loads through L1/L2
 //   * per-lane traversal stack: kSmemStack 8-byte entries in shared memory (thread-interleaved,
@@ -91,6 +92,12 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ void sts128f(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 as_float4(uint4 q) {
+    return make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -154,6 +161,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     uint2* slut = reinterpret_cast<uint2*>(smem_raw + 16);  // byte o of slut[b]: bit p = bit (p ^ o) of b
+    unsigned char* spool = smem_raw + 16 + 2048;  // ray pools: 32 rays x 32 B per warp
     uint2* sstack = reinterpret_cast<uint2*>(smem_raw + kTraceSmemFixed);
     unsigned char* snodes = smem_raw + kTraceSmemFixed + (size_t)SSTACK * BLOCK * sizeof(uint2);  // STAGED only
     unsigned char* stris = snodes + (size_t)a.num_nodes * BPT_NODE_BYTES;  // STAGED only
@@ -197,6 +205,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t stack_a = smem_u32(sstack + threadIdx.x);  // entry i of this lane: stack_a + i * BLOCK * 8
     const uint32_t snodes_a = smem_u32(snodes), stris_a = smem_u32(stris), slut_a = smem_u32(slut);
+    const uint32_t pool_a = smem_u32(spool) + (threadIdx.x >> 5) * 1024u;
     uint2 lstack[kLocalStack];
     const uint32_t magic = a.magic;
     const int refill_below = a.refill_below, steps_per_refill = a.steps_per_refill;
@@ -210,6 +219,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
     int sp = 0;
     uint32_t ray_idx = 0;
     bool active = false, exhausted = false;
+    uint32_t pool_base = 0u, pool_count = 0u, pool_next = 0u;  // warp-uniform: the warp's ray pool in shared memory
     unsigned long long cnt_nodes = 0, cnt_tris = 0, cnt_witer = 0, cnt_wnode = 0, cnt_wtri = 0, cnt_liter = 0;
 
 #define BPT_PUSH(E)                                                                               \
@@ -221,18 +231,33 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
 
     for (;;) {
         unsigned actmask = __ballot_sync(FULL, active);
-        if (!exhausted && __popc(actmask) < refill_below) {
-            const unsigned idle = ~actmask;
-            const int nidle = __popc(idle);
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(a.fetch_ctr, (uint32_t)nidle);
-            base = __shfl_sync(FULL, base, 0);
-            if (!active) {
-                uint32_t ri = base + __popc(idle & lt);
-                if (ri < nrays) {
-                    const float4 ro = __ldg(&a.rays[2 * (size_t)ri]);
-                    const float4 rd = __ldg(&a.rays[2 * (size_t)ri + 1]);
-                    ray_idx = ri;
+        if (__popc(actmask) < refill_below && (!exhausted || pool_next < pool_count)) {
+            // Refill idle lanes from the warp's ray pool: 32 consecutive rays fetched with one atomic and two coalesced
+            // 128-bit loads per lane into shared memory; lanes that finish take the next pool entries without touching
+            // global memory, so the warp can top itself up every iteration and runs ~31 live lanes instead of ~26.
+            unsigned idle = ~actmask;
+            while (idle) {
+                if (pool_next >= pool_count) {
+                    if (exhausted) break;
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(a.fetch_ctr, 32u);
+                    base = __shfl_sync(FULL, base, 0);
+                    if (base >= nrays) { exhausted = true; break; }
+                    pool_base = base; pool_count = min(32u, nrays - base); pool_next = 0u;
+                    if (lane < pool_count) {
+                        const float4 ro = __ldg(&a.rays[2 * (size_t)(base + lane)]);
+                        const float4 rd = __ldg(&a.rays[2 * (size_t)(base + lane) + 1]);
+                        sts128f(pool_a + lane * 32u, ro);
+                        sts128f(pool_a + lane * 32u + 16u, rd);
+                    }
+                    __syncwarp();
+                }
+                const uint32_t avail = pool_count - pool_next;
+                const uint32_t rank = __popc(idle & lt);
+                if (!active && rank < avail) {
+                    const uint32_t slot = pool_next + rank;
+                    const float4 ro = as_float4(lds128(pool_a + slot * 32u)), rd = as_float4(lds128(pool_a + slot * 32u + 16u));
+                    ray_idx = pool_base + slot;
                     r.ox = ro.x; r.oy = ro.y; r.oz = ro.z; r.tmin = ro.w;
                     r.dx = rd.x; r.dy = rd.y; r.dz = rd.z; r.tbest = rd.w;
                     const float eps = 1e-30f;  // keep 1/d finite; direction sign is kept
@@ -248,9 +273,11 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                     sp = 0;
                     active = true;
                 }
+                pool_next += min(avail, (uint32_t)__popc(idle));
+                __syncwarp();  // pool reads are done before a refill of the pool overwrites it
+                idle = ~__ballot_sync(FULL, active);
             }
-            if (base + (uint32_t)nidle >= nrays) exhausted = true;
-            actmask = __ballot_sync(FULL, active);
+            actmask = ~idle;
         }
         if (actmask == 0u) break;
 
