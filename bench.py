@@ -355,11 +355,10 @@ def run_ours(args):
     pt.set_option(bpt.OPT_COUNT_TRAVERSAL, 0)
     nodes_per_ray = sc.nodes_visited / max(sc.rays_traced, 1)
     tris_per_ray = sc.tris_tested / max(sc.rays_traced, 1)
-    # algorithmic bytes: 32 B ray + 16 B hit + the CONTENT of every node visited (80 B: origin, steps, bases,
-    # valid word, 48 plane bytes) and triangle tested (52 B: 3 Woop rows + primitive id). The records are padded to
-    # 96 / 64 B for 256-bit loads; the padded figure is reported next to it as `requested_bytes_per_ray`.
-    bytes_per_ray = 48.0 + 80.0 * nodes_per_ray + 52.0 * tris_per_ray
-    requested_per_ray = 48.0 + 96.0 * nodes_per_ray + 64.0 * tris_per_ray
+    # algorithmic bytes: 32 B ray + 16 B hit + one 64 B record per node visited and per triangle tested
+    # (the triangle record's second half is only read when the ray reaches the triangle's plane; counted in full)
+    bytes_per_ray = 48.0 + 64.0 * nodes_per_ray + 64.0 * tris_per_ray
+    requested_per_ray = bytes_per_ray
     launches = max(st.trace_launches, 1)
     avg_launch_ms = st.trace_kernel_ms / launches
     achieved = bytes_per_ray * st.rays_traced / max(st.trace_kernel_ms * 1e-3, 1e-12) / 1e9

@@ -108,15 +108,15 @@ typedef struct bpt_stats {
 typedef struct bpt_accel_info {
     uint32_t num_tris;        /* triangles in the bottom-level structure                    */
     uint32_t num_instances;
-    uint32_t num_nodes8;      /* BVH8 nodes (96 B each)                                     */
+    uint32_t num_nodes8;      /* BVH8 nodes (64 B each)                                     */
     uint32_t num_binary_nodes;/* LBVH internal nodes (N-1)                                  */
-    uint32_t top_nodes_smem;  /* nodes staged into shared memory by TMA: all of them for a
-                                 scene small enough (with its triangles), else 0            */
+    uint32_t top_nodes_smem;  /* records (nodes + triangles) staged into shared memory by TMA:
+                                 all of them for a scene small enough, else the BFS prefix  */
     uint32_t max_depth8;      /* depth of the BVH8                                          */
-    uint64_t bytes_nodes;     /* num_nodes8 * 96                                            */
+    uint64_t bytes_nodes;     /* num_nodes8 * 64                                            */
     uint64_t bytes_tris;      /* num_tris * 64 (Woop rows + primitive id)                   */
     uint32_t num_tlas_nodes8; /* two-level builds: nodes in the instance BVH8               */
-    uint32_t reserved;
+    uint32_t num_records;     /* nodes + triangle records of the (mesh-level) record array  */
 } bpt_accel_info;
 
 /* options for bpt_set_option */
@@ -129,7 +129,7 @@ typedef struct bpt_accel_info {
 #define BPT_OPT_USE_GRAPH        6 /* 1: replay a captured CUDA graph per sample pass        */
 #define BPT_OPT_PASS_PATHS       10 /* target paths per sample pass: a pass carries min(spp, this / tile pixels)
                                       samples of every tile pixel (default 2^27); results do not depend on it */
-#define BPT_OPT_TOP_NODES        11 /* big scenes: BVH8 nodes of the BFS prefix (top of the tree) staged in shared memory */
+#define BPT_OPT_TOP_NODES        11 /* big scenes: records of the BFS prefix (top of the tree) staged in shared memory */
 #define BPT_OPT_TRACE_REFILL_BELOW 8     /* traversal: refill a warp when fewer lanes than this are live */
 #define BPT_OPT_TRACE_STEPS_PER_REFILL 9 /* traversal: loop iterations between two refill votes           */
 
@@ -210,9 +210,12 @@ int bpt_generate_rays(bpt_context* ctx, const bpt_params* p, uint32_t sample_in_
                       float* rays, uint32_t* seeds);
 
 /* ---- BVH introspection for the build-invariant tests (copies device -> host) --------- */
-/* nodes8: num_nodes8 * 96 bytes; tri_index: num_tris uint32 (leaf order -> primitive);
- * woop: num_tris * 64 bytes (12 floats of Woop rows, the primitive id, 3 pad words). Any pointer may be NULL. */
-int bpt_download_accel(bpt_context* ctx, void* nodes8, uint32_t* tri_index, float* woop);
+/* The mesh-level record array: records = num_records * 64 bytes (BVH8 nodes and triangle records interleaved, record
+ * 0 = root; layouts in csrc/common.cuh), rec_prim = num_records uint32 (primitive id of a triangle record, 0xffffffff
+ * for a node record), grid = 6 floats (bias xyz and step xyz of the grid the node origins are quantised on:
+ * origin = fmaf(float(2^23 + c), step, bias)).
+ * Any pointer may be NULL. */
+int bpt_download_accel(bpt_context* ctx, void* records, uint32_t* rec_prim, float* grid);
 /* the uploaded (or device-generated) mesh, as bpt_upload_mesh would have received it. */
 int bpt_download_mesh(bpt_context* ctx, float* verts, uint32_t* indices, float* faces);
 /* sorted 64-bit (morton<<32 | prim) keys of the last build. */

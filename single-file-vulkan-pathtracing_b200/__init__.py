@@ -60,17 +60,17 @@ class AccelInfo(C.Structure):
         ("num_tris", C.c_uint32), ("num_instances", C.c_uint32), ("num_nodes8", C.c_uint32),
         ("num_binary_nodes", C.c_uint32), ("top_nodes_smem", C.c_uint32), ("max_depth8", C.c_uint32),
         ("bytes_nodes", C.c_uint64), ("bytes_tris", C.c_uint64), ("num_tlas_nodes8", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("num_records", C.c_uint32),
     ]
 
 
 HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4")])
+# the two faces of a 64-byte record (csrc/common.cuh)
 NODE8_DTYPE = np.dtype([
-    ("p", "<f4", 3), ("s", "<f4", 3), ("child_base", "<u4"), ("tri_base", "<u4"), ("valid", "<u4"), ("pad0", "<u4"),
-    ("qlox", "u1", 8), ("qloy", "u1", 8), ("qloz", "u1", 8), ("qhix", "u1", 8), ("qhiy", "u1", 8), ("qhiz", "u1", 8),
-    ("pad1", "<u4", 2)])
+    ("org", "<u8"), ("e_valid", "<u4"), ("child_base", "<u4"),
+    ("qlox", "u1", 8), ("qloy", "u1", 8), ("qloz", "u1", 8), ("qhix", "u1", 8), ("qhiy", "u1", 8), ("qhiz", "u1", 8)])
 WOOP_DTYPE = np.dtype([("rows", "<f4", (3, 4)), ("prim", "<u4"), ("pad", "<u4", 3)])
-assert NODE8_DTYPE.itemsize == 96 and WOOP_DTYPE.itemsize == 64
+assert NODE8_DTYPE.itemsize == 64 and WOOP_DTYPE.itemsize == 64
 
 # every symbol include/bpt.h declares: (restype, argtypes)
 _vp, _u32, _i32, _sz = C.c_void_p, C.c_uint32, C.c_int, C.c_size_t
@@ -264,12 +264,14 @@ class PathTracer:
 
     # -- introspection -----------------------------------------------------------------------
     def download_accel(self):
+        """(records as NODE8_DTYPE, the same bytes as WOOP_DTYPE, rec_prim, grid_bias, grid_step) of the mesh-level BVH;
+        a node origin is fmaf(float(2^23 + c), grid_step, grid_bias) per axis."""
         info = self.accel_info()
-        nodes = np.zeros(info.num_nodes8, NODE8_DTYPE)
-        tri_index = np.zeros(info.num_tris, np.uint32)
-        woop = np.zeros(info.num_tris, WOOP_DTYPE)
-        self._check(self._L.bpt_download_accel(self._h, _ptr(nodes), _ptr(tri_index), _ptr(woop)))
-        return nodes, tri_index, woop
+        recs = np.zeros(info.num_records, NODE8_DTYPE)
+        rec_prim = np.zeros(info.num_records, np.uint32)
+        grid = np.zeros(6, np.float32)
+        self._check(self._L.bpt_download_accel(self._h, _ptr(recs), _ptr(rec_prim), _ptr(grid)))
+        return recs, recs.view(WOOP_DTYPE), rec_prim, grid[:3].copy(), grid[3:].copy()
 
     def download_mesh(self, ntris, nverts=None):
         nverts = 3 * ntris if nverts is None else nverts

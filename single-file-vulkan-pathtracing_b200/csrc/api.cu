@@ -40,14 +40,13 @@ struct bpt_context {
     // acceleration structure
     Bvh8 blas;                      // over the mesh triangles
     Bvh8 tlas;                      // over the instances (two-level scenes only)
-    WoopTri* d_woop = nullptr;      // [triangle records | instance records]
-    Node8* d_nodes_all = nullptr;   // two-level scenes: [mesh nodes | instance nodes]
+    Node8* d_recs_all = nullptr;    // two-level scenes: [mesh records | instance-level records]
     float4* d_srec = nullptr;       // shading records, 64 B per primitive (shade.cuh)
     bool two_level = false;
     bool built = false, built_nodes_ok = false;
     bool staged = false;  // the traversal kernel instance that holds the whole BVH in shared memory is in use
-    uint32_t top_nodes = 0;  // else: BFS prefix staged in shared memory
-    int64_t opt_top_nodes = 600;  // BPT_OPT_TOP_NODES
+    uint32_t top_recs = 0;  // else: BFS prefix of the record array staged in shared memory
+    int64_t opt_top_recs = 900;  // BPT_OPT_TOP_NODES
 
     // wavefront buffers
     size_t cap_paths = 0;
@@ -200,13 +199,14 @@ int row_major_image(bpt_context* c, const float4** out) {
 TraceArgs make_trace_args(bpt_context* c, const float4* rays, uint4* hits, const uint32_t* count, uint32_t* fetch) {
     TraceArgs a;
     a.rays = rays; a.hits = hits; a.count_ptr = count; a.fetch_ctr = fetch;
-    a.nodes = c->two_level ? c->d_nodes_all : c->blas.nodes;
-    a.tris = c->d_woop;
-    a.num_nodes = c->blas.num_nodes + (c->two_level ? c->tlas.num_nodes : 0u);
-    a.num_tris = c->ntris + (c->two_level ? c->ninst : 0u);
-    a.root = c->two_level ? c->blas.num_nodes : 0u;
-    a.top_nodes = c->staged ? 0u : c->top_nodes;
+    a.recs = c->two_level ? c->d_recs_all : c->blas.recs;
+    a.staged_recs = c->staged ? c->blas.num_recs + (c->two_level ? c->tlas.num_recs : 0u) : c->top_recs;
+    a.root = c->two_level ? c->blas.num_recs : 0u;
     a.num_mesh_tris = c->ntris;
+    for (int k = 0; k < 3; ++k) {
+        a.gbias[0][k] = c->blas.grid_bias[k]; a.gstep[0][k] = c->blas.grid_step[k];
+        a.gbias[1][k] = c->two_level ? c->tlas.grid_bias[k] : 0.f; a.gstep[1][k] = c->two_level ? c->tlas.grid_step[k] : 0.f;
+    }
     a.refill_below = c->refill_below; a.steps_per_refill = c->steps_per_refill;
     a.magic = 0x47000000u;
     a.stat = c->d_stats;
@@ -231,13 +231,13 @@ void launch_trace(bpt_context* c, const TraceArgs& a) {
 // Small scenes run the traversal instance that keeps the whole BVH in shared memory (TMA-staged once per CTA).
 void plan_staging(bpt_context* c) {
     const uint64_t nodes = (uint64_t)c->blas.num_nodes + (c->two_level ? c->tlas.num_nodes : 0u);
-    const uint64_t recs = (uint64_t)c->ntris + (c->two_level ? c->ninst : 0u);
+    const uint64_t recs = (uint64_t)c->blas.num_recs + (c->two_level ? c->tlas.num_recs : 0u);
     c->staged = c->built_nodes_ok && nodes <= (uint64_t)c->opt_stage_max_nodes &&
-                trace_smem_bytes((uint32_t)nodes, (uint32_t)recs) <= (size_t)kTraceMaxSmem;
-    // the BFS prefix only makes sense for a single-level array (node 0 = root)
-    const uint64_t cap = (kTraceMaxSmem - trace_smem_bytes(0, 0)) / BPT_NODE_BYTES;
-    c->top_nodes = (c->staged || c->two_level || c->opt_stage_max_nodes == 0) ? 0u
-                   : (uint32_t)std::min<uint64_t>(std::min<uint64_t>((uint64_t)c->opt_top_nodes, nodes), cap);
+                trace_smem_bytes((uint32_t)recs) <= (size_t)kTraceMaxSmem;
+    // the BFS prefix only makes sense for a single-level array (record 0 = root)
+    const uint64_t cap = (kTraceMaxSmem - trace_smem_bytes(0)) / BPT_REC_BYTES;
+    c->top_recs = (c->staged || c->two_level || c->opt_stage_max_nodes == 0) ? 0u
+                  : (uint32_t)std::min<uint64_t>(std::min<uint64_t>((uint64_t)c->opt_top_recs, recs), cap);
 }
 
 // inverse of a row-major 3x4 affine transform, in double; false if singular
@@ -325,8 +325,8 @@ void bpt_destroy(bpt_context* c) {
     free_scene(c);
     free_paths(c);
     bvh8_free(c->blas); bvh8_free(c->tlas);
-    cudaFree(c->d_nodes_all); cudaFree(c->d_srec); cudaFree(c->frame_sum);
-    cudaFree(c->d_woop); cudaFree(c->image); cudaFree(c->image_linear); cudaFree(c->counters); cudaFree(c->d_stats);
+    cudaFree(c->d_recs_all); cudaFree(c->d_srec); cudaFree(c->frame_sum);
+    cudaFree(c->image); cudaFree(c->image_linear); cudaFree(c->counters); cudaFree(c->d_stats);
     for (auto& p : c->frame_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto& p : c->trace_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
@@ -348,7 +348,7 @@ int bpt_set_option(bpt_context* c, int option, int64_t value) {
             return BPT_OK;
         case BPT_OPT_TOP_NODES:
             if (value < 0) return bpt_fail(c, BPT_E_INVALID, "node count must be >= 0");
-            c->opt_top_nodes = value;
+            c->opt_top_recs = value;
             if (c->built) plan_staging(c);
             return BPT_OK;
         case BPT_OPT_TRACE_REFILL_BELOW:
@@ -462,11 +462,9 @@ int bpt_build_accel(bpt_context* c) {
     if (c->blas.num_leaf_slots != c->ntris)
         return bpt_fail(c, BPT_E_STATE, "BVH8 collapse placed %u of %u triangles", c->blas.num_leaf_slots, c->ntris);
     c->two_level = c->d_xforms != nullptr;
-    const uint32_t nrec = c->ntris + (c->two_level ? c->ninst : 0u);
-    cudaFree(c->d_woop); cudaFree(c->d_nodes_all);
-    c->d_woop = nullptr; c->d_nodes_all = nullptr;
-    BPT_CUDA_TRY(c, cudaMalloc(&c->d_woop, (size_t)nrec * sizeof(WoopTri) + 32));
-    bvh8_launch_woop(c->blas, c->d_verts, c->d_idx, c->d_woop, c->stream);
+    cudaFree(c->d_recs_all);
+    c->d_recs_all = nullptr;
+    bvh8_launch_woop(c->blas, c->d_verts, c->d_idx, c->stream);
     cudaFree(c->d_srec);
     c->d_srec = nullptr;
     BPT_CUDA_TRY(c, cudaMalloc(&c->d_srec, (size_t)c->ntris * 64));
@@ -479,11 +477,11 @@ int bpt_build_accel(bpt_context* c) {
         BPT_CUDA_TRY(c, bvh8_build(c->tlas, c->stream));
         if (c->tlas.num_leaf_slots != c->ninst)
             return bpt_fail(c, BPT_E_STATE, "instance BVH8 collapse placed %u of %u instances", c->tlas.num_leaf_slots, c->ninst);
-        bvh8_launch_instance_records(c->tlas, c->d_xforms_inv, c->d_woop + c->ntris, c->stream);
-        const uint32_t nb = c->blas.num_nodes, nt = c->tlas.num_nodes;
-        BPT_CUDA_TRY(c, cudaMalloc(&c->d_nodes_all, (size_t)(nb + nt) * sizeof(Node8)));
-        BPT_CUDA_TRY(c, cudaMemcpyAsync(c->d_nodes_all, c->blas.nodes, (size_t)nb * sizeof(Node8), cudaMemcpyDeviceToDevice, c->stream));
-        bvh8_launch_append_nodes(c->tlas.nodes, nt, nb, c->ntris, c->d_nodes_all + nb, c->stream);
+        bvh8_launch_instance_records(c->tlas, c->d_xforms_inv, c->stream);
+        const uint32_t rb = c->blas.num_recs, rt = c->tlas.num_recs;
+        BPT_CUDA_TRY(c, cudaMalloc(&c->d_recs_all, (size_t)(rb + rt) * sizeof(Node8)));
+        BPT_CUDA_TRY(c, cudaMemcpyAsync(c->d_recs_all, c->blas.recs, (size_t)rb * sizeof(Node8), cudaMemcpyDeviceToDevice, c->stream));
+        bvh8_launch_append_recs(c->tlas, rb, c->d_recs_all + rb, c->stream);
         depth += c->tlas.depth + 1;  // + the sentinel
     } else {
         bvh8_free(c->tlas);
@@ -511,11 +509,12 @@ int bpt_accel_info_get(bpt_context* c, bpt_accel_info* out) {
     out->num_instances = c->ninst;
     out->num_nodes8 = c->blas.num_nodes;
     out->num_binary_nodes = c->ntris - 1;
-    out->top_nodes_smem = c->staged ? c->blas.num_nodes + (c->two_level ? c->tlas.num_nodes : 0u) : c->top_nodes;
+    out->top_nodes_smem = c->staged ? c->blas.num_recs + (c->two_level ? c->tlas.num_recs : 0u) : c->top_recs;
+    out->num_records = c->blas.num_recs;
     out->max_depth8 = c->blas.depth;
     out->num_tlas_nodes8 = c->two_level ? c->tlas.num_nodes : 0;
-    out->bytes_nodes = (uint64_t)c->blas.num_nodes * BPT_NODE_BYTES;
-    out->bytes_tris = (uint64_t)c->ntris * BPT_TRI_BYTES;
+    out->bytes_nodes = (uint64_t)c->blas.num_nodes * BPT_REC_BYTES;
+    out->bytes_tris = (uint64_t)c->ntris * BPT_REC_BYTES;
     return BPT_OK;
 }
 
@@ -714,14 +713,15 @@ int bpt_generate_rays(bpt_context* c, const bpt_params* p, uint32_t sample_in_fr
     return BPT_OK;
 }
 
-int bpt_download_accel(bpt_context* c, void* nodes8, uint32_t* tri_index, float* woop) {
+int bpt_download_accel(bpt_context* c, void* records, uint32_t* rec_prim, float* grid) {
     if (!c) return BPT_E_INVALID;
     if (!c->built) return bpt_fail(c, BPT_E_STATE, "no acceleration structure built");
     cudaSetDevice(c->device);
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    if (nodes8) BPT_CUDA_TRY(c, cudaMemcpy(nodes8, c->blas.nodes, (size_t)c->blas.num_nodes * BPT_NODE_BYTES, cudaMemcpyDeviceToHost));
-    if (tri_index) BPT_CUDA_TRY(c, cudaMemcpy(tri_index, c->blas.prim_index, (size_t)c->ntris * 4, cudaMemcpyDeviceToHost));
-    if (woop) BPT_CUDA_TRY(c, cudaMemcpy(woop, c->d_woop, (size_t)c->ntris * BPT_TRI_BYTES, cudaMemcpyDeviceToHost));
+    if (records) BPT_CUDA_TRY(c, cudaMemcpy(records, c->blas.recs, (size_t)c->blas.num_recs * BPT_REC_BYTES, cudaMemcpyDeviceToHost));
+    if (rec_prim) BPT_CUDA_TRY(c, cudaMemcpy(rec_prim, c->blas.rec_prim, (size_t)c->blas.num_recs * 4, cudaMemcpyDeviceToHost));
+    if (grid)
+        for (int k = 0; k < 3; ++k) { grid[k] = c->blas.grid_bias[k]; grid[3 + k] = c->blas.grid_step[k]; }
     return BPT_OK;
 }
 

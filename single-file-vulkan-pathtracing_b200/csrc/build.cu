@@ -8,8 +8,10 @@
 //   K4  lbvh_hierarchy   Karras 2012: one thread per internal node, clz on key XOR
 //   K5  lbvh_refit       bottom-up AABBs with per-node arrival counters
 //   K6  bvh8_collapse    binary -> 8-wide, greedy largest-area opening, octant slot assignment,
-//                        quantisation to the 96-byte Node8 (level-synchronous, BFS node order)
-//   K7  woop_transform   64-byte records (unit-triangle transform + primitive id) in leaf order
+//                        quantisation to the 64-byte Node8 (level-synchronous; nodes and triangle
+//                        records share one array, a node's children records are contiguous)
+//   K7  woop_transform   64-byte records (unit-triangle transform + primitive id) at the record
+//                        positions the collapse reserved
 // Everything is generic over "primitives with an AABB" so the same code builds the instance-level
 // BVH8 of two-level scenes.
 #include <cfloat>
@@ -208,12 +210,15 @@ struct CollapseArgs {
     const uint64_t* keys;
     const uint32_t *left, *right, *first, *last;
     const float4 *nlo, *nhi;
-    Node8* nodes;
-    uint32_t* wide_src;    // node8 index -> binary node id it expands
-    uint32_t* prim_index;  // leaf slot -> primitive id
-    uint32_t* counters;    // [0] node count, [1] leaf-slot count
-    uint32_t level_begin, level_end;
-    float pad;             // conservative widening of every quantised box (world units)
+    Node8* recs;              // the record array; this kernel writes the node records
+    uint32_t* wide_src;       // record index of a node -> binary node id it expands
+    uint32_t* rec_prim;       // record index -> primitive id (triangle records; BPT_MISS for nodes)
+    uint32_t* counters;       // [0] records allocated, [1] nodes queued for the next level, [2] triangle records
+    const uint32_t* list_cur; // records of this level's nodes
+    uint32_t* list_next;      // records of the next level's nodes
+    uint32_t level_count;
+    float pad;                // conservative widening of every quantised box (world units)
+    float gbias[3], gstep[3]; // scene grid the node origins are quantised on (BPT_GRID_BITS per axis), build.cuh
 };
 
 __device__ __forceinline__ uint32_t node_count(const CollapseArgs& a, uint32_t node) {
@@ -238,8 +243,9 @@ __device__ __forceinline__ int quant_exponent(float ext) {
 }
 
 __global__ void k_bvh8_collapse(CollapseArgs a) {
-    uint32_t w = a.level_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= a.level_end) return;
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= a.level_count) return;
+    const uint32_t w = a.list_cur[li];
     const uint32_t src = a.wide_src[w];
 
     uint32_t cand[8];
@@ -269,12 +275,29 @@ __global__ void k_bvh8_collapse(CollapseArgs a) {
 
     const float4 blo = a.nlo[src], bhi = a.nhi[src];
     const float pad = a.pad;
-    // grid: exponent from the padded extent (with ~5 steps of slack), origin one margin below the padded box
-    const int ex = quant_exponent((bhi.x - blo.x) + 2.f * pad), ey = quant_exponent((bhi.y - blo.y) + 2.f * pad),
-              ez = quant_exponent((bhi.z - blo.z) + 2.f * pad);
-    const float sx = exp2f((float)ex), sy = exp2f((float)ey), sz = exp2f((float)ez);
-    const float isx = exp2f((float)-ex), isy = exp2f((float)-ey), isz = exp2f((float)-ez);
-    const float px = blo.x - pad - kQuantMargin * sx, py = blo.y - pad - kQuantMargin * sy, pz = blo.z - pad - kQuantMargin * sz;
+    // Child-box grid: ONE exponent for the three axes, from the largest padded extent plus the resolution of the
+    // origin grid (the origin is rounded down onto it) with ~5 steps of slack; the origin sits one margin below the
+    // padded box, on the scene grid.
+    const float ext = fmaxf(fmaxf((bhi.x - blo.x) + a.gstep[0], (bhi.y - blo.y) + a.gstep[1]), (bhi.z - blo.z) + a.gstep[2]);
+    const int ex = quant_exponent(ext + 2.f * pad);
+    const float sx = exp2f((float)ex), isx = exp2f((float)-ex);
+    const float sy = sx, sz = sx, isy = isx, isz = isx;
+    uint32_t org[3];
+    float porg[3];
+    {
+        const float target[3] = {blo.x - pad - kQuantMargin * sx, blo.y - pad - kQuantMargin * sy, blo.z - pad - kQuantMargin * sz};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            // decode(c) is what the traversal kernel evaluates: fmaf(float(2^23 + c), gstep, gbias)
+            auto decode = [&](int c) { return fmaf(8388608.0f + (float)c, a.gstep[k], a.gbias[k]); };
+            int c = (int)floorf((target[k] - decode(0)) / a.gstep[k]);
+            c = max(0, min(c, (1 << BPT_GRID_BITS) - 1));
+            while (c > 0 && decode(c) > target[k]) --c;
+            org[k] = (uint32_t)c;
+            porg[k] = decode(c);
+        }
+    }
+    const float px = porg[0], py = porg[1], pz = porg[2];
     const float cx = 0.5f * (blo.x + bhi.x), cy = 0.5f * (blo.y + bhi.y), cz = 0.5f * (blo.z + bhi.z);
 
     // slot assignment: slot bit 2/1/0 set = child lies on the +x/+y/+z side of the node centre.
@@ -307,19 +330,20 @@ __global__ void k_bvh8_collapse(CollapseArgs a) {
         child_in[bsl] = bc;
     }
 
-    // allocate internal children (contiguous, in slot order) and leaf slots
+    // allocate the children records: internal children first (slot order), then the leaf triangles
     uint32_t n_int = 0, n_leaf = 0;
     for (int c = 0; c < nc; ++c) {
         if (cnt[c] > 3u) ++n_int; else n_leaf += cnt[c];
     }
-    uint32_t child_base = n_int ? atomicAdd(&a.counters[0], n_int) : 0u;
-    uint32_t tri_base = n_leaf ? atomicAdd(&a.counters[1], n_leaf) : 0u;
+    const uint32_t child_base = atomicAdd(&a.counters[0], n_int + n_leaf);
+    const uint32_t qbase = n_int ? atomicAdd(&a.counters[1], n_int) : 0u;
+    if (n_leaf) atomicAdd(&a.counters[2], n_leaf);
+    const uint32_t tri_base = child_base + n_int;
 
     Node8 nd;
-    nd.px = px; nd.py = py; nd.pz = pz;
-    nd.sx = sx; nd.sy = sy; nd.sz = sz;
+    nd.org_lo = org[0] | (org[1] << 21);
+    nd.org_hi = (org[1] >> 11) | (org[2] << 10);
     nd.child_base = child_base;
-    nd.tri_base = tri_base;
     uint32_t valid = 0, int_rank = 0, leaf_off = 0;
     for (int s = 0; s < 8; ++s) {
         int c = child_in[s];
@@ -349,32 +373,34 @@ __global__ void k_bvh8_collapse(CollapseArgs a) {
         nd.qloy[s] = qlo(clo[c].y, py, sy, isy); nd.qhiy[s] = qhi(chi[c].y, py, sy, isy);
         nd.qloz[s] = qlo(clo[c].z, pz, sz, isz); nd.qhiz[s] = qhi(chi[c].z, pz, sz, isz);
         if (cnt[c] > 3u) {
-            valid |= 1u << (24 + s);
+            valid |= 1u << (16 + s);
             a.wide_src[child_base + int_rank] = cand[c];
+            a.list_next[qbase + int_rank] = child_base + int_rank;
             ++int_rank;
         } else {
             uint32_t k = cnt[c];
-            valid |= ((1u << k) - 1u) << (3 * s);
+            valid |= k << (2 * s);
             uint32_t f = node_first(a, cand[c]);
             for (uint32_t j = 0; j < k; ++j)
-                a.prim_index[tri_base + leaf_off + j] = (uint32_t)(a.keys[f + j] & 0xffffffffu);
+                a.rec_prim[tri_base + leaf_off + j] = (uint32_t)(a.keys[f + j] & 0xffffffffu);
             leaf_off += k;
         }
     }
-    nd.valid = valid;
-    nd.pad0 = nd.pad1 = nd.pad2 = 0;
-    uint4* dst = reinterpret_cast<uint4*>(a.nodes + w);
+    nd.e_valid = valid | ((uint32_t)(ex + 127) << 24);
+    uint4* dst = reinterpret_cast<uint4*>(a.recs + w);
     const uint4* srcw = reinterpret_cast<const uint4*>(&nd);
 #pragma unroll
-    for (int q = 0; q < 6; ++q) dst[q] = srcw[q];
+    for (int q = 0; q < 4; ++q) dst[q] = srcw[q];
 }
 
-// K7: Woop transform of the triangle in leaf slot s. Rows are computed in double and rounded once.
+// K7: Woop transform of the triangle a record holds. Rows are computed in double and rounded once.
 __global__ void k_woop(const float* __restrict__ verts, const uint32_t* __restrict__ idx,
-                       const uint32_t* __restrict__ prim_index, uint32_t n, WoopTri* __restrict__ out) {
+                       const uint32_t* __restrict__ rec_prim, uint32_t nrecs, Node8* __restrict__ recs) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    uint32_t prim = prim_index[s];
+    if (s >= nrecs) return;
+    uint32_t prim = rec_prim[s];
+    if (prim == BPT_MISS) return;  // a node record
+    WoopTri* out = reinterpret_cast<WoopTri*>(recs);
     double v[3][3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -405,29 +431,29 @@ __global__ void k_woop(const float* __restrict__ verts, const uint32_t* __restri
     out[s] = w;
 }
 
-// K8: record of the instance in leaf slot s of the instance-level BVH8: rows of the inverse 3x4 transform + instance id
-__global__ void k_instance_records(const float* __restrict__ inv, const uint32_t* __restrict__ prim_index, uint32_t n,
-                                   WoopTri* __restrict__ out) {
+// K8: instance records of the instance-level BVH8: rows of the inverse 3x4 transform + instance id
+__global__ void k_instance_records(const float* __restrict__ inv, const uint32_t* __restrict__ rec_prim, uint32_t nrecs,
+                                   Node8* __restrict__ recs) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const uint32_t inst = prim_index[s];
+    if (s >= nrecs) return;
+    const uint32_t inst = rec_prim[s];
+    if (inst == BPT_MISS) return;
     const float* m = inv + 12 * (size_t)inst;
     WoopTri w;
     w.ru = make_float4(m[0], m[1], m[2], m[3]);
     w.rv = make_float4(m[4], m[5], m[6], m[7]);
     w.rw = make_float4(m[8], m[9], m[10], m[11]);
     w.prim = inst; w.pad0 = w.pad1 = w.pad2 = 0;
-    out[s] = w;
+    reinterpret_cast<WoopTri*>(recs)[s] = w;
 }
 
-// K8: copies the instance-level nodes behind the mesh nodes, rebasing their child and record indices
-__global__ void k_append_nodes(const Node8* __restrict__ src, uint32_t n, uint32_t node_off, uint32_t rec_off,
-                               Node8* __restrict__ dst) {
+// K8: copies the instance-level records behind the mesh records, rebasing the child pointers of its nodes
+__global__ void k_append_recs(const Node8* __restrict__ src, const uint32_t* __restrict__ rec_prim, uint32_t n,
+                              uint32_t rec_off, Node8* __restrict__ dst) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Node8 nd = src[i];
-    nd.child_base += node_off;
-    nd.tri_base += rec_off;
+    if (rec_prim[i] == BPT_MISS) nd.child_base += rec_off;
     dst[i] = nd;
 }
 
@@ -441,8 +467,8 @@ cudaError_t dalloc(T** p, size_t count) {
 void bvh8_free(Bvh8& b) {
     cudaFree(b.plo); cudaFree(b.phi); cudaFree(b.keys); cudaFree(b.keys_tmp); cudaFree(b.left); cudaFree(b.right);
     cudaFree(b.parent); cudaFree(b.first); cudaFree(b.last); cudaFree(b.arrive); cudaFree(b.nlo); cudaFree(b.nhi);
-    cudaFree(b.nodes); cudaFree(b.wide_src); cudaFree(b.prim_index); cudaFree(b.counters); cudaFree(b.bounds);
-    cudaFree(b.sort_tmp);
+    cudaFree(b.recs); cudaFree(b.wide_src); cudaFree(b.rec_prim); cudaFree(b.list[0]); cudaFree(b.list[1]);
+    cudaFree(b.counters); cudaFree(b.bounds); cudaFree(b.sort_tmp);
     b = Bvh8{};
 }
 
@@ -456,10 +482,11 @@ cudaError_t bvh8_alloc(Bvh8& b, uint32_t n) {
     A(dalloc(&b.left, n)); A(dalloc(&b.right, n)); A(dalloc(&b.first, n)); A(dalloc(&b.last, n));
     A(dalloc(&b.parent, 2 * (size_t)n)); A(dalloc(&b.arrive, n));
     A(dalloc(&b.nlo, 2 * (size_t)n)); A(dalloc(&b.nhi, 2 * (size_t)n));
-    // every wide node expands at least one binary internal node, so n nodes always suffice
+    // every wide node expands at least one binary internal node, so n nodes always suffice; + n triangle records
     b.nodes_cap = n < 8 ? 8 : n;
-    A(dalloc(&b.nodes, b.nodes_cap)); A(dalloc(&b.wide_src, b.nodes_cap));
-    A(dalloc(&b.prim_index, n));
+    b.recs_cap = b.nodes_cap + n;
+    A(dalloc(&b.recs, b.recs_cap)); A(dalloc(&b.wide_src, b.recs_cap)); A(dalloc(&b.rec_prim, b.recs_cap));
+    A(dalloc(&b.list[0], b.nodes_cap)); A(dalloc(&b.list[1], b.nodes_cap));
     A(dalloc(&b.counters, 8)); A(dalloc(&b.bounds, 8));
     b.sort_tmp_bytes = radix_sort_u64_temp_bytes(n);
     A(cudaMalloc(&b.sort_tmp, b.sort_tmp_bytes));
@@ -505,42 +532,59 @@ cudaError_t bvh8_build(Bvh8& b, cudaStream_t st) {
     }
     diag = sqrtf(diag);
 
+    // scene grid of the node origins: BPT_GRID_BITS per axis over the padded scene box
+    const float pad = 9.5367431640625e-07f * fmaxf(diag, mag);  // 2^-20 of the scene scale
+    for (int a = 0; a < 3; ++a) {
+        const float ext = (b.scene_hi[a] - b.scene_lo[a]) + 4.f * pad + 1e-30f;
+        b.grid_lo[a] = b.scene_lo[a] - 2.f * pad - ext * 0.001f;
+        b.grid_step[a] = ext * 1.002f / (float)(1 << BPT_GRID_BITS);
+        b.grid_bias[a] = b.grid_lo[a] - 8388608.0f * b.grid_step[a];
+    }
+
     CollapseArgs a;
     a.n = n; a.keys = b.keys; a.left = b.left; a.right = b.right; a.first = b.first; a.last = b.last;
-    a.nlo = b.nlo; a.nhi = b.nhi; a.nodes = b.nodes; a.wide_src = b.wide_src; a.prim_index = b.prim_index;
+    a.nlo = b.nlo; a.nhi = b.nhi; a.recs = b.recs; a.wide_src = b.wide_src; a.rec_prim = b.rec_prim;
     a.counters = b.counters;
-    a.pad = 9.5367431640625e-07f * fmaxf(diag, mag);  // 2^-20 of the scene scale
-    uint32_t init[2] = {1u, 0u};                       // node 0 = root, expands binary root
-    uint32_t root_src = (n == 1) ? 0u : 0u;            // internal 0, or leaf 0 when n == 1 (same id)
+    a.pad = pad;
+    for (int k = 0; k < 3; ++k) { a.gbias[k] = b.grid_bias[k]; a.gstep[k] = b.grid_step[k]; }
+    const uint32_t init[3] = {1u, 0u, 0u};  // record 0 = root node, expands the binary root (internal 0, or leaf 0 when n == 1)
+    const uint32_t zero = 0u;
+    if ((e = cudaMemsetAsync(b.rec_prim, 0xff, sizeof(uint32_t) * b.recs_cap, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(b.counters, init, sizeof(init), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyAsync(b.wide_src, &root_src, sizeof(uint32_t), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
-    uint32_t begin = 0, end = 1, depth = 0;
-    while (begin < end) {
-        a.level_begin = begin;
-        a.level_end = end;
-        k_bvh8_collapse<<<grid_for(end - begin, 64), 64, 0, st>>>(a);
-        uint32_t hc[2];
+    if ((e = cudaMemcpyAsync(b.wide_src, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(b.list[0], &zero, sizeof(uint32_t), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    uint32_t count = 1, depth = 0, nodes = 0;
+    int cur = 0;
+    while (count) {
+        a.list_cur = b.list[cur];
+        a.list_next = b.list[cur ^ 1];
+        a.level_count = count;
+        k_bvh8_collapse<<<grid_for(count, 64), 64, 0, st>>>(a);
+        uint32_t hc[3];
         if ((e = cudaMemcpyAsync(hc, b.counters, sizeof(hc), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(b.counters + 1, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         ++depth;
-        begin = end;
-        end = hc[0];
-        b.num_leaf_slots = hc[1];
-        if (end > b.nodes_cap) return cudaErrorMemoryAllocation;
+        nodes += count;
+        count = hc[1];
+        b.num_recs = hc[0];
+        b.num_leaf_slots = hc[2];
+        if (b.num_recs > b.recs_cap || nodes + count > b.nodes_cap) return cudaErrorMemoryAllocation;
+        cur ^= 1;
     }
-    b.num_nodes = end;
+    b.num_nodes = nodes;
     b.depth = depth;
     return cudaSuccess;
 }
 
-void bvh8_launch_woop(const Bvh8& b, const float* verts, const uint32_t* idx, WoopTri* out, cudaStream_t st) {
-    k_woop<<<grid_for(b.n), kBlock, 0, st>>>(verts, idx, b.prim_index, b.n, out);
+void bvh8_launch_woop(const Bvh8& b, const float* verts, const uint32_t* idx, cudaStream_t st) {
+    k_woop<<<grid_for(b.num_recs), kBlock, 0, st>>>(verts, idx, b.rec_prim, b.num_recs, b.recs);
 }
 
-void bvh8_launch_instance_records(const Bvh8& tlas, const float* inv_xforms, WoopTri* out, cudaStream_t st) {
-    k_instance_records<<<grid_for(tlas.n), kBlock, 0, st>>>(inv_xforms, tlas.prim_index, tlas.n, out);
+void bvh8_launch_instance_records(const Bvh8& tlas, const float* inv_xforms, cudaStream_t st) {
+    k_instance_records<<<grid_for(tlas.num_recs), kBlock, 0, st>>>(inv_xforms, tlas.rec_prim, tlas.num_recs, tlas.recs);
 }
-void bvh8_launch_append_nodes(const Node8* src, uint32_t n, uint32_t node_off, uint32_t rec_off, Node8* dst, cudaStream_t st) {
-    k_append_nodes<<<grid_for(n), kBlock, 0, st>>>(src, n, node_off, rec_off, dst);
+void bvh8_launch_append_recs(const Bvh8& tlas, uint32_t rec_off, Node8* dst, cudaStream_t st) {
+    k_append_recs<<<grid_for(tlas.num_recs), kBlock, 0, st>>>(tlas.recs, tlas.rec_prim, tlas.num_recs, rec_off, dst);
 }

@@ -12,17 +12,20 @@ struct Bvh8 {
     uint64_t *keys = nullptr, *keys_tmp = nullptr;
     uint32_t *left = nullptr, *right = nullptr, *parent = nullptr, *first = nullptr, *last = nullptr, *arrive = nullptr;
     float4 *nlo = nullptr, *nhi = nullptr;  // 2n-1 boxes: internal nodes, then leaves (sorted order)
-    // BVH8 (K6)
-    Node8* nodes = nullptr;
-    uint32_t nodes_cap = 0;
-    uint32_t* wide_src = nullptr;
-    uint32_t* prim_index = nullptr;  // leaf slot -> primitive id
+    // BVH8 (K6): one array of 64-byte records, nodes and triangle (instance) records interleaved
+    Node8* recs = nullptr;
+    uint32_t nodes_cap = 0, recs_cap = 0;
+    uint32_t* wide_src = nullptr;    // node record -> binary node it expands
+    uint32_t* rec_prim = nullptr;    // record -> primitive id, BPT_MISS for node records
+    uint32_t* list[2] = {nullptr, nullptr};  // node records of the current / next level
     uint32_t* counters = nullptr;
     void* sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
     // host copies, valid after bvh8_build
-    uint32_t num_nodes = 0, num_leaf_slots = 0, depth = 0;
+    uint32_t num_recs = 0, num_nodes = 0, num_leaf_slots = 0, depth = 0;
     float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};
+    // scene grid of the node origins: origin = fmaf(float(2^23 + c), grid_step, grid_bias), c < 2^BPT_GRID_BITS
+    float grid_lo[3] = {0, 0, 0}, grid_step[3] = {1, 1, 1}, grid_bias[3] = {0, 0, 0};
 };
 
 cudaError_t bvh8_alloc(Bvh8& b, uint32_t n);
@@ -31,11 +34,13 @@ void bvh8_launch_tri_bounds(Bvh8& b, const float* verts, const uint32_t* idx, cu
 void bvh8_launch_instance_bounds(Bvh8& b, const float* xforms, const float mesh_lo[3], const float mesh_hi[3],
                                  cudaStream_t st);
 cudaError_t bvh8_build(Bvh8& b, cudaStream_t st);
-void bvh8_launch_woop(const Bvh8& b, const float* verts, const uint32_t* idx, WoopTri* out, cudaStream_t st);
+// writes the triangle records at the positions the collapse reserved for them
+void bvh8_launch_woop(const Bvh8& b, const float* verts, const uint32_t* idx, cudaStream_t st);
 
-// two-level scenes: instance leaf records (inverse transforms) and the merged node array [mesh | instances]
-void bvh8_launch_instance_records(const Bvh8& tlas, const float* inv_xforms, WoopTri* out, cudaStream_t st);
-void bvh8_launch_append_nodes(const Node8* src, uint32_t n, uint32_t node_off, uint32_t rec_off, Node8* dst, cudaStream_t st);
+// two-level scenes: instance records (inverse transforms) at the instance-level leaf positions, and the merged
+// record array [mesh | instances] (child pointers of the instance-level nodes rebased by rec_off)
+void bvh8_launch_instance_records(const Bvh8& tlas, const float* inv_xforms, cudaStream_t st);
+void bvh8_launch_append_recs(const Bvh8& tlas, uint32_t rec_off, Node8* dst, cudaStream_t st);
 
 // radix_sort.cu — stable LSD radix sort of 64-bit keys on bits [begin_bit, end_bit).
 // Returns the buffer (keys or tmp) that holds the sorted result.

@@ -8,44 +8,44 @@
 #define BPT_MISS 0xffffffffu
 #define BPT_NUM_SMS_DEFAULT 148
 
-// ------------------------------------------------------------------ BVH8 node (96 bytes)
-// Compressed 8-wide node after Ylitie, Karras, Laine 2017, re-laid out for sm_100: three 32-byte words, 32-byte
-// aligned, so a lane fetches a node with three 256-bit loads (LDG.E.256). The traversal kernel is bound by L1
-// wavefronts — every lane walks its own node, so each load instruction costs one wavefront per lane whatever its
-// width — and 3 x 32 B costs 40 % fewer wavefronts than the 5 x 16 B of the classic 80-byte node. The per-child
-// meta bytes are replaced by one validity word so that the kernel spends one predicated OR per child (trace.cu).
-//   v0: px, py, pz (grid origin, f32) | sx, sy, sz (grid step per axis, f32, a power of two) | child_base | tri_base
-//   v1: valid | 0 | qlo_x[0..7] | qlo_y[0..7] | qlo_z[0..7]
-//   v2: qhi_x[0..7] | qhi_y[0..7] | qhi_z[0..7] | 0 | 0
-// valid: bit 24+s set   = child slot s is an internal node; the internal children of a node are
-//                         consecutive nodes from child_base, in slot order
-//        bits 3s..3s+2  = unary triangle count (001, 011, 111) of leaf child s, 0 if s is internal
-//                         or empty; the triangles of a node are consecutive leaf slots from tri_base
-//                         in (slot, k) order, so bit b of the low 24 is triangle
-//                         tri_base + popc(valid & ((1 << b) - 1) & 0xffffff)
-// Child boxes are origin + q * step per axis; slot bit 2/1/0 = child on the +x/+y/+z side.
+// ------------------------------------------------------------------ acceleration-structure records (64 bytes)
+// The traversal kernel is bound by the L1 data pipe: every 32-byte sector a lane receives costs one cycle of it
+// (every lane walks its own node, nothing coalesces), so the records are sized in sectors. One array of 64-byte,
+// 64-byte-aligned records holds BVH8 nodes AND triangle (or instance) records: two 256-bit loads (LDG.E.256) each.
+//
+// Node8 — compressed 8-wide node after Ylitie, Karras, Laine 2017, squeezed from their 80 bytes to 64:
+//   w0,w1 : grid origin, 3 x 21-bit unsigned coordinates c on the scene grid: x = bits 0..20, y = 21..41,
+//           z = 42..62; origin = fmaf(float(2^23 + c), grid_step, grid_bias) per axis, grid_step / grid_bias are
+//           per-BVH kernel arguments (grid_bias = grid_lo - 2^23 * grid_step); builder and kernel evaluate the same
+//           float expression, so they agree bit for bit
+//   w2    : bits 0..15 = triangle count (0..3) of leaf child s in bits 2s..2s+1; bits 16..23 = internal-child mask;
+//           bits 24..31 = biased exponent e of the child-box grid step 2^(e-127), shared by the three axes
+//   w3    : child_base = record index of the node's first child record. Children records are contiguous: first the
+//           internal children (nodes) in slot order, then the triangles of the leaf children in (slot, k) order —
+//           one base pointer serves both, which is what frees the bytes for the planes
+//   w4..15: qlo_x[8] qlo_y[8] | qlo_z[8] qhi_x[8] qhi_y[8] qhi_z[8]   (first sector ends after qlo_y)
+// Child boxes are origin + q * 2^(e-127) per axis; slot bit 2/1/0 = child on the +x/+y/+z side.
 struct __align__(32) Node8 {
-    float px, py, pz;
-    float sx, sy, sz;
-    uint32_t child_base, tri_base;
-    uint32_t valid, pad0;
-    uint8_t qlox[8], qloy[8], qloz[8];
-    uint8_t qhix[8], qhiy[8], qhiz[8];
-    uint32_t pad1, pad2;
+    uint32_t org_lo, org_hi;
+    uint32_t e_valid;
+    uint32_t child_base;
+    uint8_t qlox[8], qloy[8];
+    uint8_t qloz[8], qhix[8], qhiy[8], qhiz[8];
 };
-static_assert(sizeof(Node8) == 96, "Node8 must be 96 bytes");
+static_assert(sizeof(Node8) == 64, "Node8 must be 64 bytes");
 
 // Woop-transformed triangle: three rows (r.xyz, r.w) of the affine map that sends
-// v0,v1,v2,v0+n to (0,0,0),(1,0,0),(0,1,0),(0,0,1): row 0 -> u, row 1 -> v, row 2 -> w; plus the primitive id
-// the leaf slot holds. 64 bytes, 32-byte aligned: two 256-bit loads per test, and the hit record / the
-// duplicate-triangle tie-break get the primitive id without a second gather.
+// v0,v1,v2,v0+n to (0,0,0),(1,0,0),(0,1,0),(0,0,1): row 0 -> u, row 1 -> v, row 2 -> w; plus the primitive id.
+// First sector = rows w and u... see the order below: the kernel reads {rw, prim} first (plane distance test) and
+// the second sector {ru, rv} only for triangles whose plane the ray segment reaches.
+// Instance records of two-level scenes reuse the struct: rows of the inverse 3x4 transform + instance id.
 struct __align__(32) WoopTri {
     float4 ru, rv, rw;
     uint32_t prim, pad0, pad1, pad2;
 };
 static_assert(sizeof(WoopTri) == 64, "WoopTri must be 64 bytes");
-#define BPT_NODE_BYTES 96u
-#define BPT_TRI_BYTES 64u
+#define BPT_REC_BYTES 64u
+#define BPT_GRID_BITS 21
 
 // ------------------------------------------------------------------ wavefront records (SoA)
 // ray   : 2 x float4  {ox,oy,oz,tmin} {dx,dy,dz,tmax}

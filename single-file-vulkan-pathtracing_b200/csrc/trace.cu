@@ -19,8 +19,11 @@
 // What bounds it. The kernel moves almost no DRAM bytes (L2 hit rate 76-85 %); it is bound by instruction issue and
 // by L1 wavefronts (profiles/: l1tex throughput 77 %, issue 68 %, ALU pipe 56 %), and on sm_100 the ALU pipe
 // (PRMT/LOP3/FMNMX/SEL) runs at half the rate of the FMA pipe. Hence:
-//   * nodes are 96 bytes = three 256-bit loads, triangles 64 bytes = two (LDG.E.256): every lane walks its own
-//     node, so a load instruction costs one L1 wavefront per lane whatever its width
+//   * nodes and triangle records are 64 bytes = two 256-bit loads (LDG.E.256) in ONE record array: every lane walks
+//     its own node, and every 32-byte sector a lane receives costs one cycle of the SM's L1 data pipe — the unit
+//     that is 82-87 % busy; a 4th sector per node visit costs 23 %, so the node was squeezed from Ylitie's 80 bytes
+//     to 64 (21-bit grid origin, one shared exponent, 2-bit triangle counts, one child pointer for nodes and
+//     triangles alike; common.cuh)
 //   * a quantised plane byte q becomes the float 32768+q with ONE byte-permute (magic word from the constant bank,
 //     selector immediate); the 32768 bias is folded into the per-axis offset with one FMA per axis instead of one
 //     subtraction per plane (the fold costs <= 2^-9 of a quantisation step; the builder quantises with a 2^-7-step
@@ -131,8 +134,9 @@ struct RayState {
     uint32_t oct;     // dx>=0?4:0 | dy>=0?2:0 | dz>=0?1:0: slot s is visited with priority s ^ oct
 };
 
-// Tests the 4 children (slots 4Q..4Q+3) of one half of a node; returns the hit word contributions: bit 24+s and
-// bits 3s..3s+2 for every slot s whose box the ray segment overlaps. bx/by/bz carry the -32768*ad bias of byte_f.
+// Tests the 4 children (slots 4Q..4Q+3) of one half of a node; returns the hit word contributions: bit 16+s and
+// bits 2s..2s+1 for every slot s whose box the ray segment overlaps (the node's valid word keeps the internal-child
+// bit of internal children and the triangle count of leaf children). bx/by/bz carry the -32768*ad bias of byte_f.
 template <int Q>
 __device__ __forceinline__ uint32_t test_quad(uint32_t xn, uint32_t yn, uint32_t zn, uint32_t xf, uint32_t yf,
                                               uint32_t zf, float adx, float ady, float adz, float bx, float by,
@@ -145,7 +149,7 @@ __device__ __forceinline__ uint32_t test_quad(uint32_t xn, uint32_t yn, uint32_t
         float tz0 = fmaf(byte_f<J>(zn, magic), adz, bz), tz1 = fmaf(byte_f<J>(zf, magic), adz, bz);         \
         float tn = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, tmin));                                                \
         float tf = fminf(fminf(tx1, ty1), fminf(tz1, tbest));                                               \
-        if (tn <= tf) hit |= (7u << (3 * (4 * Q + J))) | (1u << (24 + 4 * Q + J));                          \
+        if (tn <= tf) hit |= (3u << (2 * (4 * Q + J))) | (1u << (16 + 4 * Q + J));                          \
     }
     BPT_CHILD(0) BPT_CHILD(1) BPT_CHILD(2) BPT_CHILD(3)
 #undef BPT_CHILD
@@ -163,27 +167,22 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
     uint2* slut = reinterpret_cast<uint2*>(smem_raw + 16);  // byte o of slut[b]: bit p = bit (p ^ o) of b
     unsigned char* spool = smem_raw + 16 + 2048;  // ray pools: 32 rays x 32 B per warp
     uint2* sstack = reinterpret_cast<uint2*>(smem_raw + kTraceSmemFixed);
-    unsigned char* snodes = smem_raw + kTraceSmemFixed + (size_t)SSTACK * BLOCK * sizeof(uint2);  // STAGED only
-    unsigned char* stris = snodes + (size_t)a.num_nodes * BPT_NODE_BYTES;  // STAGED only
+    unsigned char* srecs = smem_raw + kTraceSmemFixed + (size_t)SSTACK * BLOCK * sizeof(uint2);  // staged records
 
     const uint32_t nrays = *a.count_ptr;
     if (nrays == 0u) return;  // uniform across the grid: an exhausted bounce costs one launch and nothing else
 
-    // ---- STAGED: the whole BVH (nodes, then triangles) moves into shared memory with TMA bulk copies;
-    //      otherwise the BFS prefix of a.top_nodes nodes (the top of the tree) does
-    if (STAGED || a.top_nodes) {
-        const uint32_t node_bytes = (STAGED ? a.num_nodes : a.top_nodes) * BPT_NODE_BYTES;
-        const uint32_t tri_bytes = a.num_tris * BPT_TRI_BYTES * (STAGED ? 1u : 0u);  // triangles only in the STAGED instance
+    // ---- the first a.staged_recs records move into shared memory with TMA bulk copies: all of them in the STAGED
+    //      instance, else the BFS prefix (the top of the tree with its triangles)
+    if (a.staged_recs) {
+        const uint32_t bytes = a.staged_recs * BPT_REC_BYTES;
         if (threadIdx.x == 0) mbar_init(bar, 1);
         __syncthreads();
         if (threadIdx.x == 0) {
-            mbar_expect_tx(bar, node_bytes + tri_bytes);
+            mbar_expect_tx(bar, bytes);
             constexpr uint32_t kChunk = 32768u;
-            for (uint32_t off = 0; off < node_bytes; off += kChunk)
-                tma_bulk_g2s(snodes + off, reinterpret_cast<const unsigned char*>(a.nodes) + off, min(kChunk, node_bytes - off), bar);
-            if (STAGED)
-                for (uint32_t off = 0; off < tri_bytes; off += kChunk)
-                    tma_bulk_g2s(stris + off, reinterpret_cast<const unsigned char*>(a.tris) + off, min(kChunk, tri_bytes - off), bar);
+            for (uint32_t off = 0; off < bytes; off += kChunk)
+                tma_bulk_g2s(srecs + off, reinterpret_cast<const unsigned char*>(a.recs) + off, min(kChunk, bytes - off), bar);
         }
         mbar_wait(bar, 0);
     }
@@ -204,7 +203,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t stack_a = smem_u32(sstack + threadIdx.x);  // entry i of this lane: stack_a + i * BLOCK * 8
-    const uint32_t snodes_a = smem_u32(snodes), stris_a = smem_u32(stris), slut_a = smem_u32(slut);
+    const uint32_t srecs_a = smem_u32(srecs), slut_a = smem_u32(slut);
     const uint32_t pool_a = smem_u32(spool) + (threadIdx.x >> 5) * 1024u;
     uint2 lstack[kLocalStack];
     const uint32_t magic = a.magic;
@@ -313,11 +312,10 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                 }
                 else if (T.y == 0u) {
                     T = e; --sp;
-                    if (STAGED) { Tb = lds32(snodes_a + e.x * BPT_NODE_BYTES + 28u); Tv = lds32(snodes_a + e.x * BPT_NODE_BYTES + 32u); }
+                    if (STAGED || e.x < a.staged_recs) { const uint2 h = lds64(srecs_a + e.x * BPT_REC_BYTES + 8u); Tv = h.x; Tb = h.y; }
                     else {
-                        const unsigned char* np = reinterpret_cast<const unsigned char*>(a.nodes) + (size_t)e.x * BPT_NODE_BYTES;
-                        Tb = __ldg(reinterpret_cast<const uint32_t*>(np + 28));
-                        Tv = __ldg(reinterpret_cast<const uint32_t*>(np + 32));
+                        const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(a.recs) + (size_t)e.x * BPT_REC_BYTES + 8));
+                        Tv = h.x; Tb = h.y;
                     }
                 }
             }
@@ -331,62 +329,69 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                 const uint32_t slot = (bit - 24u) ^ r.oct;
                 const uint32_t rel = __popc(G.y & ~(0xffffffffu << slot) & 0xffu);
                 const uint32_t node = G.x + rel;
-                U8 v0, v1, v2;
-                if (STAGED) {
-                    const uint32_t np = snodes_a + node * BPT_NODE_BYTES;
-                    v0 = lds256(np); v1 = lds256(np + 32u); v2.lo = lds128(np + 64u); v2.hi = make_uint4(lds32(np + 80u), lds32(np + 84u), 0u, 0u);
-                } else if (node < a.top_nodes) {  // staged top of the tree: no miss-path traffic for the hottest levels
-                    const uint32_t np = snodes_a + node * BPT_NODE_BYTES;
-                    v0 = lds256(np); v1 = lds256(np + 32u); v2.lo = lds128(np + 64u); v2.hi = make_uint4(lds32(np + 80u), lds32(np + 84u), 0u, 0u);
+                U8 v0, v1;
+                if (STAGED || node < a.staged_recs) {  // staged: the whole BVH, or the top of the tree
+                    const uint32_t np = srecs_a + node * BPT_REC_BYTES;
+                    v0 = lds256(np); v1 = lds256(np + 32u);
                 } else {
-                    const unsigned char* np = reinterpret_cast<const unsigned char*>(a.nodes) + (size_t)node * BPT_NODE_BYTES;
-                    v0 = ldg256(np); v1 = ldg256(np + 32); v2 = ldg256(np + 64);
+                    const unsigned char* np = reinterpret_cast<const unsigned char*>(a.recs) + (size_t)node * BPT_REC_BYTES;
+                    v0 = ldg256(np); v1 = ldg256(np + 32);
                 }
-                // v0: px py pz sx | sy sz child_base tri_base   v1: valid - qlox qlox | qloy qloy qloz qloz
-                // v2: qhix qhix qhiy qhiy | qhiz qhiz - -
-                const float adx = __uint_as_float(v0.lo.w) * r.idx;
-                const float ady = __uint_as_float(v0.hi.x) * r.idy;
-                const float adz = __uint_as_float(v0.hi.y) * r.idz;
-                const float bx = fmaf(adx, -kByteBias, (__uint_as_float(v0.lo.x) - r.ox) * r.idx);
-                const float by = fmaf(ady, -kByteBias, (__uint_as_float(v0.lo.y) - r.oy) * r.idy);
-                const float bz = fmaf(adz, -kByteBias, (__uint_as_float(v0.lo.z) - r.oz) * r.idz);
+                // v0: org_lo org_hi e|valid child_base | qlox qlox qloy qloy   v1: qloz qloz qhix qhix | qhiy qhiy qhiz qhiz
+                const int lvl = TWO_LEVEL ? (node >= a.root ? 1 : 0) : 0;  // instance-level nodes live behind the mesh's
+                // origin: 21-bit grid coordinate c -> float 2^23 + c by OR-ing the exponent pattern (one LOP3), the 2^23
+                // bias is folded into the grid offset on the host (gbias = glo - 2^23 * gstep); the builder evaluates
+                // the same expression, so both sides agree on the origin bit for bit
+                const float pox = fmaf(__uint_as_float((v0.lo.x & 0x1fffffu) | 0x4b000000u), a.gstep[lvl][0], a.gbias[lvl][0]);
+                const float poy = fmaf(__uint_as_float((__funnelshift_r(v0.lo.x, v0.lo.y, 21) & 0x1fffffu) | 0x4b000000u), a.gstep[lvl][1], a.gbias[lvl][1]);
+                const float poz = fmaf(__uint_as_float(((v0.lo.y >> 10) & 0x1fffffu) | 0x4b000000u), a.gstep[lvl][2], a.gbias[lvl][2]);
+                const float step = __uint_as_float((v0.lo.z >> 1) & 0x7f800000u);  // exponent byte on top of the word
+                const float adx = step * r.idx, ady = step * r.idy, adz = step * r.idz;
+                const float bx = fmaf(adx, -kByteBias, (pox - r.ox) * r.idx);
+                const float by = fmaf(ady, -kByteBias, (poy - r.oy) * r.idy);
+                const float bz = fmaf(adz, -kByteBias, (poz - r.oz) * r.idz);
                 // near / far plane bytes by direction sign
                 const bool nx = r.idx < 0.f, ny = r.idy < 0.f, nz = r.idz < 0.f;
-                const uint32_t xn0 = nx ? v2.lo.x : v1.lo.z, xn1 = nx ? v2.lo.y : v1.lo.w, xf0 = nx ? v1.lo.z : v2.lo.x, xf1 = nx ? v1.lo.w : v2.lo.y;
-                const uint32_t yn0 = ny ? v2.lo.z : v1.hi.x, yn1 = ny ? v2.lo.w : v1.hi.y, yf0 = ny ? v1.hi.x : v2.lo.z, yf1 = ny ? v1.hi.y : v2.lo.w;
-                const uint32_t zn0 = nz ? v2.hi.x : v1.hi.z, zn1 = nz ? v2.hi.y : v1.hi.w, zf0 = nz ? v1.hi.z : v2.hi.x, zf1 = nz ? v1.hi.w : v2.hi.y;
+                const uint32_t xn0 = nx ? v1.lo.z : v0.hi.x, xn1 = nx ? v1.lo.w : v0.hi.y, xf0 = nx ? v0.hi.x : v1.lo.z, xf1 = nx ? v0.hi.y : v1.lo.w;
+                const uint32_t yn0 = ny ? v1.hi.x : v0.hi.z, yn1 = ny ? v1.hi.y : v0.hi.w, yf0 = ny ? v0.hi.z : v1.hi.x, yf1 = ny ? v0.hi.w : v1.hi.y;
+                const uint32_t zn0 = nz ? v1.hi.z : v1.lo.x, zn1 = nz ? v1.hi.w : v1.lo.y, zf0 = nz ? v1.lo.x : v1.hi.z, zf1 = nz ? v1.lo.y : v1.hi.w;
                 uint32_t hit = test_quad<0>(xn0, yn0, zn0, xf0, yf0, zf0, adx, ady, adz, bx, by, bz, r.tmin, r.tbest, magic);
                 hit |= test_quad<1>(xn1, yn1, zn1, xf1, yf1, zf1, adx, ady, adz, bx, by, bz, r.tmin, r.tbest, magic);
-                const uint32_t valid = v1.lo.x;
-                hit &= valid;  // internal children in the top byte, triangles in the low 24 bits
-                // internal hits in visiting priority (bit p <- slot p ^ oct) into byte 3, internal mask into byte 0
-                const uint2 row = lds64(slut_a + ((hit >> 24) << 3));
-                const uint32_t prio = __byte_perm(row.x, row.y, octsel);  // byte 3 = row byte `oct`, bytes 0-2 = row byte 0
-                G.x = v0.hi.z;
-                G.y = (prio & 0xff000000u) | (valid >> 24);
-                if (hit & 0x00ffffffu) {
+                const uint32_t valid = v0.lo.z;  // bits 0..15 triangle counts, 16..23 internal mask (24..31: exponent)
+                hit &= valid;
+                // internal hits in visiting priority (bit p <- slot p ^ oct) into byte 3, internal mask into byte 0;
+                // bytes 1 and 2 of a node group are never looked at
+                const uint2 row = lds64(slut_a + ((hit >> 16) << 3));
+                const uint32_t prio = __byte_perm(row.x, row.y, octsel);  // byte 3 = row byte `oct`
+                G.x = v0.lo.w;
+                G.y = __byte_perm(valid, prio, 0x7002);
+                if (hit & 0xffffu) {
                     if (T.y) BPT_PUSH(T)  // a group is still draining: park it, it is popped like any other entry
                     T.x = node;
-                    T.y = hit & 0x00ffffffu;
-                    Tb = v0.hi.w; Tv = valid;
+                    T.y = hit & 0xffffu;  // per hit leaf slot: how many of its triangles are still to be tested
+                    Tb = v0.lo.w; Tv = valid;
                 }
             }
             // ---------------- triangle step: one triangle of the lane's pending group
             __syncwarp();
             if (T.y) {
                 if (COUNT) { if (BPT_LEADER()) ++cnt_wtri; ++cnt_tris; }
-                const uint32_t k = 31u - __clz(T.y);
-                T.y &= ~(1u << k);
-                const uint32_t tri = Tb + __popc(Tv & ~(0xffffffffu << k));  // k < 24: internal bits never counted
+                // highest pending slot s, its last untested triangle k; the record sits behind the node's internal
+                // children and the triangles of the lower leaf slots
+                const uint32_t sh = (31u - __clz(T.y)) & ~1u;            // 2 * s
+                const uint32_t k = ((T.y >> sh) & 3u) - 1u;
+                T.y -= 1u << sh;
+                const uint32_t below = Tv & ~(0xffffffffu << sh);        // counts of the slots below s
+                const uint32_t tri = Tb + __popc(Tv & 0xff0000u) + __popc(below & 0x5555u) + 2u * __popc(below & 0xaaaau) + k;
                 U8 w0, w1;  // w0: ru rv   w1: rw | prim - - -
-                if (STAGED) {
-                    const uint32_t tp = stris_a + tri * BPT_TRI_BYTES;
+                if (STAGED || tri < a.staged_recs) {
+                    const uint32_t tp = srecs_a + tri * BPT_REC_BYTES;
                     w0 = lds256(tp); w1.lo = lds128(tp + 32u); w1.hi = make_uint4(lds32(tp + 48u), 0u, 0u, 0u);
                 } else {
-                    const unsigned char* tp = reinterpret_cast<const unsigned char*>(a.tris) + (size_t)tri * BPT_TRI_BYTES;
+                    const unsigned char* tp = reinterpret_cast<const unsigned char*>(a.recs) + (size_t)tri * BPT_REC_BYTES;
                     w0 = ldg256(tp); w1 = ldg256(tp + 32);
                 }
-                if (TWO_LEVEL && tri >= a.num_mesh_tris) {
+                if (TWO_LEVEL && tri >= a.root) {
                     // instance record: w0 = rows 0,1 and w1.lo = row 2 of the inverse transform, w1.hi.x = instance
                     if (G.y & 0xff000000u) BPT_PUSH(G)
                     if (T.y) BPT_PUSH(T)
@@ -455,10 +460,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
 
 }  // namespace
 
-// shared memory the traversal kernel needs; staged_* = 0 for the global instance
-size_t trace_smem_bytes(uint32_t staged_nodes, uint32_t staged_tris) {
-    return kTraceSmemFixed + (size_t)kTraceSmemStack * kTraceBlock * sizeof(uint2) + (size_t)staged_nodes * BPT_NODE_BYTES +
-           (size_t)staged_tris * BPT_TRI_BYTES;
+// shared memory the traversal kernel needs with `staged_recs` records staged
+size_t trace_smem_bytes(uint32_t staged_recs) {
+    return kTraceSmemFixed + (size_t)kTraceSmemStack * kTraceBlock * sizeof(uint2) + (size_t)staged_recs * BPT_REC_BYTES;
 }
 
 cudaError_t trace_configure() {
@@ -474,7 +478,7 @@ cudaError_t trace_configure() {
 }
 
 void trace_launch(const TraceArgs& a, unsigned grid, bool staged, bool two_level, bool count, cudaStream_t st) {
-    const size_t smem = staged ? trace_smem_bytes(a.num_nodes, a.num_tris) : trace_smem_bytes(a.top_nodes, 0);
+    const size_t smem = trace_smem_bytes(a.staged_recs);
 #define GO(S, L, C) k_trace<kTraceBlock, kTraceSmemStack, S, L, C><<<grid, kTraceBlock, smem, st>>>(a)
     if (staged) {
         if (two_level) { if (count) GO(true, true, true); else GO(true, true, false); }

@@ -19,18 +19,20 @@ struct TraceArgs {
     uint4* hits;                   // {t, -, -, prim or BPT_MISS}
     const uint32_t* count_ptr;     // number of rays (device)
     uint32_t* fetch_ctr;           // global ray fetch counter (zeroed before launch)
-    const Node8* nodes;            // BVH8 nodes, BFS order
-    const WoopTri* tris;           // triangle records, leaf order
-    uint32_t num_nodes, num_tris;  // array sizes (the STAGED instance copies all of them into shared memory)
-    uint32_t top_nodes;            // global instance: BFS prefix of the node array staged in shared memory
-    uint32_t root;                 // node the traversal starts from (0, or the instance-level root)
-    uint32_t num_mesh_tris;        // TWO_LEVEL: records from this index on are instances
+    const Node8* recs;             // the record array: BVH8 nodes and triangle / instance records (common.cuh)
+    uint32_t staged_recs;          // records [0, staged_recs) are copied into shared memory: all of them in the STAGED
+                                   // instance, else the BFS prefix (top of the tree)
+    uint32_t root;                 // record of the root node (0; the instance-level root in two-level scenes — every
+                                   // record from it on belongs to the instance level)
+    uint32_t num_mesh_tris;        // TWO_LEVEL: primitive id = instance * num_mesh_tris + triangle
+    float gbias[2][3], gstep[2][3];  // scene grids of the node origins ([0] mesh level, [1] instance level):
+                                   // origin = fmaf(float(2^23 + c), gstep, gbias), gbias = grid_lo - 2^23 * gstep
     int refill_below;              // refill a warp's idle lanes when fewer than this many are live
     int steps_per_refill;          // traversal iterations between two refill votes
     uint32_t magic;                // 0x47000000 (float 32768): byte->float permute constant, see trace.cu byte_f
     unsigned long long* stat;      // BPT_STAT_* counters (may be null when not counting: only [RAYS] is touched)
 };
 
-size_t trace_smem_bytes(uint32_t staged_nodes, uint32_t staged_tris);
+size_t trace_smem_bytes(uint32_t staged_recs);
 cudaError_t trace_configure();
 void trace_launch(const TraceArgs& a, unsigned grid, bool staged, bool two_level, bool count, cudaStream_t st);

@@ -31,7 +31,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(bpt.Params) == 7 * 4 + 9 * 4 + 2 * 4 + 2 * 4 + 3 * 4
     assert C.sizeof(bpt.Stats) == 13 * 8
     assert C.sizeof(bpt.AccelInfo) == 6 * 4 + 2 * 8 + 2 * 4
-    assert bpt.NODE8_DTYPE.itemsize == 96 and bpt.WOOP_DTYPE.itemsize == 64 and bpt.HIT_DTYPE.itemsize == 16
+    assert bpt.NODE8_DTYPE.itemsize == 64 and bpt.WOOP_DTYPE.itemsize == 64 and bpt.HIT_DTYPE.itemsize == 16
 
 
 def test_default_params_are_the_reference_constants():

@@ -107,32 +107,42 @@ def check_build_invariants(pt, verts, idx):
         np.testing.assert_array_equal(leaf_boxes[:, 3:], hi[prim_sorted])
         np.testing.assert_array_equal(aabbs[0, :3], slo)
         np.testing.assert_array_equal(aabbs[0, 3:], shi)
-    # K6: BVH8 — every triangle in exactly one leaf slot; quantised child boxes contain their triangles
-    nodes, tri_index, woop = pt.download_accel()
-    assert np.array_equal(np.sort(tri_index), np.arange(n, dtype=np.uint32))
-    visited_nodes = np.zeros(len(nodes), np.int32)
+    # K6: BVH8 — one array of 64-byte records; every triangle in exactly one triangle record; quantised child boxes
+    # contain their triangles; children records are contiguous (internal children, then triangles in slot order)
+    recs, woop, rec_prim, gbias, gstep = pt.download_accel()
+    nrec = len(recs)
+    is_tri = rec_prim != O.MISS
+    assert is_tri.sum() == n and np.array_equal(np.sort(rec_prim[is_tri]), np.arange(n, dtype=np.uint32))
+    assert info.num_nodes8 == nrec - n
+    visited = np.zeros(nrec, np.int32)
     tri_seen = np.zeros(n, np.int32)
-    stack = [(0, None, None)]
     depth = 0
     level = [(0, None, None)]
+    gbias64, gstep64 = gbias.astype(np.float64), gstep.astype(np.float64)
     while level:
         depth += 1
         nxt = []
         for (ni, plo, phi) in level:
-            nd = nodes[ni]
-            visited_nodes[ni] += 1
-            scale = nd["s"].astype(np.float64)
-            assert np.all(np.frexp(scale)[0] == 0.5)  # grid steps are powers of two
-            p = nd["p"].astype(np.float64)
+            assert not is_tri[ni]
+            nd = recs[ni]
+            visited[ni] += 1
+            org = int(nd["org"])
+            cell = np.array([org & 0x1FFFFF, (org >> 21) & 0x1FFFFF, (org >> 42) & 0x1FFFFF], np.float64)
+            # the kernel decodes the origin with one f32 FMA per axis: fmaf(float(2^23 + c), grid_step, grid_bias)
+            p = ((np.float64(8388608.0) + cell) * gstep64 + gbias64).astype(np.float32).astype(np.float64)
+            ev = int(nd["e_valid"])
+            scale = np.ldexp(1.0, (ev >> 24) - 127)
+            counts, imask = ev & 0xFFFF, (ev >> 16) & 0xFF
+            base = int(nd["child_base"])
+            n_int = bin(imask).count("1")
             rank = 0
-            valid = int(nd["valid"])
-            leaf_rank = 0  # triangles of a node are dense in (slot, k) order from tri_base
+            leaf_rank = 0
             for s in range(8):
-                inner = (valid >> (24 + s)) & 1
-                unary = (valid >> (3 * s)) & 7
-                if not inner and not unary:
+                inner = (imask >> s) & 1
+                cnt = (counts >> (2 * s)) & 3
+                if not inner and not cnt:
                     continue
-                assert not (inner and unary) and unary in (0, 1, 3, 7)
+                assert not (inner and cnt)
                 qlo = np.array([nd["qlox"][s], nd["qloy"][s], nd["qloz"][s]], np.float64)
                 qhi = np.array([nd["qhix"][s], nd["qhiy"][s], nd["qhiz"][s]], np.float64)
                 blo, bhi = p + qlo * scale, p + qhi * scale
@@ -140,27 +150,28 @@ def check_build_invariants(pt, verts, idx):
                     # node's grid, so they nest only up to one quantisation step of this node (+ the padding)
                     assert np.all(blo >= plo - scale - 1e-4) and np.all(bhi <= phi + scale + 1e-4)
                 if inner:
-                    nxt.append((int(nd["child_base"]) + rank, blo, bhi))
+                    nxt.append((base + rank, blo, bhi))
                     rank += 1
                 else:
-                    cnt = {1: 1, 3: 2, 7: 3}[unary]
                     for j in range(cnt):
-                        slot = int(nd["tri_base"]) + leaf_rank + j
-                        prim = tri_index[slot]
+                        rec = base + n_int + leaf_rank + j
+                        assert is_tri[rec] and woop["prim"][rec] == rec_prim[rec]
+                        prim = rec_prim[rec]
+                        visited[rec] += 1
                         tri_seen[prim] += 1
                         # quantised box contains the triangle with the margin the traversal kernel relies on
                         assert np.all(blo <= lo[prim] - scale / 256) and np.all(bhi >= hi[prim] + scale / 256)
                     leaf_rank += cnt
-            assert rank == bin(valid >> 24).count("1")
         level = nxt
-    assert np.all(visited_nodes == 1) and np.all(tri_seen == 1)
+    assert np.all(visited == 1) and np.all(tri_seen == 1)
     assert depth == info.max_depth8
     # K7: Woop rows map v0,v1,v2 to (0,0,0),(1,0,0),(0,1,0)
-    t = tri[tri_index].astype(np.float64)
+    tri_recs = np.nonzero(is_tri)[0]
+    t = tri[rec_prim[tri_recs]].astype(np.float64)
     area = np.linalg.norm(np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0]), axis=1)
     ok = area > 1e-12
-    assert np.array_equal(woop["prim"], tri_index)
-    M, c = woop["rows"][:, :, :3].astype(np.float64), woop["rows"][:, :, 3].astype(np.float64)
+    rows = woop["rows"][tri_recs]
+    M, c = rows[:, :, :3].astype(np.float64), rows[:, :, 3].astype(np.float64)
     # the rows are rounded once to f32, so the residual is bounded by a few f32 ulps of the magnitudes summed
     # (slivers have large rows: an absolute tolerance would measure the triangle's conditioning, not the kernel)
     eps = float(np.finfo(np.float32).eps)
@@ -237,13 +248,13 @@ def test_soup_build_and_trace(soup20k):
         compare_hits(gpu, ref, None, max_mismatch=5e-4)
         # staging must not change a single hit: default BFS prefix, no prefix, the largest prefix that fits, and the
         # whole-BVH instance switched off
-        assert 0 < pt.accel_info().top_nodes_smem <= 600
+        assert 0 < pt.accel_info().top_nodes_smem <= 900
         for opt, val in ((bpt.OPT_TOP_NODES, 0), (bpt.OPT_TOP_NODES, 1 << 20), (bpt.OPT_SMEM_TOP_NODES, 0)):
             pt.set_option(opt, val)
             assert np.array_equal(pt.trace_rays(rays), gpu), (opt, val)
         assert pt.accel_info().top_nodes_smem == 0
         pt.set_option(bpt.OPT_SMEM_TOP_NODES, 1 << 20)
-        pt.set_option(bpt.OPT_TOP_NODES, 600)
+        pt.set_option(bpt.OPT_TOP_NODES, 900)
         # instrumented kernel: same hits, plausible counters
         pt.set_option(bpt.OPT_COUNT_TRAVERSAL, 1)
         pt.reset_stats()
