@@ -111,7 +111,7 @@ typedef struct bpt_accel_info {
     uint32_t num_nodes8;      /* BVH8 nodes (64 B each)                                     */
     uint32_t num_binary_nodes;/* LBVH internal nodes (N-1)                                  */
     uint32_t top_nodes_smem;  /* records (nodes + triangles) staged into shared memory by TMA:
-                                 all of them for a scene small enough, else the BFS prefix  */
+                                 all of them for a scene small enough, else 0               */
     uint32_t max_depth8;      /* depth of the BVH8                                          */
     uint64_t bytes_nodes;     /* num_nodes8 * 64                                            */
     uint64_t bytes_tris;      /* num_tris * 64 (Woop rows + primitive id)                   */
@@ -122,14 +122,13 @@ typedef struct bpt_accel_info {
 /* options for bpt_set_option */
 #define BPT_OPT_PROFILE          1 /* 1: bracket every traversal launch with CUDA events     */
 #define BPT_OPT_COUNT_TRAVERSAL  2 /* 1: use the instrumented traversal kernel (nodes/tris)  */
-#define BPT_OPT_SMEM_TOP_NODES   3 /* stage the whole BVH in shared memory when it has at most
+#define BPT_OPT_SMEM_TOP_NODES   3 /* stage the whole BVH in shared memory (TMA) when it has at most
                                       this many nodes and fits (0 = never stage)             */
 #define BPT_OPT_TRACE_CTAS_PER_SM 4 /* persistent grid = 148 * this                          */
 #define BPT_OPT_SORT_RAYS        5 /* reserved                                               */
 #define BPT_OPT_USE_GRAPH        6 /* 1: replay a captured CUDA graph per sample pass        */
 #define BPT_OPT_PASS_PATHS       10 /* target paths per sample pass: a pass carries min(spp, this / tile pixels)
                                       samples of every tile pixel (default 2^27); results do not depend on it */
-#define BPT_OPT_TOP_NODES        11 /* big scenes: records of the BFS prefix (top of the tree) staged in shared memory */
 #define BPT_OPT_TRACE_REFILL_BELOW 8     /* traversal: refill a warp when fewer lanes than this are live */
 #define BPT_OPT_TRACE_STEPS_PER_REFILL 9 /* traversal: loop iterations between two refill votes           */
 

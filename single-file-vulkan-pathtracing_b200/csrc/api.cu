@@ -45,8 +45,6 @@ struct bpt_context {
     bool two_level = false;
     bool built = false, built_nodes_ok = false;
     bool staged = false;  // the traversal kernel instance that holds the whole BVH in shared memory is in use
-    uint32_t top_recs = 0;  // else: BFS prefix of the record array staged in shared memory
-    int64_t opt_top_recs = 900;  // BPT_OPT_TOP_NODES
 
     // wavefront buffers
     size_t cap_paths = 0;
@@ -200,7 +198,7 @@ TraceArgs make_trace_args(bpt_context* c, const float4* rays, uint4* hits, const
     TraceArgs a;
     a.rays = rays; a.hits = hits; a.count_ptr = count; a.fetch_ctr = fetch;
     a.recs = c->two_level ? c->d_recs_all : c->blas.recs;
-    a.staged_recs = c->staged ? c->blas.num_recs + (c->two_level ? c->tlas.num_recs : 0u) : c->top_recs;
+    a.staged_recs = c->staged ? c->blas.num_recs + (c->two_level ? c->tlas.num_recs : 0u) : 0u;
     a.root = c->two_level ? c->blas.num_recs : 0u;
     a.num_mesh_tris = c->ntris;
     for (int k = 0; k < 3; ++k) {
@@ -234,10 +232,6 @@ void plan_staging(bpt_context* c) {
     const uint64_t recs = (uint64_t)c->blas.num_recs + (c->two_level ? c->tlas.num_recs : 0u);
     c->staged = c->built_nodes_ok && nodes <= (uint64_t)c->opt_stage_max_nodes &&
                 trace_smem_bytes((uint32_t)recs) <= (size_t)kTraceMaxSmem;
-    // the BFS prefix only makes sense for a single-level array (record 0 = root)
-    const uint64_t cap = (kTraceMaxSmem - trace_smem_bytes(0)) / BPT_REC_BYTES;
-    c->top_recs = (c->staged || c->two_level || c->opt_stage_max_nodes == 0) ? 0u
-                  : (uint32_t)std::min<uint64_t>(std::min<uint64_t>((uint64_t)c->opt_top_recs, recs), cap);
 }
 
 // inverse of a row-major 3x4 affine transform, in double; false if singular
@@ -344,11 +338,6 @@ int bpt_set_option(bpt_context* c, int option, int64_t value) {
         case BPT_OPT_SMEM_TOP_NODES:
             if (value < 0) return bpt_fail(c, BPT_E_INVALID, "node count must be >= 0");
             c->opt_stage_max_nodes = value;
-            if (c->built) plan_staging(c);
-            return BPT_OK;
-        case BPT_OPT_TOP_NODES:
-            if (value < 0) return bpt_fail(c, BPT_E_INVALID, "node count must be >= 0");
-            c->opt_top_recs = value;
             if (c->built) plan_staging(c);
             return BPT_OK;
         case BPT_OPT_TRACE_REFILL_BELOW:
@@ -509,7 +498,7 @@ int bpt_accel_info_get(bpt_context* c, bpt_accel_info* out) {
     out->num_instances = c->ninst;
     out->num_nodes8 = c->blas.num_nodes;
     out->num_binary_nodes = c->ntris - 1;
-    out->top_nodes_smem = c->staged ? c->blas.num_recs + (c->two_level ? c->tlas.num_recs : 0u) : c->top_recs;
+    out->top_nodes_smem = c->staged ? c->blas.num_recs + (c->two_level ? c->tlas.num_recs : 0u) : 0u;
     out->num_records = c->blas.num_recs;
     out->max_depth8 = c->blas.depth;
     out->num_tlas_nodes8 = c->two_level ? c->tlas.num_nodes : 0;

@@ -9,7 +9,7 @@
 //     (one atomic on the global counter + two coalesced 128-bit loads per lane per pool) and tops its idle lanes
 //     up from it (ballot + popc prefix) whenever fewer than `refill_below` lanes are live
 //   * small scenes are staged once per CTA into shared memory with TMA bulk copies (cp.async.bulk +
-//     mbarrier complete_tx); big scenes read nodes / triangles with 256-bit loads through L1/L2
+//     mbarrier complete_tx); big scenes read their records with 256-bit loads through L1/L2
 //   * per-lane traversal stack: kSmemStack 8-byte entries in shared memory (thread-interleaved,
 //     conflict-free), overflow in local memory
 //   * rays are 2 x float4, hits 1 x uint4 -> all record traffic is 128-bit
@@ -40,10 +40,10 @@
 //     ran at 2/32 lanes
 //   * the whole warp runs every phase of the loop behind a __syncwarp(): without it the lanes that popped and the
 //     lanes that did not reach the node step as two groups and the node step runs twice per iteration at 12/32 lanes
-//   * small scenes (Cornell box: every node and triangle fits) run the STAGED instance: the BVH is copied into
-//     shared memory once per CTA by TMA bulk copies (cp.async.bulk + mbarrier) and never touched in global memory
-//     again; big scenes run the global instance, which stages the BFS prefix of the node array (the top of the
-//     tree, 600 nodes by default) the same way — worth +1 % on the 10 M soup; more than ~1000 nodes starves L1
+//   * small scenes (Cornell box: every record fits) run the STAGED instance: the record array is copied into shared
+//     memory once per CTA by TMA bulk copies (cp.async.bulk + mbarrier) and never touched in global memory again;
+//     big scenes run the global instance (staging only the top of the tree was measured at +-1 %: the shared/global
+//     dual path costs the issue slots the saved round trips buy)
 #include "trace.cuh"
 
 namespace {
@@ -172,9 +172,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
     const uint32_t nrays = *a.count_ptr;
     if (nrays == 0u) return;  // uniform across the grid: an exhausted bounce costs one launch and nothing else
 
-    // ---- the first a.staged_recs records move into shared memory with TMA bulk copies: all of them in the STAGED
-    //      instance, else the BFS prefix (the top of the tree with its triangles)
-    if (a.staged_recs) {
+    // ---- STAGED: the whole record array moves into shared memory with TMA bulk copies
+    if (STAGED) {
         const uint32_t bytes = a.staged_recs * BPT_REC_BYTES;
         if (threadIdx.x == 0) mbar_init(bar, 1);
         __syncthreads();
@@ -312,7 +311,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                 }
                 else if (T.y == 0u) {
                     T = e; --sp;
-                    if (STAGED || e.x < a.staged_recs) { const uint2 h = lds64(srecs_a + e.x * BPT_REC_BYTES + 8u); Tv = h.x; Tb = h.y; }
+                    if (STAGED) { const uint2 h = lds64(srecs_a + e.x * BPT_REC_BYTES + 8u); Tv = h.x; Tb = h.y; }
                     else {
                         const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(a.recs) + (size_t)e.x * BPT_REC_BYTES + 8));
                         Tv = h.x; Tb = h.y;
@@ -330,7 +329,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                 const uint32_t rel = __popc(G.y & ~(0xffffffffu << slot) & 0xffu);
                 const uint32_t node = G.x + rel;
                 U8 v0, v1;
-                if (STAGED || node < a.staged_recs) {  // staged: the whole BVH, or the top of the tree
+                if (STAGED) {  // staged: the whole BVH, or the top of the tree
                     const uint32_t np = srecs_a + node * BPT_REC_BYTES;
                     v0 = lds256(np); v1 = lds256(np + 32u);
                 } else {
@@ -384,7 +383,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                 const uint32_t below = Tv & ~(0xffffffffu << sh);        // counts of the slots below s
                 const uint32_t tri = Tb + __popc(Tv & 0xff0000u) + __popc(below & 0x5555u) + 2u * __popc(below & 0xaaaau) + k;
                 U8 w0, w1;  // w0: ru rv   w1: rw | prim - - -
-                if (STAGED || tri < a.staged_recs) {
+                if (STAGED) {
                     const uint32_t tp = srecs_a + tri * BPT_REC_BYTES;
                     w0 = lds256(tp); w1.lo = lds128(tp + 32u); w1.hi = make_uint4(lds32(tp + 48u), 0u, 0u, 0u);
                 } else {

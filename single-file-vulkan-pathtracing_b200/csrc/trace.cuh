@@ -20,8 +20,7 @@ struct TraceArgs {
     const uint32_t* count_ptr;     // number of rays (device)
     uint32_t* fetch_ctr;           // global ray fetch counter (zeroed before launch)
     const Node8* recs;             // the record array: BVH8 nodes and triangle / instance records (common.cuh)
-    uint32_t staged_recs;          // records [0, staged_recs) are copied into shared memory: all of them in the STAGED
-                                   // instance, else the BFS prefix (top of the tree)
+    uint32_t staged_recs;          // STAGED instance: number of records (all of them) to copy into shared memory
     uint32_t root;                 // record of the root node (0; the instance-level root in two-level scenes — every
                                    // record from it on belongs to the instance level)
     uint32_t num_mesh_tris;        // TWO_LEVEL: primitive id = instance * num_mesh_tris + triangle

@@ -41,8 +41,8 @@ def test_soup10m_closest_hits_match_the_oracle(pt_soup10m):
 
 
 def test_soup10m_4096_invariances(pt_soup10m):
-    """One 4096 x 4096 frame of 2 spp: the image does not depend on how many samples a pass carries, on the staged
-    BFS prefix, or on rendering it as 4 interleaved tiles (the multi-GPU decomposition); rays are conserved."""
+    """One 4096 x 4096 frame of 2 spp: the image does not depend on how many samples a pass carries, on the refill
+    policy of the traversal kernel, or on rendering it as 4 interleaved tiles (the multi-GPU decomposition); rays are conserved."""
     pt = pt_soup10m
     W = H = 4096
     p = bpt.default_params(W, H, 2, 8)
@@ -53,7 +53,7 @@ def test_soup10m_4096_invariances(pt_soup10m):
     sky = np.array([0.7, 0.6, 0.5], np.float32)
     assert np.array_equal(full[0, 0, :3], sky) and np.array_equal(full[-1, -1, :3], sky)   # corners see the sky (KAT-2)
     assert np.isfinite(full).all() and (full[H // 2 - 200:H // 2 + 200, W // 2 - 200:W // 2 + 200, :3] != sky).any()
-    for opt, val, back in ((bpt.OPT_PASS_PATHS, 1, 1 << 27), (bpt.OPT_TOP_NODES, 0, 900)):
+    for opt, val, back in ((bpt.OPT_PASS_PATHS, 1, 1 << 27), (bpt.OPT_TRACE_REFILL_BELOW, 20, 30)):
         pt.set_option(opt, val)
         pt.clear_image(); pt.reset_stats()
         assert np.array_equal(pt.render(p), full), opt
