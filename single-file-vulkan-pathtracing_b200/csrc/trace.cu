@@ -128,6 +128,13 @@ __device__ __forceinline__ float byte_f(uint32_t w, uint32_t magic) {
 }
 constexpr float kByteBias = 32768.0f;
 
+// 1/d for the slab tests: |d| is kept away from 0 (the sign survives) and the reciprocal is the hardware approximation
+// (MUFU.RCP, ~1 ulp): its error is far inside the padding the builder gives every box (2^-20 of the scene scale).
+__device__ __forceinline__ float safe_rcp(float d) {
+    const float eps = 1e-30f;
+    return __fdividef(1.0f, fabsf(d) > eps ? d : copysignf(eps, d));
+}
+
 struct RayState {
     float ox, oy, oz, dx, dy, dz, idx, idy, idz, tmin, tbest;
     uint32_t hprim;   // primitive of the closest hit, BPT_MISS if none
@@ -258,10 +265,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                     ray_idx = pool_base + slot;
                     r.ox = ro.x; r.oy = ro.y; r.oz = ro.z; r.tmin = ro.w;
                     r.dx = rd.x; r.dy = rd.y; r.dz = rd.z; r.tbest = rd.w;
-                    const float eps = 1e-30f;  // keep 1/d finite; direction sign is kept
-                    r.idx = 1.0f / (fabsf(rd.x) > eps ? rd.x : copysignf(eps, rd.x));
-                    r.idy = 1.0f / (fabsf(rd.y) > eps ? rd.y : copysignf(eps, rd.y));
-                    r.idz = 1.0f / (fabsf(rd.z) > eps ? rd.z : copysignf(eps, rd.z));
+                    r.idx = safe_rcp(rd.x);
+                    r.idy = safe_rcp(rd.y);
+                    r.idz = safe_rcp(rd.z);
                     r.oct = (rd.x >= 0.f ? 4u : 0u) | (rd.y >= 0.f ? 2u : 0u) | (rd.z >= 0.f ? 1u : 0u);
                     octsel = r.oct << 12;
                     r.hprim = BPT_MISS;
@@ -300,10 +306,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                         const float4 rd = __ldg(&a.rays[2 * (size_t)ray_idx + 1]);
                         r.ox = ro.x; r.oy = ro.y; r.oz = ro.z;
                         r.dx = rd.x; r.dy = rd.y; r.dz = rd.z;
-                        const float eps = 1e-30f;
-                        r.idx = 1.0f / (fabsf(rd.x) > eps ? rd.x : copysignf(eps, rd.x));
-                        r.idy = 1.0f / (fabsf(rd.y) > eps ? rd.y : copysignf(eps, rd.y));
-                        r.idz = 1.0f / (fabsf(rd.z) > eps ? rd.z : copysignf(eps, rd.z));
+                        r.idx = safe_rcp(rd.x);
+                        r.idy = safe_rcp(rd.y);
+                        r.idz = safe_rcp(rd.z);
                         r.oct = (rd.x >= 0.f ? 4u : 0u) | (rd.y >= 0.f ? 2u : 0u) | (rd.z >= 0.f ? 1u : 0u);
                         octsel = r.oct << 12;
                         inst_base = 0u;
@@ -403,10 +408,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                     const float dx = m00 * r.dx + m01 * r.dy + m02 * r.dz, dy = m10 * r.dx + m11 * r.dy + m12 * r.dz,
                                 dz = m20 * r.dx + m21 * r.dy + m22 * r.dz;
                     r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
-                    const float eps = 1e-30f;
-                    r.idx = 1.0f / (fabsf(dx) > eps ? dx : copysignf(eps, dx));
-                    r.idy = 1.0f / (fabsf(dy) > eps ? dy : copysignf(eps, dy));
-                    r.idz = 1.0f / (fabsf(dz) > eps ? dz : copysignf(eps, dz));
+                    r.idx = safe_rcp(dx);
+                    r.idy = safe_rcp(dy);
+                    r.idz = safe_rcp(dz);
                     r.oct = (dx >= 0.f ? 4u : 0u) | (dy >= 0.f ? 2u : 0u) | (dz >= 0.f ? 1u : 0u);
                     octsel = r.oct << 12;
                     inst_base = w1.hi.x * a.num_mesh_tris;
