@@ -47,7 +47,7 @@ WORKLOADS = {
 METRIC = "Mray/s"
 TILE_BLOCK = 8          # rows per interleaved block
 CPU_SAMPLE_ROWS = 128   # rows of the image the CPU baseline renders per step (spread uniformly over the image)
-CPU_SAMPLE_SPP = 4      # samples per pixel of those rows: ~10 s of work on 16 cores for the 10 M soup
+CPU_SAMPLE_SPP = 12     # samples per pixel of those rows: 10-20 s of work on 16-32 cores for the 10 M soup
 
 
 def parse_args(argv=None):
