@@ -19,6 +19,7 @@
 
 namespace {
 constexpr uint32_t kMaxDepth = 64;
+static_assert(kCounterStride == kMaxDepth + 1, "counter arrays are kMaxDepth + 1 long");
 std::string g_create_error;
 }  // namespace
 
@@ -57,7 +58,7 @@ struct bpt_context {
     float4* image_linear = nullptr;  // row-major copy produced on demand under interleaved tiling
     uint32_t img_w = 0, img_h = 0;
     uint32_t tile_block = 0, tile_nranks = 1, tile_rank = 0;  // tiling of the last bpt_trace
-    uint32_t* counters = nullptr;            // counts[kMaxDepth+1] then fetch[kMaxDepth+1]
+    uint32_t* counters = nullptr;            // counts[], fetch[], shade tile counters[] (kMaxDepth+1 each; shade.cuh)
     unsigned long long* d_stats = nullptr;   // BPT_STAT_* (trace.cuh)
 
     // options
@@ -299,7 +300,7 @@ int bpt_create(int device, void* stream, bpt_context** out) {
         }
         c->own_stream = true;
     }
-    if ((e = cudaMalloc(&c->counters, 2 * (kMaxDepth + 1) * sizeof(uint32_t))) != cudaSuccess ||
+    if ((e = cudaMalloc(&c->counters, 3 * (kMaxDepth + 1) * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&c->d_stats, BPT_STAT_COUNT * sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaMemsetAsync(c->d_stats, 0, BPT_STAT_COUNT * sizeof(unsigned long long), c->stream)) != cudaSuccess ||
         (e = trace_configure()) != cudaSuccess) {
@@ -542,7 +543,7 @@ int bpt_trace(bpt_context* c, const bpt_params* p) {
         int cur = 0;
         for (uint32_t d = 0; d < f.max_depth; ++d) {
             launch_trace(c, make_trace_args(c, c->q[cur].rays, c->hits, counts + d, fetch + d));
-            launch_shade(f, sv, d, c->q[cur], c->hits, c->q[cur ^ 1], counts, c->path_color, npix * n, c->stream);
+            launch_shade(f, sv, d, c->q[cur], c->hits, c->q[cur ^ 1], counts, fetch, c->path_color, npix * n, c->stream);
             c->stats.kernel_launches++;
             cur ^= 1;
         }

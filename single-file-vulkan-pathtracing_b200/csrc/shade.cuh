@@ -36,6 +36,10 @@ struct SceneView {
 };
 void launch_shade_records(const float* verts, const uint32_t* idx, const float* faces, uint32_t ntris, float4* out, cudaStream_t st);
 
+// Per-pass device counters: counts[d] = length of bounce d's queue, fetch[d] = ray fetch counter of bounce d's traversal
+// launch, fetch[kCounterStride + d] = tile counter of bounce d's shade launch; k_generate resets all three.
+constexpr uint32_t kCounterStride = 65;  // kMaxDepth + 1 (api.cu)
+
 // One wavefront queue (SoA): ray 2 x float4, state float4 {w.rgb, seed bits}, pixel u32 (= path id of the pass).
 struct PathQueue {
     float4* rays;
@@ -51,7 +55,7 @@ void launch_gather_pass(uint32_t npix, uint32_t ns, float4* path_color, float4* 
 // depth: index of the bounce being shaded; counts[depth] paths in `in`, survivors appended to `out`
 // and counted in counts[depth+1]. path_color: per-path radiance of the pass (indexed by path id).
 void launch_shade(const FrameParams& p, const SceneView& s, uint32_t depth, PathQueue in, const uint4* hits,
-                  PathQueue out, uint32_t* counts, float4* path_color, uint32_t max_paths, cudaStream_t st);
+                  PathQueue out, uint32_t* counts, uint32_t* fetch, float4* path_color, uint32_t max_paths, cudaStream_t st);
 // re-derives (u,v) of every hit from the original vertices (what k_shade does internally)
 void launch_refine_hits(const SceneView& s, const float4* rays, uint4* hits, uint32_t n, cudaStream_t st);
 void launch_accumulate(const FrameParams& p, float4* frame_sum, float4* image, cudaStream_t st);
