@@ -234,10 +234,18 @@ __global__ void k_gather_pass(uint32_t npix, uint32_t ns, float4* __restrict__ p
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
     float4 acc = frame_sum[i];
-    for (uint32_t s = 0; s < ns; ++s) {
-        const float4 c = path_color[(size_t)s * npix + i];
-        path_color[(size_t)s * npix + i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        acc.x += c.x; acc.y += c.y; acc.z += c.z;
+    for (uint32_t s0 = 0; s0 < ns; s0 += 8) {  // 8 independent loads in flight, then the adds in sample order
+        float4 c[8];
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k)
+            c[k] = s0 + k < ns ? path_color[(size_t)(s0 + k) * npix + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) {
+            if (s0 + k < ns) {
+                path_color[(size_t)(s0 + k) * npix + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                acc.x += c[k].x; acc.y += c[k].y; acc.z += c[k].z;
+            }
+        }
     }
     frame_sum[i] = acc;
 }
