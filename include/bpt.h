@@ -170,7 +170,8 @@ int bpt_set_instances(bpt_context* ctx, const float* xforms3x4, uint32_t n);
 int bpt_upload_soup(bpt_context* ctx, uint32_t ntris, uint32_t seed);
 
 /* ---- build: replaces Accel(...) -> buildAccelerationStructuresKHR (main.cpp:416-450,
- *      called for the BLAS at :512 and the TLAS at :538). Stream-ordered, no host sync. */
+ *      called for the BLAS at :512 and the TLAS at :538). The mesh level is rebuilt only after a new mesh was
+ *      uploaded; bpt_set_instances + bpt_build_accel rebuilds the instance level alone (moving instances). */
 int bpt_build_accel(bpt_context* ctx);
 int bpt_accel_info_get(bpt_context* ctx, bpt_accel_info* out);
 

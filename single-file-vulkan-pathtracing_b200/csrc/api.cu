@@ -45,6 +45,7 @@ struct bpt_context {
     float4* d_srec = nullptr;       // shading records, 64 B per primitive (shade.cuh)
     bool two_level = false;
     bool built = false, built_nodes_ok = false;
+    bool mesh_built = false;  // the mesh-level BVH8, triangle and shading records match the uploaded mesh
     bool staged = false;  // the traversal kernel instance that holds the whole BVH in shared memory is in use
 
     // wavefront buffers
@@ -110,6 +111,7 @@ void free_scene(bpt_context* c) {
     c->nverts = c->nidx = c->nfaces = c->ntris = 0;
     c->ninst = 1;
     c->built = false;
+    c->mesh_built = false;
 }
 void free_paths(bpt_context* c) {
     for (auto& q : c->q) {
@@ -446,19 +448,24 @@ int bpt_build_accel(bpt_context* c) {
     c->built = false; c->built_nodes_ok = false; c->staged = false;
     cudaEvent_t e0 = get_event(c), e1 = get_event(c);
     cudaEventRecord(e0, c->stream);
-    BPT_CUDA_TRY(c, bvh8_alloc(c->blas, c->ntris));
-    bvh8_launch_tri_bounds(c->blas, c->d_verts, c->d_idx, c->stream);
-    BPT_CUDA_TRY(c, bvh8_build(c->blas, c->stream));
-    if (c->blas.num_leaf_slots != c->ntris)
-        return bpt_fail(c, BPT_E_STATE, "BVH8 collapse placed %u of %u triangles", c->blas.num_leaf_slots, c->ntris);
+    // Mesh level (the reference's BLAS, main.cpp:512): only when the mesh changed. Moving the instances
+    // (bpt_set_instances + bpt_build_accel) rebuilds just the instance level below, like a TLAS rebuild.
+    if (!c->mesh_built) {
+        BPT_CUDA_TRY(c, bvh8_alloc(c->blas, c->ntris));
+        bvh8_launch_tri_bounds(c->blas, c->d_verts, c->d_idx, c->stream);
+        BPT_CUDA_TRY(c, bvh8_build(c->blas, c->stream));
+        if (c->blas.num_leaf_slots != c->ntris)
+            return bpt_fail(c, BPT_E_STATE, "BVH8 collapse placed %u of %u triangles", c->blas.num_leaf_slots, c->ntris);
+        bvh8_launch_woop(c->blas, c->d_verts, c->d_idx, c->stream);
+        cudaFree(c->d_srec);
+        c->d_srec = nullptr;
+        BPT_CUDA_TRY(c, cudaMalloc(&c->d_srec, (size_t)c->ntris * 64));
+        launch_shade_records(c->d_verts, c->d_idx, c->d_faces, c->ntris, c->d_srec, c->stream);
+        c->mesh_built = true;
+    }
     c->two_level = c->d_xforms != nullptr;
     cudaFree(c->d_recs_all);
     c->d_recs_all = nullptr;
-    bvh8_launch_woop(c->blas, c->d_verts, c->d_idx, c->stream);
-    cudaFree(c->d_srec);
-    c->d_srec = nullptr;
-    BPT_CUDA_TRY(c, cudaMalloc(&c->d_srec, (size_t)c->ntris * 64));
-    launch_shade_records(c->d_verts, c->d_idx, c->d_faces, c->ntris, c->d_srec, c->stream);
     uint32_t depth = c->blas.depth;
     if (c->two_level) {
         // K8: the same builder over the instances' world boxes (main.cpp:514-538), then one node array [mesh | instances]

@@ -498,6 +498,25 @@ def test_single_transformed_instance_matches_transformed_mesh(cornell):
         assert O.rel_l2(a.render(pa), b.render(pb)) <= 1e-3
 
 
+def test_moving_instances_rebuilds_only_the_instance_level(cornell):
+    """new transforms + bpt_build_accel keep the mesh-level BVH (the reference's BLAS) and rebuild
+    the instance level (its TLAS); the result equals a context built from scratch with the new transforms."""
+    xf0, xf1 = instance_grid(seed=3), instance_grid(seed=4)
+    rays = random_rays(100_000, 13, lo=(-5, -6, -5), hi=(5, 4, 5))
+    with bpt.PathTracer(0) as a, bpt.PathTracer(0) as b:
+        a.upload_mesh(*cornell); a.set_instances(xf0); a.build_accel()
+        recs0 = a.download_accel()[0].copy()
+        h0 = a.trace_rays(rays)
+        a.set_instances(xf1); a.build_accel()                      # instances moved
+        assert np.array_equal(a.download_accel()[0], recs0)        # mesh-level records untouched
+        b.upload_mesh(*cornell); b.set_instances(xf1); b.build_accel()
+        h1 = a.trace_rays(rays)
+        assert np.array_equal(h1, b.trace_rays(rays)) and not np.array_equal(h1, h0)
+        a.upload_mesh(*cornell)                                     # a new mesh resets to one identity instance
+        a.build_accel()
+        assert a.accel_info().num_instances == 1 and a.accel_info().num_tlas_nodes8 == 0
+
+
 def test_instance_errors(cornell):
     with bpt.PathTracer(0) as pt:
         with pytest.raises(bpt.BptError):
