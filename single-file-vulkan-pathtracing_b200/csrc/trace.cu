@@ -6,8 +6,8 @@
 //
 // Design (B200):
 //   * one persistent CTA per SM (grid = #SMs * ctas_per_sm); every warp keeps a pool of 32 rays in shared memory
-//     (one atomic on the global counter + two coalesced 128-bit loads per lane per pool) and tops its idle lanes
-//     up from it (ballot + popc prefix) whenever fewer than `refill_below` lanes are live
+//     (one atomic on the global counter + two coalesced 128-bit loads per lane per pool; 1/d and the octant are
+//     computed there, at full SIMD width) and tops its idle lanes up from it (ballot + popc prefix) whenever fewer than `refill_below` lanes are live
 //   * small scenes are staged once per CTA into shared memory with TMA bulk copies (cp.async.bulk +
 //     mbarrier complete_tx); big scenes read their records with 256-bit loads through L1/L2
 //   * per-lane traversal stack: kSmemStack 8-byte entries in shared memory (thread-interleaved,
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     uint2* slut = reinterpret_cast<uint2*>(smem_raw + 16);  // byte o of slut[b]: bit p = bit (p ^ o) of b
-    unsigned char* spool = smem_raw + 16 + 2048;  // ray pools: 32 rays x 32 B per warp
+    unsigned char* spool = smem_raw + 16 + 2048;  // ray pools: 32 rays x 48 B ({o,tmin} {d,tmax} {1/d,octant}) per warp
     uint2* sstack = reinterpret_cast<uint2*>(smem_raw + kTraceSmemFixed);
     unsigned char* srecs = smem_raw + kTraceSmemFixed + (size_t)SSTACK * BLOCK * sizeof(uint2);  // staged records
 
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t stack_a = smem_u32(sstack + threadIdx.x);  // entry i of this lane: stack_a + i * BLOCK * 8
     const uint32_t srecs_a = smem_u32(srecs), slut_a = smem_u32(slut);
-    const uint32_t pool_a = smem_u32(spool) + (threadIdx.x >> 5) * 1024u;
+    const uint32_t pool_a = smem_u32(spool) + (threadIdx.x >> 5) * 1536u;
     uint2 lstack[kLocalStack];
     const uint32_t magic = a.magic;
     const int refill_below = a.refill_below, steps_per_refill = a.steps_per_refill;
@@ -264,10 +264,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                     if (base >= nrays) { exhausted = true; break; }
                     pool_base = base; pool_count = min(32u, nrays - base); pool_next = 0u;
                     if (lane < pool_count) {
+                        // all 32 lanes set their pool ray up (1/d, octant) here, at full SIMD width, so that a lane
+                        // that takes a ray later only copies 48 bytes
                         const float4 ro = __ldg(&a.rays[2 * (size_t)(base + lane)]);
                         const float4 rd = __ldg(&a.rays[2 * (size_t)(base + lane) + 1]);
-                        sts128f(pool_a + lane * 32u, ro);
-                        sts128f(pool_a + lane * 32u + 16u, rd);
+                        const uint32_t oct = (rd.x >= 0.f ? 4u : 0u) | (rd.y >= 0.f ? 2u : 0u) | (rd.z >= 0.f ? 1u : 0u);
+                        sts128f(pool_a + lane * 48u, ro);
+                        sts128f(pool_a + lane * 48u + 16u, rd);
+                        sts128f(pool_a + lane * 48u + 32u, make_float4(safe_rcp(rd.x), safe_rcp(rd.y), safe_rcp(rd.z), __uint_as_float(oct)));
                     }
                     __syncwarp();
                 }
@@ -275,14 +279,13 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                 const uint32_t rank = __popc(idle & lt);
                 if (!active && rank < avail) {
                     const uint32_t slot = pool_next + rank;
-                    const float4 ro = as_float4(lds128(pool_a + slot * 32u)), rd = as_float4(lds128(pool_a + slot * 32u + 16u));
+                    const float4 ro = as_float4(lds128(pool_a + slot * 48u)), rd = as_float4(lds128(pool_a + slot * 48u + 16u));
+                    const float4 ri = as_float4(lds128(pool_a + slot * 48u + 32u));
                     ray_idx = pool_base + slot;
                     r.ox = ro.x; r.oy = ro.y; r.oz = ro.z; r.tmin = ro.w;
                     r.dx = rd.x; r.dy = rd.y; r.dz = rd.z; r.tbest = rd.w;
-                    r.idx = safe_rcp(rd.x);
-                    r.idy = safe_rcp(rd.y);
-                    r.idz = safe_rcp(rd.z);
-                    r.oct = (rd.x >= 0.f ? 4u : 0u) | (rd.y >= 0.f ? 2u : 0u) | (rd.z >= 0.f ? 1u : 0u);
+                    r.idx = ri.x; r.idy = ri.y; r.idz = ri.z;
+                    r.oct = __float_as_uint(ri.w);
                     octsel = r.oct << 12;
                     r.hprim = BPT_MISS;
                     inst_base = 0u;

@@ -5,7 +5,7 @@
 constexpr int kTraceBlock = 1024;      // one persistent CTA of 32 warps per SM
 constexpr int kTraceSmemStack = 8;     // per-lane stack entries held in shared memory
 constexpr int kTraceMaxSmem = 227 * 1024;
-constexpr int kTraceSmemFixed = 16 + 2048 + kTraceBlock * 32;  // mbarrier + octant permutation table + per-warp ray pools
+constexpr int kTraceSmemFixed = 16 + 2048 + kTraceBlock * 48;  // mbarrier + octant permutation table + per-warp ray pools
 constexpr int kTraceLocalStack = 40;   // overflow entries per lane in local memory
 // every node step pushes at most one sibling group and one parked triangle group
 constexpr int kTraceMaxDepth = (kTraceSmemStack + kTraceLocalStack) / 2 - 1;
