@@ -437,7 +437,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                 const float rwx = __uint_as_float(w1.lo.x), rwy = __uint_as_float(w1.lo.y), rwz = __uint_as_float(w1.lo.z);
                 const float oz = __uint_as_float(w1.lo.w) + r.ox * rwx + r.oy * rwy + r.oz * rwz;
                 const float dz = r.dx * rwx + r.dy * rwy + r.dz * rwz;
-                const float t = __fdividef(-oz, dz);
+                float rdz;  // MUFU.RCP alone: a denormal dz (ray in the triangle's plane) gives inf / NaN, which fails the range test
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rdz) : "f"(dz));
+                const float t = -oz * rdz;
                 if (t >= r.tmin && t <= r.tbest) {
                     const float rux = __uint_as_float(w0.lo.x), ruy = __uint_as_float(w0.lo.y), ruz = __uint_as_float(w0.lo.z);
                     const float rvx = __uint_as_float(w0.hi.x), rvy = __uint_as_float(w0.hi.y), rvz = __uint_as_float(w0.hi.z);
