@@ -5,32 +5,30 @@
 // ray/triangle test of the driver's acceleration structure.
 //
 // Design (B200):
-//   * one persistent CTA per SM (grid = #SMs * ctas_per_sm); every warp keeps a pool of 32 rays in shared memory
-//     (one atomic on the global counter + two coalesced 128-bit loads per lane per pool; 1/d and the octant are
-//     computed there, at full SIMD width) and tops its idle lanes up from it (ballot + popc prefix) whenever fewer than `refill_below` lanes are live
-//   * small scenes are staged once per CTA into shared memory with TMA bulk copies (cp.async.bulk +
-//     mbarrier complete_tx); big scenes read their records with 256-bit loads through L1/L2
-//   * per-lane traversal stack: kSmemStack 8-byte entries in shared memory (thread-interleaved,
-//     conflict-free), overflow in local memory
-//   * rays are 2 x float4, hits 1 x uint4 -> all record traffic is 128-bit
-//   * traversal order: octant-permuted slot priority (Ylitie et al. 2017), node groups and
-//     triangle groups share one 64-bit stack entry format
+//   * one persistent CTA of 32 warps per SM (64 registers/thread = the whole register file); every warp keeps a pool
+//     of 32 rays in shared memory (one atomic on the global counter + two coalesced 128-bit loads per lane per pool;
+//     1/d and the octant are computed there, at full SIMD width) and tops its idle lanes up from it (ballot + popc
+//     prefix) whenever fewer than `refill_below` lanes are live
+//   * per-lane traversal stack: kSmemStack 8-byte entries in shared memory (thread-interleaved, conflict-free),
+//     overflow in local memory; node groups, parked triangle groups and the instance sentinel share the entry format
+//   * rays are 2 x float4, hits 1 x uint4 -> all queue traffic is 128-bit
+//   * traversal order: octant-permuted slot priority (Ylitie et al. 2017)
 //
-// What bounds it. The kernel moves almost no DRAM bytes (L2 hit rate 76-85 %); it is bound by instruction issue and
-// by L1 wavefronts (profiles/: l1tex throughput 77 %, issue 68 %, ALU pipe 56 %), and on sm_100 the ALU pipe
-// (PRMT/LOP3/FMNMX/SEL) runs at half the rate of the FMA pipe. Hence:
-//   * nodes and triangle records are 64 bytes = two 256-bit loads (LDG.E.256) in ONE record array: every lane walks
-//     its own node, and every 32-byte sector a lane receives costs one cycle of the SM's L1 data pipe — the unit
-//     that is 82-87 % busy; a 4th sector per node visit costs 23 %, so the node was squeezed from Ylitie's 80 bytes
-//     to 64 (21-bit grid origin, one shared exponent, 2-bit triangle counts, one child pointer for nodes and
-//     triangles alike; common.cuh)
+// What bounds it (profiles/). The kernel moves almost no DRAM bytes (L2 hit rate 83-90 %). With
+// 80- and 96-byte nodes it was bound by the SM's L1 data pipe: every lane walks its own node, nothing coalesces, and
+// every 32-byte sector a lane receives costs one cycle of that pipe (82-87 % busy; a 4th sector per node visit cost
+// 23 %). With 64-byte records the bound is instruction issue (70-73 %) and the ALU pipe (PRMT/LOP3/FMNMX/SEL: half
+// the rate of the FMA pipe on sm_100, 63-66 % busy). Hence:
+//   * nodes and triangle records are 64 bytes = two 256-bit loads (LDG.E.256) in ONE record array: the node was
+//     squeezed from Ylitie's 80 bytes to 64 (21-bit grid origin, one shared exponent, 2-bit triangle counts, one
+//     child pointer for nodes and triangles alike; common.cuh)
 //   * a quantised plane byte q becomes the float 32768+q with ONE byte-permute (magic word from the constant bank,
 //     selector immediate); the 32768 bias is folded into the per-axis offset with one FMA per axis instead of one
 //     subtraction per plane (the fold costs <= 2^-9 of a quantisation step; the builder quantises with a 2^-7-step
-//     margin, build.cu)
-//   * a child that passes the slab test ORs one immediate into the hit word (its internal-child bit and its three
-//     triangle bits); one AND with the node's `valid` word then yields the internal hits (top byte, slot order) and
-//     the triangle hits (low 24 bits) — no per-child meta decoding
+//     margin, build.cu); two planes share one packed FMA (FFMA2)
+//   * a child that passes the slab test ORs one immediate into the hit word (its internal-child bit and a 2-bit
+//     all-ones triangle field); one AND with the node's `valid` word then yields the internal hits (bits 16..23,
+//     slot order) and, per hit leaf slot, its triangle count (bits 0..15) — no per-child meta decoding
 //   * the octant permutation of the internal hits (bit p <- slot p ^ oct) is one 64-bit lookup in a 2 KB
 //     shared-memory table (LSU pipe; the row of a hit byte holds its 8 permutations, so lanes with equal hit bytes
 //     broadcast) instead of three conditional bit-swap stages
@@ -40,10 +38,10 @@
 //     ran at 2/32 lanes
 //   * the whole warp runs every phase of the loop behind a __syncwarp(): without it the lanes that popped and the
 //     lanes that did not reach the node step as two groups and the node step runs twice per iteration at 12/32 lanes
-//   * small scenes (Cornell box: every record fits) run the STAGED instance: the record array is copied into shared
-//     memory once per CTA by TMA bulk copies (cp.async.bulk + mbarrier) and never touched in global memory again;
-//     big scenes run the global instance (staging only the top of the tree was measured at +-1 %: the shared/global
-//     dual path costs the issue slots the saved round trips buy)
+//   * small scenes (Cornell box, or 1000 instances of it: every record fits) run the STAGED instance: the record
+//     array is copied into shared memory once per CTA by TMA bulk copies (cp.async.bulk + mbarrier complete_tx) and
+//     never touched in global memory again; big scenes run the global instance (staging only the top of the tree was
+//     measured at +-1 %: the shared/global dual path costs the issue slots the saved round trips buy)
 #include "trace.cuh"
 
 namespace {
