@@ -408,7 +408,10 @@ def run_ours(args):
             pt.trace(params(s))
             if d.active:
                 pt.allgather_image(W, H)
-            pt.read_image(W, H, out=himg_np)         # D2H: the frame the reference would present
+            if d.rank == 0:
+                pt.read_image(W, H, out=himg_np)     # D2H: the frame the reference would present (one presenter)
+            else:
+                pt.sync()
         e1.record(stream)
         torch.cuda.synchronize(); d.barrier()
         tw1 = time.perf_counter()
@@ -417,7 +420,8 @@ def run_ours(args):
         e2e = {"value": d.sum(s2.rays_traced) / (ems * 1e-3) / 1e6, "unit": METRIC,
                "h2d_bytes_per_step": int(nt * 72 / K), "d2h_bytes_per_step": int(W * H * 16),
                "includes": f"mesh upload from pinned host memory + BVH build (once, amortised over {K} steps) + per-step "
-                           "bpt_trace" + (" + all-gather" if d.active else "") + " + full-image read-back to pinned host memory",
+                           "bpt_trace" + (" + all-gather" if d.active else "") + " + full-image read-back to pinned host memory"
+                           + (" on rank 0 (the presenter)" if d.active else ""),
                "ms_total": ems}
 
     cpu = None
