@@ -400,10 +400,13 @@ def run_ours(args):
         d.barrier(); torch.cuda.synchronize()
         tw0 = time.perf_counter()
         e0.record(stream)
+        dbg = os.environ.get("BPT_BENCH_DEBUG")
         pt.upload_mesh(hv, hi, hf)                   # H2D: 72 B per triangle
+        if dbg: print(f"[rank {d.rank}] upload {1e3 * (time.perf_counter() - tw0):.1f} ms", file=sys.stderr, flush=True)
         if w.get("instances"):
             pt.set_instances(instance_grid(w["instances"]))
         pt.build_accel()
+        if dbg: print(f"[rank {d.rank}] +build {1e3 * (time.perf_counter() - tw0):.1f} ms", file=sys.stderr, flush=True)
         for s in range(K):
             pt.trace(params(s))
             if d.active:
@@ -412,6 +415,7 @@ def run_ours(args):
                 pt.read_image(W, H, out=himg_np)     # D2H: the frame the reference would present (one presenter)
             else:
                 pt.sync()
+            if dbg: print(f"[rank {d.rank}] +step {s} {1e3 * (time.perf_counter() - tw0):.1f} ms", file=sys.stderr, flush=True)
         e1.record(stream)
         torch.cuda.synchronize(); d.barrier()
         tw1 = time.perf_counter()

@@ -43,6 +43,7 @@ struct bpt_context {
     Bvh8 tlas;                      // over the instances (two-level scenes only)
     Node8* d_recs_all = nullptr;    // two-level scenes: [mesh records | instance-level records]
     float4* d_srec = nullptr;       // shading records, 64 B per primitive (shade.cuh)
+    uint32_t srec_cap = 0;
     bool two_level = false;
     bool built = false, built_nodes_ok = false;
     bool mesh_built = false;  // the mesh-level BVH8, triangle and shading records match the uploaded mesh
@@ -373,10 +374,18 @@ static int adopt_mesh(bpt_context* c, const void* verts, uint32_t nverts, const 
     if (nfaces != nindices / 3) return bpt_fail(c, BPT_E_INVALID, "face count %u != triangle count %u", nfaces, nindices / 3);
     if (nverts == 0) return bpt_fail(c, BPT_E_INVALID, "no vertices");
     cudaSetDevice(c->device);
-    free_scene(c);
-    BPT_CUDA_TRY(c, cudaMalloc(&c->d_verts, (size_t)nverts * 12));
-    BPT_CUDA_TRY(c, cudaMalloc(&c->d_idx, (size_t)nindices * 4));
-    BPT_CUDA_TRY(c, cudaMalloc(&c->d_faces, (size_t)nfaces * 24));
+    if (c->d_verts && c->nverts == nverts && c->nidx == nindices && c->nfaces == nfaces) {
+        // same sizes (an animated mesh): keep the allocations, only the contents and the derived structures change
+        cudaFree(c->d_xforms); cudaFree(c->d_xforms_inv);
+        c->d_xforms = nullptr; c->d_xforms_inv = nullptr;
+        c->ninst = 1;
+        c->built = false; c->mesh_built = false;
+    } else {
+        free_scene(c);
+        BPT_CUDA_TRY(c, cudaMalloc(&c->d_verts, (size_t)nverts * 12));
+        BPT_CUDA_TRY(c, cudaMalloc(&c->d_idx, (size_t)nindices * 4));
+        BPT_CUDA_TRY(c, cudaMalloc(&c->d_faces, (size_t)nfaces * 24));
+    }
     BPT_CUDA_TRY(c, cudaMemcpyAsync(c->d_verts, verts, (size_t)nverts * 12, kind, c->stream));
     BPT_CUDA_TRY(c, cudaMemcpyAsync(c->d_idx, indices, (size_t)nindices * 4, kind, c->stream));
     BPT_CUDA_TRY(c, cudaMemcpyAsync(c->d_faces, faces, (size_t)nfaces * 24, kind, c->stream));
@@ -457,9 +466,12 @@ int bpt_build_accel(bpt_context* c) {
         if (c->blas.num_leaf_slots != c->ntris)
             return bpt_fail(c, BPT_E_STATE, "BVH8 collapse placed %u of %u triangles", c->blas.num_leaf_slots, c->ntris);
         bvh8_launch_woop(c->blas, c->d_verts, c->d_idx, c->stream);
-        cudaFree(c->d_srec);
-        c->d_srec = nullptr;
-        BPT_CUDA_TRY(c, cudaMalloc(&c->d_srec, (size_t)c->ntris * 64));
+        if (c->srec_cap != c->ntris) {
+            cudaFree(c->d_srec);
+            c->d_srec = nullptr; c->srec_cap = 0;
+            BPT_CUDA_TRY(c, cudaMalloc(&c->d_srec, (size_t)c->ntris * 64));
+            c->srec_cap = c->ntris;
+        }
         launch_shade_records(c->d_verts, c->d_idx, c->d_faces, c->ntris, c->d_srec, c->stream);
         c->mesh_built = true;
     }

@@ -473,6 +473,7 @@ void bvh8_free(Bvh8& b) {
 }
 
 cudaError_t bvh8_alloc(Bvh8& b, uint32_t n) {
+    if (b.n == n && b.recs) return cudaSuccess;  // rebuild over the same primitive count: keep the buffers
     bvh8_free(b);
     b.n = n;
     cudaError_t e;
