@@ -126,7 +126,8 @@ typedef struct bpt_accel_info {
                                       this many nodes and fits (0 = never stage)             */
 #define BPT_OPT_TRACE_CTAS_PER_SM 4 /* persistent grid = 148 * this                          */
 #define BPT_OPT_SORT_RAYS        5 /* reserved                                               */
-#define BPT_OPT_USE_GRAPH        6 /* 1: replay a captured CUDA graph per sample pass        */
+#define BPT_OPT_USE_GRAPH        6 /* 1: capture a frame's launch list as a CUDA graph and replay it while only the
+                                      frame index changes (pays off for launch-bound, small frames)             */
 #define BPT_OPT_PASS_PATHS       10 /* target paths per sample pass: a pass carries min(spp, this / tile pixels)
                                       samples of every tile pixel (default 2^27); results do not depend on it */
 #define BPT_OPT_TRACE_REFILL_BELOW 8     /* traversal: refill a warp when fewer lanes than this are live */

@@ -68,6 +68,14 @@ struct bpt_context {
     int64_t opt_stage_max_nodes = 1 << 20;  // BPT_OPT_SMEM_TOP_NODES: 0 disables shared-memory staging
     int ctas_per_sm = 1;
     int refill_below = 30, steps_per_refill = 2;
+    // BPT_OPT_USE_GRAPH: the launch list of a frame captured once as a CUDA graph and replayed while nothing but the
+    // frame index changes (the kernels then read the frame index from d_frame)
+    bool use_graph = false;
+    int32_t* d_frame = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    bpt_params graph_key{};
+    uint64_t graph_epoch = 0, epoch = 1;  // epoch moves whenever a buffer a captured graph points at may have moved
+    uint64_t graph_kernel_launches = 0, graph_trace_launches = 0;
     int64_t pass_paths = 1ll << 27;  // BPT_OPT_PASS_PATHS: target number of paths per sample pass
 
     // statistics
@@ -127,6 +135,7 @@ void free_paths(bpt_context* c) {
 int ensure_paths(bpt_context* c, size_t n) {
     if (n <= c->cap_paths) return BPT_OK;
     free_paths(c);
+    c->epoch++;
     for (auto& q : c->q) {
         BPT_CUDA_TRY(c, cudaMalloc(&q.rays, n * 2 * sizeof(float4)));
         BPT_CUDA_TRY(c, cudaMalloc(&q.state, n * sizeof(float4)));
@@ -141,6 +150,7 @@ int ensure_paths(bpt_context* c, size_t n) {
 
 int ensure_frame_sum(bpt_context* c, size_t npix) {
     if (npix <= c->cap_pixels) return BPT_OK;
+    c->epoch++;
     cudaFree(c->frame_sum);
     c->frame_sum = nullptr;
     c->cap_pixels = 0;
@@ -152,6 +162,7 @@ int ensure_frame_sum(bpt_context* c, size_t npix) {
 
 int ensure_image(bpt_context* c, uint32_t w, uint32_t h) {
     if (c->image && c->img_w == w && c->img_h == h) return BPT_OK;
+    c->epoch++;
     cudaFree(c->image); cudaFree(c->image_linear);
     c->image = nullptr; c->image_linear = nullptr;
     BPT_CUDA_TRY(c, cudaMalloc(&c->image, (size_t)w * h * sizeof(float4)));
@@ -227,6 +238,30 @@ void launch_trace(bpt_context* c, const TraceArgs& a) {
         c->trace_events.emplace_back(e0, e1);
     }
     c->stats.trace_launches++;
+    c->stats.kernel_launches++;
+}
+
+// The launch list of one frame on c's stream: per sample pass one generate, per bounce one traversal + one shade,
+// one gather; then the running mean. frame_dev: null, or the device int the kernels read the frame index from.
+void enqueue_frame(bpt_context* c, const FrameParams& f, uint32_t npix, uint32_t ns, const int32_t* frame_dev) {
+    SceneView sv{c->d_srec, c->d_xforms, c->ntris};
+    uint32_t* counts = c->counters;
+    uint32_t* fetch = c->counters + (kMaxDepth + 1);
+    for (uint32_t s0 = 0; s0 < f.spp_per_frame; s0 += ns) {
+        const uint32_t n = std::min(ns, f.spp_per_frame - s0);
+        launch_generate(f, frame_dev, s0, n, c->q[0], counts, fetch, f.max_depth + 1, c->stream);
+        c->stats.kernel_launches++;
+        int cur = 0;
+        for (uint32_t d = 0; d < f.max_depth; ++d) {
+            launch_trace(c, make_trace_args(c, c->q[cur].rays, c->hits, counts + d, fetch + d));
+            launch_shade(f, sv, d, c->q[cur], c->hits, c->q[cur ^ 1], counts, fetch, c->path_color, npix * n, c->stream);
+            c->stats.kernel_launches++;
+            cur ^= 1;
+        }
+        launch_gather_pass(npix, n, c->path_color, c->frame_sum, c->stream);
+        c->stats.kernel_launches++;
+    }
+    launch_accumulate(f, frame_dev, c->frame_sum, c->image, c->stream);
     c->stats.kernel_launches++;
 }
 
@@ -323,6 +358,8 @@ void bpt_destroy(bpt_context* c) {
     free_scene(c);
     free_paths(c);
     bvh8_free(c->blas); bvh8_free(c->tlas);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    cudaFree(c->d_frame);
     cudaFree(c->d_recs_all); cudaFree(c->d_srec); cudaFree(c->frame_sum);
     cudaFree(c->image); cudaFree(c->image_linear); cudaFree(c->counters); cudaFree(c->d_stats);
     for (auto& p : c->frame_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
@@ -336,6 +373,7 @@ const char* bpt_last_error(const bpt_context* c) { return c ? c->err.c_str() : g
 
 int bpt_set_option(bpt_context* c, int option, int64_t value) {
     if (!c) return BPT_E_INVALID;
+    c->epoch++;  // every option may change what a frame launches
     switch (option) {
         case BPT_OPT_PROFILE: c->profile = value != 0; return BPT_OK;
         case BPT_OPT_COUNT_TRAVERSAL: c->count = value != 0; return BPT_OK;
@@ -360,8 +398,8 @@ int bpt_set_option(bpt_context* c, int option, int64_t value) {
             if (value < 1) return bpt_fail(c, BPT_E_INVALID, "paths per pass must be >= 1");
             c->pass_paths = value;
             return BPT_OK;
-        case BPT_OPT_SORT_RAYS:
-        case BPT_OPT_USE_GRAPH: return bpt_fail(c, BPT_E_INVALID, "option %d is reserved", option);
+        case BPT_OPT_SORT_RAYS: return bpt_fail(c, BPT_E_INVALID, "option %d is reserved", option);
+        case BPT_OPT_USE_GRAPH: c->use_graph = value != 0; return BPT_OK;
         default: return bpt_fail(c, BPT_E_INVALID, "unknown option %d", option);
     }
 }
@@ -455,6 +493,7 @@ int bpt_build_accel(bpt_context* c) {
     if (c->ntris == 0) return bpt_fail(c, BPT_E_STATE, "bpt_build_accel before bpt_upload_mesh");
     cudaSetDevice(c->device);
     c->built = false; c->built_nodes_ok = false; c->staged = false;
+    c->epoch++;
     cudaEvent_t e0 = get_event(c), e1 = get_event(c);
     cudaEventRecord(e0, c->stream);
     // Mesh level (the reference's BLAS, main.cpp:512): only when the mesh changed. Moving the instances
@@ -549,28 +588,39 @@ int bpt_trace(bpt_context* c, const bpt_params* p) {
         c->tile_nranks = f.tile_block ? f.tile_nranks : 1;
         c->tile_rank = f.tile_block ? f.tile_rank : 0;
     }
-    SceneView sv{c->d_srec, c->d_xforms, c->ntris};
-    uint32_t* counts = c->counters;
-    uint32_t* fetch = c->counters + (kMaxDepth + 1);
-
     cudaEvent_t e0 = get_event(c), e1 = get_event(c);
     cudaEventRecord(e0, c->stream);
-    for (uint32_t s0 = 0; s0 < f.spp_per_frame; s0 += ns) {
-        const uint32_t n = std::min(ns, f.spp_per_frame - s0);
-        launch_generate(f, s0, n, c->q[0], counts, fetch, f.max_depth + 1, c->stream);
-        c->stats.kernel_launches++;
-        int cur = 0;
-        for (uint32_t d = 0; d < f.max_depth; ++d) {
-            launch_trace(c, make_trace_args(c, c->q[cur].rays, c->hits, counts + d, fetch + d));
-            launch_shade(f, sv, d, c->q[cur], c->hits, c->q[cur ^ 1], counts, fetch, c->path_color, npix * n, c->stream);
-            c->stats.kernel_launches++;
-            cur ^= 1;
+    // Graph replay (BPT_OPT_USE_GRAPH): frames whose launch list is short enough to be launch-bound (a Cornell box at
+    // 256 x 256 is seven launches of a few microseconds each) are captured once and replayed with one graph launch;
+    // only the frame index changes between frames, and the kernels read it from d_frame. Per-launch event timing
+    // (BPT_OPT_PROFILE) needs individual launches, so it switches the replay off.
+    if (c->use_graph && !c->profile) {
+        bpt_params key = *p;
+        key.frame = 0;
+        if (!c->d_frame) BPT_CUDA_TRY(c, cudaMalloc(&c->d_frame, sizeof(int32_t)));
+        if (!c->graph_exec || c->graph_epoch != c->epoch || memcmp(&key, &c->graph_key, sizeof(key)) != 0) {
+            if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+            const uint64_t k0 = c->stats.kernel_launches, t0 = c->stats.trace_launches;
+            cudaGraph_t g = nullptr;
+            BPT_CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            enqueue_frame(c, f, npix, ns, c->d_frame);
+            BPT_CUDA_TRY(c, cudaStreamEndCapture(c->stream, &g));
+            c->graph_kernel_launches = c->stats.kernel_launches - k0;
+            c->graph_trace_launches = c->stats.trace_launches - t0;
+            c->stats.kernel_launches = k0; c->stats.trace_launches = t0;
+            cudaError_t ge = cudaGraphInstantiate(&c->graph_exec, g, 0);
+            cudaGraphDestroy(g);
+            BPT_CUDA_TRY(c, ge);
+            c->graph_key = key;
+            c->graph_epoch = c->epoch;
         }
-        launch_gather_pass(npix, n, c->path_color, c->frame_sum, c->stream);
-        c->stats.kernel_launches++;
+        launch_set_i32(c->d_frame, f.frame, c->stream);
+        BPT_CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, c->stream));
+        c->stats.kernel_launches += c->graph_kernel_launches + 1;
+        c->stats.trace_launches += c->graph_trace_launches;
+    } else {
+        enqueue_frame(c, f, npix, ns, nullptr);
     }
-    launch_accumulate(f, c->frame_sum, c->image, c->stream);
-    c->stats.kernel_launches++;
     cudaEventRecord(e1, c->stream);
     c->frame_events.emplace_back(e0, e1);
     c->stats.paths += (uint64_t)npix * f.spp_per_frame;
@@ -713,7 +763,7 @@ int bpt_generate_rays(bpt_context* c, const bpt_params* p, uint32_t sample_in_fr
     if ((rc = ensure_paths(c, npix)) != BPT_OK) return rc;
     uint32_t* counts = c->counters;
     uint32_t* fetch = c->counters + (kMaxDepth + 1);
-    launch_generate(f, sample_in_frame, 1, c->q[0], counts, fetch, f.max_depth + 1, c->stream);
+    launch_generate(f, nullptr, sample_in_frame, 1, c->q[0], counts, fetch, f.max_depth + 1, c->stream);
     std::vector<float4> st(npix);
     BPT_CUDA_TRY(c, cudaMemcpyAsync(rays, c->q[0].rays, (size_t)npix * 32, cudaMemcpyDeviceToHost, c->stream));
     BPT_CUDA_TRY(c, cudaMemcpyAsync(st.data(), c->q[0].state, (size_t)npix * 16, cudaMemcpyDeviceToHost, c->stream));

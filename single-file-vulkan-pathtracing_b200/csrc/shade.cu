@@ -33,8 +33,11 @@ __device__ __forceinline__ V3 normalize(V3 a) { return a / sqrtf(dot(a, a)); }
 constexpr float kTwoPi = 6.2831855f, kPi = 3.1415927f, kPdf = 0.15915494f;
 
 // ---------------------------------------------------------------- K9
-__global__ void k_generate(FrameParams p, uint32_t s0, uint32_t ns, PathQueue q, uint32_t* counts, uint32_t* fetch,
-                           uint32_t ncounters) {
+// frame_dev: when non-null, the frame index is read from device memory instead of p.frame, so that a captured CUDA
+// graph of a frame's launches can be replayed for every frame (api.cu, BPT_OPT_USE_GRAPH).
+__global__ void k_generate(FrameParams p, const int32_t* __restrict__ frame_dev, uint32_t s0, uint32_t ns, PathQueue q,
+                           uint32_t* counts, uint32_t* fetch, uint32_t ncounters) {
+    if (frame_dev) p.frame = *frame_dev;
     const uint32_t npix = tile_local_rows(p) * p.width;
     const uint32_t npaths = npix * ns;  // one pass carries samples s0 .. s0+ns-1 of every tile pixel
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -255,7 +258,9 @@ __device__ __forceinline__ float unorm8_roundtrip(float x) {
     float c = fminf(fmaxf(x, 0.0f), 1.0f);  // NaN -> 0 (fmaxf drops the NaN)
     return rintf(c * 255.0f) / 255.0f;
 }
-__global__ void k_accumulate(FrameParams p, float4* __restrict__ frame_sum, float4* __restrict__ image) {
+__global__ void k_accumulate(FrameParams p, const int32_t* __restrict__ frame_dev, float4* __restrict__ frame_sum,
+                             float4* __restrict__ image) {
+    if (frame_dev) p.frame = *frame_dev;
     const uint32_t npix = tile_local_rows(p) * p.width;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
@@ -329,10 +334,10 @@ inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kBlock - 1) / kBlo
 
 }  // namespace
 
-void launch_generate(const FrameParams& p, uint32_t s0, uint32_t ns, PathQueue q, uint32_t* counts, uint32_t* fetch,
-                     uint32_t ncounters, cudaStream_t st) {
+void launch_generate(const FrameParams& p, const int32_t* frame_dev, uint32_t s0, uint32_t ns, PathQueue q, uint32_t* counts,
+                     uint32_t* fetch, uint32_t ncounters, cudaStream_t st) {
     const uint64_t threads = std::max<uint64_t>((uint64_t)tile_local_rows(p) * p.width * ns, ncounters);  // the first threads also reset the counters
-    k_generate<<<grid_for(threads), kBlock, 0, st>>>(p, s0, ns, q, counts, fetch, ncounters);
+    k_generate<<<grid_for(threads), kBlock, 0, st>>>(p, frame_dev, s0, ns, q, counts, fetch, ncounters);
 }
 void launch_gather_pass(uint32_t npix, uint32_t ns, float4* path_color, float4* frame_sum, cudaStream_t st) {
     k_gather_pass<<<grid_for(npix), kBlock, 0, st>>>(npix, ns, path_color, frame_sum);
@@ -343,14 +348,16 @@ void launch_shade(const FrameParams& p, const SceneView& s, uint32_t depth, Path
     k_shade<<<std::min(full, 148u * 16u), kBlock, 0, st>>>(p, s, depth, in, hits, out, counts, fetch + kCounterStride + depth,
                                                             path_color);
 }
+static __global__ void k_set_i32(int32_t* dst, int32_t v) { *dst = v; }
+void launch_set_i32(int32_t* dst, int32_t v, cudaStream_t st) { k_set_i32<<<1, 1, 0, st>>>(dst, v); }
 void launch_shade_records(const float* verts, const uint32_t* idx, const float* faces, uint32_t ntris, float4* out, cudaStream_t st) {
     k_shade_records<<<grid_for(ntris), kBlock, 0, st>>>(verts, idx, faces, ntris, out);
 }
 void launch_refine_hits(const SceneView& s, const float4* rays, uint4* hits, uint32_t n, cudaStream_t st) {
     k_refine_hits<<<grid_for(n), kBlock, 0, st>>>(s, rays, hits, n);
 }
-void launch_accumulate(const FrameParams& p, float4* frame_sum, float4* image, cudaStream_t st) {
-    k_accumulate<<<grid_for((uint64_t)tile_local_rows(p) * p.width), kBlock, 0, st>>>(p, frame_sum, image);
+void launch_accumulate(const FrameParams& p, const int32_t* frame_dev, float4* frame_sum, float4* image, cudaStream_t st) {
+    k_accumulate<<<grid_for((uint64_t)tile_local_rows(p) * p.width), kBlock, 0, st>>>(p, frame_dev, frame_sum, image);
 }
 void launch_soup(uint32_t ntris, uint32_t seed, float scale, float* verts, uint32_t* idx, float* faces, cudaStream_t st) {
     k_soup<<<grid_for(ntris), kBlock, 0, st>>>(ntris, seed, scale, verts, idx, faces);

@@ -48,8 +48,10 @@ struct PathQueue {
 };
 
 // one pass = samples s0..s0+ns-1 of every tile pixel; path id = slot * tile_pixels + tile-local pixel
-void launch_generate(const FrameParams& p, uint32_t s0, uint32_t ns, PathQueue q, uint32_t* counts, uint32_t* fetch,
-                     uint32_t ncounters, cudaStream_t st);
+// frame_dev (may be null): device int that overrides p.frame (graph replay)
+void launch_generate(const FrameParams& p, const int32_t* frame_dev, uint32_t s0, uint32_t ns, PathQueue q, uint32_t* counts,
+                     uint32_t* fetch, uint32_t ncounters, cudaStream_t st);
+void launch_set_i32(int32_t* dst, int32_t v, cudaStream_t st);
 // folds the per-sample colours of a finished pass into the frame sum (sample order) and clears them
 void launch_gather_pass(uint32_t npix, uint32_t ns, float4* path_color, float4* frame_sum, cudaStream_t st);
 // depth: index of the bounce being shaded; counts[depth] paths in `in`, survivors appended to `out`
@@ -58,7 +60,7 @@ void launch_shade(const FrameParams& p, const SceneView& s, uint32_t depth, Path
                   PathQueue out, uint32_t* counts, uint32_t* fetch, float4* path_color, uint32_t max_paths, cudaStream_t st);
 // re-derives (u,v) of every hit from the original vertices (what k_shade does internally)
 void launch_refine_hits(const SceneView& s, const float4* rays, uint4* hits, uint32_t n, cudaStream_t st);
-void launch_accumulate(const FrameParams& p, float4* frame_sum, float4* image, cudaStream_t st);
+void launch_accumulate(const FrameParams& p, const int32_t* frame_dev, float4* frame_sum, float4* image, cudaStream_t st);
 void launch_soup(uint32_t ntris, uint32_t seed, float scale, float* verts, uint32_t* idx, float* faces, cudaStream_t st);
 void launch_image_to_bgra8(const float4* image, uint8_t* bgra, size_t npix, cudaStream_t st);
 // rank-major (interleaved tiling) image buffer -> row-major image

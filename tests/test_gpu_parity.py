@@ -547,6 +547,31 @@ def test_cosine_sampler_converges_to_the_parity_estimator(pt_cornell):
     assert not np.array_equal(u, c)
 
 
+def test_graph_replay_is_bit_identical(pt_cornell):
+    """BPT_OPT_USE_GRAPH: a frame's launch list captured once as a CUDA graph and replayed with only the frame index
+    changing gives the same images as launching every kernel, across frames, parameter changes (re-capture) and
+    option changes; Cfg1 (256 x 256, 1 spp, depth 2) is the launch-bound case it exists for."""
+    def run(graph):
+        pt_cornell.set_option(bpt.OPT_USE_GRAPH, graph)
+        out = []
+        for (w, h, spp, depth, frames) in ((256, 256, 1, 2, 5), (64, 48, 3, 6, 3), (256, 256, 1, 2, 2)):
+            pt_cornell.clear_image()
+            out.append(pt_cornell.render(bpt.default_params(w, h, spp, depth), frames=frames).copy())
+        pt_cornell.set_option(bpt.OPT_USE_GRAPH, 0)
+        return out
+    plain, replay = run(0), run(1)
+    for a, b in zip(plain, replay):
+        assert np.array_equal(a, b)
+    pt_cornell.reset_stats()
+    pt_cornell.set_option(bpt.OPT_USE_GRAPH, 1)
+    pt_cornell.clear_image()
+    pt_cornell.render(bpt.default_params(256, 256, 1, 2), frames=4)
+    st = pt_cornell.stats()
+    pt_cornell.set_option(bpt.OPT_USE_GRAPH, 0)
+    pt_cornell.clear_image()
+    assert st.trace_launches == 4 * 2 and st.kernel_launches == 4 * (7 + 1)   # 7 kernels in the graph + the frame setter
+
+
 def test_error_paths(cornell):
     verts, idx, faces = cornell
     with bpt.PathTracer(0) as pt:
