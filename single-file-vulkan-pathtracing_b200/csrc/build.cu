@@ -232,6 +232,9 @@ __device__ __forceinline__ float half_area(float4 lo, float4 hi) {
     return dx * dy + dy * dz + dz * dx;
 }
 
+// Triangles per leaf slot. The record format allows 3; measured on the 10 M soup: 3 -> 28.2 nodes + 8.6 triangles per
+// ray, 2 -> 29.3 + 5.5 and +2.4 % Mray/s, 1 -> 29.9 + 4.7 and the same speed with 17 % more nodes.
+constexpr uint32_t kMaxLeafTris = 2u;
 constexpr float kQuantMargin = 0.0078125f;  // 2^-7 of a quantisation step, see k_bvh8_collapse
 
 // exponent e with 2^e * 255 >= ext (with margin), clamped away from denormals
@@ -333,7 +336,7 @@ __global__ void k_bvh8_collapse(CollapseArgs a) {
     // allocate the children records: internal children first (slot order), then the leaf triangles
     uint32_t n_int = 0, n_leaf = 0;
     for (int c = 0; c < nc; ++c) {
-        if (cnt[c] > 3u) ++n_int; else n_leaf += cnt[c];
+        if (cnt[c] > kMaxLeafTris) ++n_int; else n_leaf += cnt[c];
     }
     const uint32_t child_base = atomicAdd(&a.counters[0], n_int + n_leaf);
     const uint32_t qbase = n_int ? atomicAdd(&a.counters[1], n_int) : 0u;
@@ -372,7 +375,7 @@ __global__ void k_bvh8_collapse(CollapseArgs a) {
         nd.qlox[s] = qlo(clo[c].x, px, sx, isx); nd.qhix[s] = qhi(chi[c].x, px, sx, isx);
         nd.qloy[s] = qlo(clo[c].y, py, sy, isy); nd.qhiy[s] = qhi(chi[c].y, py, sy, isy);
         nd.qloz[s] = qlo(clo[c].z, pz, sz, isz); nd.qhiz[s] = qhi(chi[c].z, pz, sz, isz);
-        if (cnt[c] > 3u) {
+        if (cnt[c] > kMaxLeafTris) {
             valid |= 1u << (16 + s);
             a.wide_src[child_base + int_rank] = cand[c];
             a.list_next[qbase + int_rank] = child_base + int_rank;
