@@ -130,6 +130,8 @@ typedef struct bpt_accel_info {
                                       frame index changes (pays off for launch-bound, small frames)             */
 #define BPT_OPT_PASS_PATHS       10 /* target paths per sample pass: a pass carries min(spp, this / tile pixels)
                                       samples of every tile pixel (default 2^27); results do not depend on it */
+#define BPT_OPT_BVH_OPTIMAL_COLLAPSE 7 /* 1 (default): SAH-optimal binary -> 8-wide collapse (Ylitie et al. 2017, dynamic
+                                        programme); 0: greedy, largest surface area first                          */
 #define BPT_OPT_TRACE_REFILL_BELOW 8     /* traversal: refill a warp when fewer lanes than this are live */
 #define BPT_OPT_TRACE_STEPS_PER_REFILL 9 /* traversal: loop iterations between two refill votes           */
 

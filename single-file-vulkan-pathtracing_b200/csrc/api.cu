@@ -76,6 +76,7 @@ struct bpt_context {
     bpt_params graph_key{};
     uint64_t graph_epoch = 0, epoch = 1;  // epoch moves whenever a buffer a captured graph points at may have moved
     uint64_t graph_kernel_launches = 0, graph_trace_launches = 0;
+    bool optimal_collapse = true;  // BPT_OPT_BVH_OPTIMAL_COLLAPSE
     int64_t pass_paths = 1ll << 27;  // BPT_OPT_PASS_PATHS: target number of paths per sample pass
 
     // statistics
@@ -400,6 +401,10 @@ int bpt_set_option(bpt_context* c, int option, int64_t value) {
             return BPT_OK;
         case BPT_OPT_SORT_RAYS: return bpt_fail(c, BPT_E_INVALID, "option %d is reserved", option);
         case BPT_OPT_USE_GRAPH: c->use_graph = value != 0; return BPT_OK;
+        case BPT_OPT_BVH_OPTIMAL_COLLAPSE:  // takes effect at the next build of a changed mesh
+            c->optimal_collapse = value != 0;
+            c->mesh_built = false;
+            return BPT_OK;
         default: return bpt_fail(c, BPT_E_INVALID, "unknown option %d", option);
     }
 }
@@ -500,6 +505,7 @@ int bpt_build_accel(bpt_context* c) {
     // (bpt_set_instances + bpt_build_accel) rebuilds just the instance level below, like a TLAS rebuild.
     if (!c->mesh_built) {
         BPT_CUDA_TRY(c, bvh8_alloc(c->blas, c->ntris));
+        c->blas.optimal_collapse = c->optimal_collapse;
         bvh8_launch_tri_bounds(c->blas, c->d_verts, c->d_idx, c->stream);
         BPT_CUDA_TRY(c, bvh8_build(c->blas, c->stream));
         if (c->blas.num_leaf_slots != c->ntris)
@@ -521,6 +527,7 @@ int bpt_build_accel(bpt_context* c) {
     if (c->two_level) {
         // K8: the same builder over the instances' world boxes (main.cpp:514-538), then one node array [mesh | instances]
         BPT_CUDA_TRY(c, bvh8_alloc(c->tlas, c->ninst));
+        c->tlas.optimal_collapse = c->optimal_collapse;
         bvh8_launch_instance_bounds(c->tlas, c->d_xforms, c->blas.scene_lo, c->blas.scene_hi, c->stream);
         BPT_CUDA_TRY(c, bvh8_build(c->tlas, c->stream));
         if (c->tlas.num_leaf_slots != c->ninst)

@@ -178,10 +178,71 @@ __global__ void k_lbvh_hierarchy(const uint64_t* __restrict__ keys, uint32_t n, 
 }
 
 // K5: leaves copy their primitive box, then climb; the second arrival at a node merges.
+// Triangles per leaf slot. The record format allows 3; measured on the 10 M soup: 3 -> 28.2 nodes + 8.6 triangles per
+// ray, 2 -> 29.3 + 5.5 and +2.4 % Mray/s, 1 -> 29.9 + 4.7 and the same speed with 17 % more nodes.
+constexpr uint32_t kMaxLeafTris = 2u;
+__device__ __forceinline__ float half_area(float4 lo, float4 hi) {
+    float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// SAH-optimal collapse (Ylitie, Karras, Laine 2017, section 3), the bottom-up half, fused into the refit:
+//   c(n,1) = min(c_leaf(n), c_dist(n,8) + A_n * c_node),  c(n,i) = min(c_dist(n,i), c(n,i-1)) for i = 2..7,
+//   c_dist(n,j) = min over 0<k<j of c(left,k) + c(right,j-k),  c_leaf(n) = A_n * P_n * c_prim if P_n <= kMaxLeafTris
+// c(n,i) is the cheapest way to hand the subtree of n to a parent that offers it i child slots. dp_cost holds
+// c(n,1..7) per binary node, dp_dec the choices: byte 0 = 1 if n ends as a leaf slot; byte j-1 (j = 2..8) = the k of
+// c_dist(n,j), with 0x80 set (j <= 7) when c(n,j) falls back to c(n,j-1).
+constexpr float kCostNode = 1.0f, kCostPrim = 0.6f;
+__device__ __forceinline__ void dp_leaf(float* __restrict__ cost, uint8_t* __restrict__ dec, uint32_t node, float area) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) cost[7 * (size_t)node + i] = area * kCostPrim;
+    dec[8 * (size_t)node] = 1;
+#pragma unroll
+    for (int j = 1; j < 8; ++j) dec[8 * (size_t)node + j] = 0x80;
+}
+__device__ __forceinline__ void dp_internal(float* __restrict__ cost, uint8_t* __restrict__ dec, uint32_t node, uint32_t l,
+                                            uint32_t r, float area, uint32_t count) {
+    float cl[7], cr[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { cl[i] = __ldcg(&cost[7 * (size_t)l + i]); cr[i] = __ldcg(&cost[7 * (size_t)r + i]); }
+    float cd[9];
+    uint8_t kb[9];
+#pragma unroll
+    for (int j = 2; j <= 8; ++j) {
+        float best = FLT_MAX;
+        int bk = 1;
+#pragma unroll
+        for (int k = 1; k < j; ++k) {
+            if (k > 7 || j - k > 7) continue;
+            const float c = cl[k - 1] + cr[j - k - 1];
+            if (c < best) { best = c; bk = k; }
+        }
+        cd[j] = best; kb[j] = (uint8_t)bk;
+    }
+    float c[8];
+    const bool leaf = count <= kMaxLeafTris;
+    c[1] = leaf ? area * (float)count * kCostPrim : cd[8] + area * kCostNode;
+    uint8_t d[8];
+    d[0] = leaf ? 1 : 0;
+    d[7] = kb[8];
+#pragma unroll
+    for (int i = 2; i <= 7; ++i) {
+        if (cd[i] < c[i - 1]) { c[i] = cd[i]; d[i - 1] = kb[i]; }
+        else { c[i] = c[i - 1]; d[i - 1] = (uint8_t)(kb[i] | 0x80); }
+    }
+#pragma unroll
+    for (int i = 1; i <= 7; ++i) cost[7 * (size_t)node + i - 1] = c[i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dec[8 * (size_t)node + j] = d[j];
+}
+
+// K5: leaves copy their primitive box, then climb; the second arrival at a node merges (boxes and collapse costs).
 __global__ void k_lbvh_refit(const uint64_t* __restrict__ keys, uint32_t n, const float4* __restrict__ plo,
                              const float4* __restrict__ phi, const uint32_t* __restrict__ left,
                              const uint32_t* __restrict__ right, const uint32_t* __restrict__ parent,
-                             uint32_t* __restrict__ arrive, float4* __restrict__ nlo, float4* __restrict__ nhi) {
+                             const uint32_t* __restrict__ first, const uint32_t* __restrict__ last,
+                             uint32_t* __restrict__ arrive, float4* __restrict__ nlo, float4* __restrict__ nhi,
+                             float* __restrict__ dp_cost, uint8_t* __restrict__ dp_dec) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     uint32_t prim = (uint32_t)(keys[k] & 0xffffffffu);
@@ -189,6 +250,7 @@ __global__ void k_lbvh_refit(const uint64_t* __restrict__ keys, uint32_t n, cons
     float4 lo = plo[prim], hi = phi[prim];
     nlo[node] = lo;
     nhi[node] = hi;
+    dp_leaf(dp_cost, dp_dec, node, half_area(lo, hi));
     if (n == 1) return;
     uint32_t p = parent[node];
     while (p != 0xffffffffu) {
@@ -200,6 +262,7 @@ __global__ void k_lbvh_refit(const uint64_t* __restrict__ keys, uint32_t n, cons
         hi = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.f);
         nlo[p] = lo;
         nhi[p] = hi;
+        dp_internal(dp_cost, dp_dec, p, a, b, half_area(lo, hi), last[p] - first[p] + 1u);
         p = parent[p];
     }
 }
@@ -218,6 +281,7 @@ struct CollapseArgs {
     uint32_t* list_next;      // records of the next level's nodes
     uint32_t level_count;
     float pad;                // conservative widening of every quantised box (world units)
+    const uint8_t* dp_dec;    // choices of the optimal collapse (k_lbvh_refit), or null: greedy area-first opening
     float gbias[3], gstep[3]; // scene grid the node origins are quantised on (BPT_GRID_BITS per axis), build.cuh
 };
 
@@ -227,14 +291,7 @@ __device__ __forceinline__ uint32_t node_count(const CollapseArgs& a, uint32_t n
 __device__ __forceinline__ uint32_t node_first(const CollapseArgs& a, uint32_t node) {
     return node >= a.n - 1 ? node - (a.n - 1) : a.first[node];
 }
-__device__ __forceinline__ float half_area(float4 lo, float4 hi) {
-    float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
-    return dx * dy + dy * dz + dz * dx;
-}
 
-// Triangles per leaf slot. The record format allows 3; measured on the 10 M soup: 3 -> 28.2 nodes + 8.6 triangles per
-// ray, 2 -> 29.3 + 5.5 and +2.4 % Mray/s, 1 -> 29.9 + 4.7 and the same speed with 17 % more nodes.
-constexpr uint32_t kMaxLeafTris = 2u;
 constexpr float kQuantMargin = 0.0078125f;  // 2^-7 of a quantisation step, see k_bvh8_collapse
 
 // exponent e with 2^e * 255 >= ext (with margin), clamped away from denormals
@@ -255,6 +312,29 @@ __global__ void k_bvh8_collapse(CollapseArgs a) {
     float area[8];
     uint32_t cnt[8];
     int nc = 1;
+    if (a.dp_dec && a.n > 1 && src < a.n - 1) {
+        // top-down half of the optimal collapse: the children of this wide node are what c_dist(src, 8) chose
+        nc = 0;
+        uint32_t st_node[8];
+        int st_slots[8];
+        int top = 0;
+        const uint32_t k8 = a.dp_dec[8 * (size_t)src + 7] & 0x7fu;
+        st_node[top] = a.right[src]; st_slots[top++] = 8 - (int)k8;
+        st_node[top] = a.left[src]; st_slots[top++] = (int)k8;
+        while (top) {
+            const uint32_t nd = st_node[--top];
+            int i = st_slots[top];
+            const uint8_t* d = a.dp_dec + 8 * (size_t)nd;
+            while (i > 1 && (d[i - 1] & 0x80u)) --i;  // c(nd,i) == c(nd,i-1)
+            if (i == 1 || nd >= a.n - 1) {
+                cand[nc] = nd; cnt[nc] = node_count(a, nd); area[nc] = 0.f; ++nc;
+            } else {
+                const int k = d[i - 1] & 0x7f;
+                st_node[top] = a.right[nd]; st_slots[top++] = i - k;
+                st_node[top] = a.left[nd]; st_slots[top++] = k;
+            }
+        }
+    } else {
     cand[0] = src;
     cnt[0] = node_count(a, src);
     area[0] = FLT_MAX;
@@ -274,6 +354,7 @@ __global__ void k_bvh8_collapse(CollapseArgs a) {
         cnt[nc] = node_count(a, r);
         area[nc] = half_area(a.nlo[r], a.nhi[r]);
         ++nc;
+    }
     }
 
     const float4 blo = a.nlo[src], bhi = a.nhi[src];
@@ -470,6 +551,7 @@ cudaError_t dalloc(T** p, size_t count) {
 void bvh8_free(Bvh8& b) {
     cudaFree(b.plo); cudaFree(b.phi); cudaFree(b.keys); cudaFree(b.keys_tmp); cudaFree(b.left); cudaFree(b.right);
     cudaFree(b.parent); cudaFree(b.first); cudaFree(b.last); cudaFree(b.arrive); cudaFree(b.nlo); cudaFree(b.nhi);
+    cudaFree(b.dp_cost); cudaFree(b.dp_dec);
     cudaFree(b.recs); cudaFree(b.wide_src); cudaFree(b.rec_prim); cudaFree(b.list[0]); cudaFree(b.list[1]);
     cudaFree(b.counters); cudaFree(b.bounds); cudaFree(b.sort_tmp);
     b = Bvh8{};
@@ -486,6 +568,7 @@ cudaError_t bvh8_alloc(Bvh8& b, uint32_t n) {
     A(dalloc(&b.left, n)); A(dalloc(&b.right, n)); A(dalloc(&b.first, n)); A(dalloc(&b.last, n));
     A(dalloc(&b.parent, 2 * (size_t)n)); A(dalloc(&b.arrive, n));
     A(dalloc(&b.nlo, 2 * (size_t)n)); A(dalloc(&b.nhi, 2 * (size_t)n));
+    A(dalloc(&b.dp_cost, 14 * (size_t)n)); A(dalloc(&b.dp_dec, 16 * (size_t)n));
     // every wide node expands at least one binary internal node, so n nodes always suffice; + n triangle records
     b.nodes_cap = n < 8 ? 8 : n;
     b.recs_cap = b.nodes_cap + n;
@@ -521,7 +604,8 @@ cudaError_t bvh8_build(Bvh8& b, cudaStream_t st) {
     if (sorted != b.keys) { uint64_t* t = b.keys; b.keys = b.keys_tmp; b.keys_tmp = t; }
     if ((e = cudaMemsetAsync(b.arrive, 0, sizeof(uint32_t) * n, st)) != cudaSuccess) return e;
     if (n > 1) k_lbvh_hierarchy<<<grid_for(n - 1), kBlock, 0, st>>>(b.keys, n, b.left, b.right, b.parent, b.first, b.last);
-    k_lbvh_refit<<<grid_for(n), kBlock, 0, st>>>(b.keys, n, b.plo, b.phi, b.left, b.right, b.parent, b.arrive, b.nlo, b.nhi);
+    k_lbvh_refit<<<grid_for(n), kBlock, 0, st>>>(b.keys, n, b.plo, b.phi, b.left, b.right, b.parent, b.first, b.last, b.arrive,
+                                                 b.nlo, b.nhi, b.dp_cost, b.dp_dec);
 
     uint32_t hb[6];
     if ((e = cudaMemcpyAsync(hb, b.bounds, sizeof(hb), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
@@ -549,6 +633,7 @@ cudaError_t bvh8_build(Bvh8& b, cudaStream_t st) {
     a.n = n; a.keys = b.keys; a.left = b.left; a.right = b.right; a.first = b.first; a.last = b.last;
     a.nlo = b.nlo; a.nhi = b.nhi; a.recs = b.recs; a.wide_src = b.wide_src; a.rec_prim = b.rec_prim;
     a.counters = b.counters;
+    a.dp_dec = b.optimal_collapse ? b.dp_dec : nullptr;
     a.pad = pad;
     for (int k = 0; k < 3; ++k) { a.gbias[k] = b.grid_bias[k]; a.gstep[k] = b.grid_step[k]; }
     const uint32_t init[3] = {1u, 0u, 0u};  // record 0 = root node, expands the binary root (internal 0, or leaf 0 when n == 1)

@@ -12,6 +12,9 @@ struct Bvh8 {
     uint64_t *keys = nullptr, *keys_tmp = nullptr;
     uint32_t *left = nullptr, *right = nullptr, *parent = nullptr, *first = nullptr, *last = nullptr, *arrive = nullptr;
     float4 *nlo = nullptr, *nhi = nullptr;  // 2n-1 boxes: internal nodes, then leaves (sorted order)
+    float* dp_cost = nullptr;               // optimal-collapse costs c(node, 1..7)
+    uint8_t* dp_dec = nullptr;              // and choices, 8 bytes per binary node (build.cu)
+    bool optimal_collapse = true;           // BPT_OPT_BVH_OPTIMAL_COLLAPSE
     // BVH8 (K6): one array of 64-byte records, nodes and triangle (instance) records interleaved
     Node8* recs = nullptr;
     uint32_t nodes_cap = 0, recs_cap = 0;
