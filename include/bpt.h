@@ -134,6 +134,8 @@ typedef struct bpt_accel_info {
                                         programme); 0: greedy, largest surface area first                          */
 #define BPT_OPT_TRACE_REFILL_BELOW 8     /* traversal: refill a warp when fewer lanes than this are live */
 #define BPT_OPT_TRACE_STEPS_PER_REFILL 9 /* traversal: loop iterations between two refill votes           */
+#define BPT_OPT_TRACE_STAGED_TRIS_PER_STEP 11 /* traversal of a shared-memory-staged scene: triangle tests per lane
+                                                per loop iteration (big scenes always run one)            */
 
 /* ---- lifecycle: replaces Context ctor/dtor (main.cpp:74-267) ------------------------- */
 int  bpt_abi_version(void);

@@ -22,7 +22,7 @@ MISS = 0xFFFFFFFF
 ACCUM_FLOAT4, ACCUM_RGBA8 = 0, 1
 SAMPLER_UNIFORM, SAMPLER_COSINE = 0, 1
 OPT_PROFILE, OPT_COUNT_TRAVERSAL, OPT_SMEM_TOP_NODES, OPT_TRACE_CTAS_PER_SM = 1, 2, 3, 4
-OPT_TRACE_REFILL_BELOW, OPT_TRACE_STEPS_PER_REFILL, OPT_PASS_PATHS = 8, 9, 10
+OPT_TRACE_REFILL_BELOW, OPT_TRACE_STEPS_PER_REFILL, OPT_PASS_PATHS, OPT_TRACE_STAGED_TRIS_PER_STEP = 8, 9, 10, 11
 OPT_USE_GRAPH = 6
 OPT_BVH_OPTIMAL_COLLAPSE = 7
 NCCL_UNIQUE_ID_BYTES = 128

@@ -67,7 +67,7 @@ struct bpt_context {
     bool profile = false, count = false;
     int64_t opt_stage_max_nodes = 1 << 20;  // BPT_OPT_SMEM_TOP_NODES: 0 disables shared-memory staging
     int ctas_per_sm = 1;
-    int refill_below = 30, steps_per_refill = 2;
+    int refill_below = 30, steps_per_refill = 2, staged_tris_per_step = 2;
     // BPT_OPT_USE_GRAPH: the launch list of a frame captured once as a CUDA graph and replayed while nothing but the
     // frame index changes (the kernels then read the frame index from d_frame)
     bool use_graph = false;
@@ -222,6 +222,7 @@ TraceArgs make_trace_args(bpt_context* c, const float4* rays, uint4* hits, const
         a.gbias[1][k] = c->two_level ? c->tlas.grid_bias[k] : 0.f; a.gstep[1][k] = c->two_level ? c->tlas.grid_step[k] : 0.f;
     }
     a.refill_below = c->refill_below; a.steps_per_refill = c->steps_per_refill;
+    a.staged_tris_per_step = c->staged_tris_per_step;
     a.magic = 0x47000000u;
     a.stat = c->d_stats;
     return a;
@@ -390,6 +391,10 @@ int bpt_set_option(bpt_context* c, int option, int64_t value) {
         case BPT_OPT_TRACE_STEPS_PER_REFILL:
             if (value < 1 || value > 64) return bpt_fail(c, BPT_E_INVALID, "steps per refill must be in [1,64]");
             c->steps_per_refill = (int)value;
+            return BPT_OK;
+        case BPT_OPT_TRACE_STAGED_TRIS_PER_STEP:
+            if (value < 1 || value > 16) return bpt_fail(c, BPT_E_INVALID, "triangle tests per step must be in [1,16]");
+            c->staged_tris_per_step = (int)value;
             return BPT_OK;
         case BPT_OPT_TRACE_CTAS_PER_SM:
             if (value != 1) return bpt_fail(c, BPT_E_INVALID, "the traversal kernel runs one 1024-thread CTA per SM");

@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
     uint2 lstack[kLocalStack];
     const uint32_t magic = a.magic;
     const int refill_below = a.refill_below, steps_per_refill = a.steps_per_refill;
+    const int tris_per_step = STAGED ? a.staged_tris_per_step : 1;
 
     RayState r;
     uint2 G = make_uint2(0u, 0u);  // node group: x = first internal child, y = hits by priority << 24 | internal mask
@@ -393,6 +394,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
             }
             // ---------------- triangle step: one triangle of the lane's pending group
             __syncwarp();
+#pragma unroll 1
+            for (int q = 0; q < tris_per_step; ++q)  // global instance: exactly one
             if (T.y) {
                 if (COUNT) { if (BPT_LEADER()) ++cnt_wtri; ++cnt_tris; }
                 // highest pending slot s, its last untested triangle k; the record sits behind the node's internal

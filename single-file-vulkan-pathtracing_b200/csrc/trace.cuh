@@ -28,6 +28,7 @@ struct TraceArgs {
                                    // origin = fmaf(float(2^23 + c), gstep, gbias), gbias = grid_lo - 2^23 * gstep
     int refill_below;              // refill a warp's idle lanes when fewer than this many are live
     int steps_per_refill;          // traversal iterations between two refill votes
+    int staged_tris_per_step;      // STAGED instance: triangle tests per lane per iteration (shared-memory records)
     uint32_t magic;                // 0x47000000 (float 32768): byte->float permute constant, see trace.cu byte_f
     unsigned long long* stat;      // BPT_STAT_* counters (may be null when not counting: only [RAYS] is touched)
 };

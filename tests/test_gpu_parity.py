@@ -194,6 +194,11 @@ def test_trace_primary_rays_cornell(pt_cornell, cornell_oracle, cornell):
     assert pt_cornell.accel_info().top_nodes_smem == 0
     assert np.array_equal(pt_cornell.trace_rays(rays), gpu)
     pt_cornell.set_option(bpt.OPT_SMEM_TOP_NODES, 1 << 20)
+    # the staged instance tests 2 triangles per lane per iteration by default; the hits do not depend on that
+    for n in (1, 3):
+        pt_cornell.set_option(bpt.OPT_TRACE_STAGED_TRIS_PER_STEP, n)
+        assert np.array_equal(pt_cornell.trace_rays(rays), gpu)
+    pt_cornell.set_option(bpt.OPT_TRACE_STAGED_TRIS_PER_STEP, 2)
     # KAT-2 named pixels
     assert gpu[128 * 256 + 128]["prim"] == 30 and gpu[200 * 256 + 200]["prim"] == 6
     assert gpu[0]["prim"] == O.MISS
@@ -469,6 +474,10 @@ def test_instanced_trace_rays(pt_instanced, cornell):
     assert np.array_equal(pt.trace_rays(rays), gpu)
     pt.set_option(bpt.OPT_SMEM_TOP_NODES, 1 << 20)
     assert pt.accel_info().top_nodes_smem > 0
+    for n in (1, 4):  # triangle / instance-record tests per iteration of the staged two-level instance
+        pt.set_option(bpt.OPT_TRACE_STAGED_TRIS_PER_STEP, n)
+        assert np.array_equal(pt.trace_rays(rays), gpu)
+    pt.set_option(bpt.OPT_TRACE_STAGED_TRIS_PER_STEP, 2)
 
 
 def test_instanced_image_parity(pt_instanced):
