@@ -50,6 +50,9 @@ CPU_SAMPLE_ROWS = 128   # rows of the image the CPU baseline renders per step (s
 CPU_SAMPLE_SPP = 12     # samples per pixel of those rows: 10-20 s of work on 16-32 cores for the 10 M soup
 
 
+_RESULT_LINE = []  # rank 0's JSON line, printed by main() once stdout is restored
+
+
 def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -278,7 +281,7 @@ def run_reference(args):
            "cpu_baseline": base,
            "e2e": {"value": val, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    _RESULT_LINE.append(json.dumps(out))
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -445,17 +448,29 @@ def run_ours(args):
                           **({"options": args.opt} if args.opt else {})},
                "samples_per_s": paths / (ms * 1e-3), "rays": int(rays), "paths": int(paths), "build_ms": build_ms,
                "gpu_launches": int(st.kernel_launches), "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
-        print(json.dumps(out), flush=True)
+        _RESULT_LINE.append(json.dumps(out))
     pt.close()
     d.close()
 
 
 def main(argv=None):
     args = parse_args(argv)
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE line, the JSON result: libraries that write to file descriptor 1 on their own
+    # (NCCL prints its version banner there) are sent to stderr while the bench runs
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(keep, 1)
+        os.close(keep)
+    if _RESULT_LINE:
+        print(_RESULT_LINE[-1], flush=True)
 
 
 if __name__ == "__main__":
