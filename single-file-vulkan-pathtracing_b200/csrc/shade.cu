@@ -137,7 +137,7 @@ __global__ void k_refine_hits(SceneView s, const float4* __restrict__ rays, uint
 
 // path_color[path id] collects `color` of one sample (raygen.rgen:76); k_gather_pass folds the samples of a pass into
 // the frame sum in sample order, so the result does not depend on how many samples a pass carries.
-__global__ void k_shade(FrameParams p, SceneView s, uint32_t depth, PathQueue in, const uint4* __restrict__ hits,
+__global__ void __launch_bounds__(kBlock, 4) k_shade(FrameParams p, SceneView s, uint32_t depth, PathQueue in, const uint4* __restrict__ hits,
                         PathQueue out, uint32_t* counts, uint32_t* tile_ctr, float4* path_color) {
     // The host does not know how many paths are still alive, so a grid of a few waves per SM pulls 256-path tiles
     // from a counter, in order (one block per 256 slots of the FULL queue would launch and retire half a million
