@@ -342,8 +342,15 @@ def run_ours(args):
     e1.record(stream)
     torch.cuda.synchronize(); d.barrier()
     t1 = time.perf_counter()
-    ms = d.max(e0.elapsed_time(e1))
+    ms_own = e0.elapsed_time(e1)
+    ms = d.max(ms_own)
     st = pt.stats()
+    # the slowest and the fastest rank's own frames (all-gather excluded): a gap between them is rank imbalance or a
+    # slow GPU, not the sharding (every rank gets the same rows modulo 8-row blocks)
+    rank_frames_ms = {"min": -d.max(-st.frame_ms), "max": d.max(st.frame_ms)}
+    if os.environ.get("BPT_BENCH_DEBUG"):
+        print(f"[rank {d.rank}] timed region {ms_own:.2f} ms, traversal kernels {st.trace_kernel_ms:.2f} ms, "
+              f"frames {st.frame_ms:.2f} ms, rays {st.rays_traced}", file=sys.stderr, flush=True)
     clk = clocks.stop(t0, t1) if clocks else None
     rays = d.sum(st.rays_traced)
     paths = d.sum(st.paths)
@@ -389,6 +396,7 @@ def run_ours(args):
                 "lanes_per_tri_step": sc.tris_tested / max(sc.warp_tri_steps, 1), "avg_launch_ms": avg_launch_ms,
                 "launches": int(st.trace_launches), "rays_per_launch": st.rays_traced / launches,
                 "trace_share_of_step": st.trace_kernel_ms / max(e0.elapsed_time(e1), 1e-9)}
+    ranks = {"frames_ms_min": rank_frames_ms["min"], "frames_ms_max": rank_frames_ms["max"], "timed_region_ms": ms}
 
     # ---- end to end through the public API with host buffers
     e2e = None
@@ -438,7 +446,7 @@ def run_ours(args):
     if d.rank == 0:
         out = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": d.world, "steps": K, "warmup": WU,
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-               "data": "synthetic",
+               "data": "synthetic", "ranks": ranks,
                "config": {"workload": w["name"], "baseline_config": w["config"], "tris": info.num_tris, "instances": info.num_instances, "width": W, "height": H,
                           "spp_per_step": w["spp"], "depth": w["depth"], "sampler": "uniform hemisphere (reference)",
                           "tiling": (f"{tile['tile_block']}-row blocks round-robin over {d.world} GPUs + 1 NCCL all-gather"

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--frames", type=int, default=3)
     ap.add_argument("--opt", action="append", default=[], help="OPTION_ID=VALUE passed to bpt_set_option before the build")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--height", type=int, default=None, help="image height (default: --size)")
+    ap.add_argument("--tile", default=None, help="NRANKS,RANK[,BLOCK]: render only that rank's row blocks (multi-GPU tiling on one GPU)")
     a = ap.parse_args()
     with bpt.PathTracer(0) as pt:
         for o in a.opt:
@@ -33,7 +35,11 @@ def main():
             pt.set_option(int(k), int(v))
         pt.upload_soup(a.tris, a.seed)
         info = pt.build_accel()
-        p = lambda f: bpt.default_params(a.size, a.size, a.spp, a.depth, f)
+        kw = {}
+        if a.tile:
+            t = [int(x) for x in a.tile.split(",")]
+            kw = dict(tile_nranks=t[0], tile_rank=t[1], tile_block=t[2] if len(t) > 2 else 8)
+        p = lambda f: bpt.default_params(a.size, a.height or a.size, a.spp, a.depth, f, **kw)
         pt.trace(p(0)); pt.sync()                      # warm-up
         pt.set_option(bpt.OPT_PROFILE, 1)
         pt.reset_stats()
