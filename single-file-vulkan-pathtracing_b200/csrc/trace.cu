@@ -35,7 +35,8 @@
 //   * triangles are software-pipelined: every loop iteration does at most ONE node step and ONE triangle test per
 //     lane; a lane keeps descending (and popping node groups) while its triangle group drains, so the triangle test
 //     runs once per iteration with every lane that has a pending triangle instead of a divergent inner loop that
-//     ran at 2/32 lanes
+//     ran at 2/32 lanes (the STAGED instance tests two per iteration: with the records in shared memory and a mesh of
+//     36 triangles under 6 nodes a lane has more triangles than nodes to work through; +16 % on the Cornell box)
 //   * the whole warp runs every phase of the loop behind a __syncwarp(): without it the lanes that popped and the
 //     lanes that did not reach the node step as two groups and the node step runs twice per iteration at 12/32 lanes
 //   * small scenes (Cornell box, or 1000 instances of it: every record fits) run the STAGED instance: the record
