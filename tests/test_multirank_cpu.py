@@ -97,7 +97,8 @@ def test_reference_arm_prints_the_contract_line():
                         "--width", "64", "--height", "64", "--steps", "2", "--warmup", "1"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
-    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert len(r.stdout.strip().splitlines()) == 1, r.stdout   # stdout carries the JSON line and nothing else
+    line = json.loads(r.stdout.strip())
     assert line["impl"] == "reference" and line["metric"] == "Mray/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
