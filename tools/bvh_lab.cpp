@@ -106,7 +106,7 @@ static Bin build_lbvh(const std::vector<Tri>& tris) {
         b.left[j.node] = child(j.lo, split - 1);
         b.right[j.node] = child(split, j.hi);
     }
-    b.root = n > 1 ? 0 : 0;
+    b.root = 0;
     return b;
 }
 
