@@ -115,6 +115,26 @@ cudaEvent_t get_event(bpt_context* c) {
     return e;
 }
 
+// Folds the finished event pairs at the head of `list` into `sum_ms` and returns their events to the pool. bpt_trace
+// calls it once enough pairs are pending, so that a caller who never asks for statistics (the reference's frame loop
+// runs until the window closes, main.cpp:647) does not pile up events; `all`: the stream has been synchronised.
+void fold_events(bpt_context* c, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& list, double& sum_ms, bool all) {
+    size_t done = 0;
+    for (; done < list.size(); ++done) {
+        if (!all && cudaEventQuery(list[done].second) != cudaSuccess) {
+            (void)cudaGetLastError();  // cudaErrorNotReady is an answer, not a failure of the caller's launches
+            break;
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, list[done].first, list[done].second);
+        sum_ms += ms;
+        c->event_pool.push_back(list[done].first);
+        c->event_pool.push_back(list[done].second);
+    }
+    list.erase(list.begin(), list.begin() + (std::ptrdiff_t)done);
+}
+constexpr size_t kFoldEventsAt = 256;  // pending pairs that trigger a fold in bpt_trace
+
 void free_scene(bpt_context* c) {
     cudaFree(c->d_verts); cudaFree(c->d_idx); cudaFree(c->d_faces); cudaFree(c->d_xforms); cudaFree(c->d_xforms_inv);
     c->d_verts = nullptr; c->d_idx = nullptr; c->d_faces = nullptr; c->d_xforms = nullptr; c->d_xforms_inv = nullptr;
@@ -600,6 +620,8 @@ int bpt_trace(bpt_context* c, const bpt_params* p) {
         c->tile_nranks = f.tile_block ? f.tile_nranks : 1;
         c->tile_rank = f.tile_block ? f.tile_rank : 0;
     }
+    if (c->frame_events.size() >= kFoldEventsAt) fold_events(c, c->frame_events, c->stats.frame_ms, false);
+    if (c->trace_events.size() >= kFoldEventsAt) fold_events(c, c->trace_events, c->stats.trace_kernel_ms, false);
     cudaEvent_t e0 = get_event(c), e1 = get_event(c);
     cudaEventRecord(e0, c->stream);
     // Graph replay (BPT_OPT_USE_GRAPH): frames whose launch list is short enough to be launch-bound (a Cornell box at
@@ -713,20 +735,8 @@ int bpt_get_stats(bpt_context* c, bpt_stats* out) {
     c->stats.warp_node_steps = h[BPT_STAT_WARP_NODE_STEPS];
     c->stats.warp_tri_steps = h[BPT_STAT_WARP_TRI_STEPS];
     c->stats.lane_iterations = h[BPT_STAT_LANE_ITERS];
-    for (auto& p : c->frame_events) {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, p.first, p.second);
-        c->stats.frame_ms += ms;
-        c->event_pool.push_back(p.first); c->event_pool.push_back(p.second);
-    }
-    c->frame_events.clear();
-    for (auto& p : c->trace_events) {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, p.first, p.second);
-        c->stats.trace_kernel_ms += ms;
-        c->event_pool.push_back(p.first); c->event_pool.push_back(p.second);
-    }
-    c->trace_events.clear();
+    fold_events(c, c->frame_events, c->stats.frame_ms, true);
+    fold_events(c, c->trace_events, c->stats.trace_kernel_ms, true);
     *out = c->stats;
     return BPT_OK;
 }

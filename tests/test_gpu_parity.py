@@ -389,6 +389,31 @@ def test_determinism(pt_cornell):
     assert np.array_equal(a, b)
 
 
+def test_long_frame_loop_folds_its_events(cornell):
+    """A caller that never asks for statistics (the reference's frame loop, main.cpp:647-685) must not pile up timing
+    events: bpt_trace folds finished event pairs into the running sums once 256 are pending; the sums stay right and
+    the image equals the one of a loop that reads the statistics every frame."""
+    import time
+    imgs = []
+    for poll in (False, True):
+        with bpt.PathTracer(0) as pt:
+            pt.upload_mesh(*cornell)
+            pt.build_accel()
+            pt.set_option(bpt.OPT_PROFILE, 1)
+            pt.reset_stats()
+            t0 = time.perf_counter()
+            for f in range(700):
+                pt.trace(bpt.default_params(32, 32, 1, 3, f))
+                if poll:
+                    pt.stats()
+            st = pt.stats()
+            wall_ms = 1e3 * (time.perf_counter() - t0)
+            assert st.paths == 700 * 32 * 32 and st.trace_launches >= 700
+            assert 0.0 < st.trace_kernel_ms < st.frame_ms <= wall_ms
+            imgs.append(pt.read_image(32, 32))
+    assert np.array_equal(imgs[0], imgs[1])
+
+
 def test_rgba8_mode(pt_cornell, cornell_oracle):
     """T2: unorm8 running mean, two frames, against the oracle's emulation; BGRA8 readback order."""
     pt_cornell.clear_image()
