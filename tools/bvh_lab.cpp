@@ -8,7 +8,9 @@
 // nodes visited without any child hit, and triangles tested. Child boxes are unquantised and children are visited
 // front to back, so absolute counts are a little below the GPU's; the ratio between variants is what matters.
 //
-//   g++ -O3 -march=native -std=c++17 -pthread tools/bvh_lab.cpp -o /tmp/bvh_lab && /tmp/bvh_lab 1000000
+//   g++ -O3 -march=native -std=c++17 -pthread tools/bvh_lab.cpp -o /tmp/bvh_lab
+//   /tmp/bvh_lab 1000000 200000        builder / traversal variants
+//   /tmp/bvh_lab 1000000 100000 simt   warp-level model of the traversal loop and its triangle-step policies
 #include <algorithm>
 #include <array>
 #include <atomic>
@@ -419,6 +421,155 @@ static Stats trace_stats(const Wide& w, const std::vector<Tri>& tris, uint32_t n
     return s;
 }
 
+// ---------------------------------------------------------------- warp-level model of k_trace's loop (trace.cu)
+// 32 lanes in lockstep: per iteration (pop) -> node step -> triangle step -> (terminate); a lane does at most one node
+// step and `tris_per_step` triangle tests per iteration, parks a draining triangle group on its stack when a node
+// produces a new one, and idle lanes are refilled when fewer than `refill_below` are live (voted every
+// `steps_per_refill` iterations). A phase costs its issue slots once per warp, however many lanes take part; the
+// per-phase instruction counts are the ncu source-view shares of profiles/r1f (375 per iteration: node step incl.
+// pick/push 240, triangle step 74, pop + refill + terminate + loop 63). Policies decide WHEN the triangle step runs.
+struct Policy {
+    const char* name;
+    int tri_every = 1;       // triangle step only every n-th iteration
+    int tri_min_lanes = 1;   // ... and only if this many lanes have a triangle pending, or a lane has nothing else to do
+    int tris_per_step = 1;
+};
+struct Ray { float o[3], d[3], inv[3], tmin, tbest; int oct; };
+struct NGroup { int32_t node = -1; uint8_t mask = 0; };   // remaining hit internal children of `node` (bit = child index)
+struct TGroup { uint8_t n = 0; uint32_t tri[16]; };
+struct SEntry { bool is_tri; NGroup g; TGroup t; };
+struct Lane { bool active = false; bool fresh = false; Ray r; NGroup G; TGroup T; std::vector<SEntry> st; };
+
+static Ray make_ray(const std::vector<Tri>& tris, uint32_t r, uint32_t seed) {
+    uint32_t st = seed + r * 0x9E3779B9u;
+    auto rnd = [&] { return (float)pcg(st) * 2.3283064365386963e-10f; };
+    const Tri& tr = tris[pcg(st) % tris.size()];
+    float u = rnd(), v = rnd(); if (u + v > 1.f) { u = 1.f - u; v = 1.f - v; }
+    const V3 o = tr.v[0] + (tr.v[1] - tr.v[0]) * u + (tr.v[2] - tr.v[0]) * v;
+    const float z = 2.f * rnd() - 1.f, ph = 6.2831853f * rnd(), rr = std::sqrt(std::max(0.f, 1.f - z * z));
+    Ray q;
+    q.o[0] = o.x; q.o[1] = o.y; q.o[2] = o.z;
+    q.d[0] = rr * std::cos(ph); q.d[1] = rr * std::sin(ph); q.d[2] = z;
+    for (int a = 0; a < 3; ++a) q.inv[a] = 1.f / q.d[a];
+    q.tmin = 1e-4f; q.tbest = 1e30f;
+    q.oct = (q.d[0] >= 0.f ? 4 : 0) | (q.d[1] >= 0.f ? 2 : 0) | (q.d[2] >= 0.f ? 1 : 0);
+    return q;
+}
+
+struct SimOut { double warp_iters = 0, lane_iters = 0, wnode = 0, wtri = 0, nodes = 0, tris = 0, cost = 0; };
+
+static SimOut simulate(const Wide& w, const std::vector<Tri>& tris, uint32_t nrays, const Policy& pol, int refill_below = 30,
+                       int steps_per_refill = 2) {
+    const unsigned T = std::max(1u, std::thread::hardware_concurrency());
+    const uint32_t nwarps = 64;  // independent warps, each pulling 32-ray pools from its own range
+    std::vector<SimOut> part(nwarps);
+    std::atomic<uint32_t> next_warp{0};
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; ++t) th.emplace_back([&] {
+        for (;;) {
+            const uint32_t wi = next_warp.fetch_add(1);
+            if (wi >= nwarps) break;
+            SimOut s;
+            uint32_t ray_lo = (uint64_t)nrays * wi / nwarps, ray_hi = (uint64_t)nrays * (wi + 1) / nwarps;
+            Lane lane[32];
+            long it = 0;
+            for (;;) {
+                if (it % steps_per_refill == 0) {
+                    int live = 0;
+                    for (auto& l : lane) live += l.active;
+                    if (live < refill_below && ray_lo < ray_hi)
+                        for (auto& l : lane) if (!l.active && ray_lo < ray_hi) {
+                            l.active = true; l.fresh = true; l.r = make_ray(tris, ray_lo++, 777u);
+                            l.G = NGroup{}; l.T.n = 0; l.st.clear();
+                        }
+                    live = 0;
+                    for (auto& l : lane) live += l.active;
+                    if (!live) break;
+                }
+                s.warp_iters += 1;
+                for (auto& l : lane) s.lane_iters += l.active;
+                // pop
+                for (auto& l : lane) if (l.active && !l.fresh && !l.G.mask && !l.st.empty()) {
+                    SEntry& e = l.st.back();
+                    if (!e.is_tri) { l.G = e.g; l.st.pop_back(); }
+                    else if (!l.T.n) { l.T = e.t; l.st.pop_back(); }
+                }
+                // node step
+                int nl = 0;
+                for (auto& l : lane) if (l.active && (l.fresh || l.G.mask)) {
+                    ++nl;
+                    int32_t visit;
+                    if (l.fresh) { visit = 0; l.fresh = false; }
+                    else {
+                        const Wide::Node& pn = w.nodes[l.G.node];
+                        int best = -1, bp = -1;
+                        for (int c = 0; c < pn.n; ++c) if (l.G.mask >> c & 1) { const int pr = pn.slot[c] ^ l.r.oct; if (pr > bp) { bp = pr; best = c; } }
+                        l.G.mask &= (uint8_t)~(1u << best);
+                        if (l.G.mask) l.st.push_back(SEntry{false, l.G, TGroup{}});
+                        visit = pn.child[best];
+                    }
+                    const Wide::Node& nd = w.nodes[visit];
+                    NGroup ng; ng.node = visit;
+                    TGroup nt;
+                    for (int c = nd.n - 1; c >= 0; --c) {
+                        float tn = l.r.tmin, tf = l.r.tbest;
+                        for (int a = 0; a < 3; ++a) {
+                            float t0 = (nd.cb[c].lo[a] - l.r.o[a]) * l.r.inv[a], t1 = (nd.cb[c].hi[a] - l.r.o[a]) * l.r.inv[a];
+                            if (t0 > t1) std::swap(t0, t1);
+                            tn = std::max(tn, t0); tf = std::min(tf, t1);
+                        }
+                        if (tn > tf) continue;
+                        if (nd.child[c] >= 0) ng.mask |= (uint8_t)(1u << c);
+                        else for (int k = 0; k < nd.ntri[c]; ++k) nt.tri[nt.n++] = nd.tri[c][k];
+                    }
+                    l.G = ng;
+                    if (nt.n) {
+                        if (l.T.n) l.st.push_back(SEntry{true, NGroup{}, l.T});
+                        l.T = nt;
+                    }
+                }
+                if (nl) { s.wnode += 1; s.nodes += nl; }
+                // triangle step
+                int pending = 0; bool starving = false;
+                for (auto& l : lane) if (l.active && l.T.n) { ++pending; if (!l.G.mask) starving = true; }
+                if (pending && it % pol.tri_every == 0 && (pending >= pol.tri_min_lanes || starving)) {
+                    s.wtri += 1;
+                    for (auto& l : lane) if (l.active && l.T.n)
+                        for (int q = 0; q < pol.tris_per_step && l.T.n; ++q) {
+                            s.tris += 1;
+                            const Tri& tq = tris[l.T.tri[--l.T.n]];
+                            const V3 o{l.r.o[0], l.r.o[1], l.r.o[2]}, dir{l.r.d[0], l.r.d[1], l.r.d[2]};
+                            const V3 e1 = tq.v[1] - tq.v[0], e2 = tq.v[2] - tq.v[0], p = cross(dir, e2);
+                            const float det = dot(e1, p);
+                            if (det == 0.f) continue;
+                            const float id = 1.f / det; const V3 sv = o - tq.v[0];
+                            const float uu = dot(sv, p) * id; const V3 qq = cross(sv, e1);
+                            const float vv = dot(dir, qq) * id, tt = dot(e2, qq) * id;
+                            if (uu >= 0.f && vv >= 0.f && uu + vv <= 1.f && tt >= l.r.tmin && tt < l.r.tbest) l.r.tbest = tt;
+                        }
+                }
+                // terminate
+                for (auto& l : lane) if (l.active && !l.fresh && !l.G.mask && !l.T.n && l.st.empty()) l.active = false;
+                ++it;
+            }
+            part[wi] = s;
+        }
+    });
+    for (auto& x : th) x.join();
+    SimOut s;
+    for (auto& p : part) { s.warp_iters += p.warp_iters; s.lane_iters += p.lane_iters; s.wnode += p.wnode; s.wtri += p.wtri; s.nodes += p.nodes; s.tris += p.tris; }
+    s.cost = (63.0 * s.warp_iters + 240.0 * s.wnode + 74.0 * s.wtri * (1.0 + 0.6 * (pol.tris_per_step - 1))) / nrays;
+    return s;
+}
+
+static void report_sim(const Wide& w, const std::vector<Tri>& tris, uint32_t nrays, const Policy& pol) {
+    const SimOut s = simulate(w, tris, nrays, pol);
+    printf("%-44s iters/ray %6.2f  nodes/ray %6.2f  tris/ray %5.2f  lanes: live %5.2f node %5.2f tri %5.2f  tri steps/iter %.3f  warp instr/ray %7.1f\n",
+           pol.name, s.lane_iters / nrays, s.nodes / nrays, s.tris / nrays, s.lane_iters / s.warp_iters, s.nodes / std::max(s.wnode, 1.0),
+           s.tris / std::max(s.wtri, 1.0), s.wtri / s.warp_iters, s.cost);
+    fflush(stdout);
+}
+
 static void report(const char* name, Bin& b, const std::vector<Tri>& tris, uint32_t nrays, int quant = 0, int order = 0) {
     Wide w = collapse(b);
     assign_slots(w);
@@ -455,6 +606,21 @@ int main(int argc, char** argv) {
         report("  one exponent, octant order (GPU)", b, tris, nrays, 1, 2);
         report("  octant order + group-min culling", b, tris, nrays, 1, 3);
         report("  octant order + per-child culling", b, tris, nrays, 1, 4);
+        if (argc > 3 && !strcmp(argv[3], "simt")) {
+            Wide w = collapse(b);
+            assign_slots(w);
+            quantise(w, 1);
+            printf("warp-level model of the traversal loop (32 lanes, refill below 30 every 2 iterations):\n");
+            report_sim(w, tris, nrays, Policy{"k_trace: 1 triangle test per iteration"});
+            report_sim(w, tris, nrays, Policy{"triangle step every 2nd iteration", 2, 1, 1});
+            report_sim(w, tris, nrays, Policy{"2 triangle tests per step", 1, 1, 2});
+            report_sim(w, tris, nrays, Policy{"all pending triangles per step", 1, 1, 16});
+            for (int th : {4, 8, 12, 16})
+                { char nm[64]; snprintf(nm, sizeof nm, "step when >= %d lanes pending or one starves", th); report_sim(w, tris, nrays, Policy{nm, 1, th, 1}); }
+            for (int th : {8, 16})
+                { char nm[64]; snprintf(nm, sizeof nm, ">= %d lanes or starving, 2 tests per step", th); report_sim(w, tris, nrays, Policy{nm, 1, th, 2}); }
+            return 0;
+        }
         for (int pass = 1; pass <= 3; ++pass) {
             const int r = rotate_pass(b); refit(b);
             char nm[64]; snprintf(nm, sizeof nm, "+ rotation pass %d (%d rotations)", pass, r);
