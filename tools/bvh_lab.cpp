@@ -433,9 +433,11 @@ struct Policy {
     int tri_every = 1;       // triangle step only every n-th iteration
     int tri_min_lanes = 1;   // ... and only if this many lanes have a triangle pending, or a lane has nothing else to do
     int tris_per_step = 1;
+    int node_steps = 1;      // (pop + node step) repetitions per iteration
+    bool cull_stale = false; // pushed sibling groups carry the minimum entry distance of their members
 };
 struct Ray { float o[3], d[3], inv[3], tmin, tbest; int oct; };
-struct NGroup { int32_t node = -1; uint8_t mask = 0; };   // remaining hit internal children of `node` (bit = child index)
+struct NGroup { int32_t node = -1; uint8_t mask = 0; float bound = -1.f; };   // remaining hit internal children of `node` (bit = child index)
 struct TGroup { uint8_t n = 0; uint32_t tri[16]; };
 struct SEntry { bool is_tri; NGroup g; TGroup t; };
 struct Lane { bool active = false; bool fresh = false; Ray r; NGroup G; TGroup T; std::vector<SEntry> st; };
@@ -488,10 +490,14 @@ static SimOut simulate(const Wide& w, const std::vector<Tri>& tris, uint32_t nra
                 }
                 s.warp_iters += 1;
                 for (auto& l : lane) s.lane_iters += l.active;
+                for (int ns = 0; ns < pol.node_steps; ++ns) {
                 // pop
                 for (auto& l : lane) if (l.active && !l.fresh && !l.G.mask && !l.st.empty()) {
                     SEntry& e = l.st.back();
-                    if (!e.is_tri) { l.G = e.g; l.st.pop_back(); }
+                    if (!e.is_tri) {
+                        l.G = e.g; l.st.pop_back();
+                        if (pol.cull_stale && l.G.bound > l.r.tbest) l.G.mask = 0;  // nothing in the group can be reached any more
+                    }
                     else if (!l.T.n) { l.T = e.t; l.st.pop_back(); }
                 }
                 // node step
@@ -511,6 +517,7 @@ static SimOut simulate(const Wide& w, const std::vector<Tri>& tris, uint32_t nra
                     const Wide::Node& nd = w.nodes[visit];
                     NGroup ng; ng.node = visit;
                     TGroup nt;
+                    float ctn[8];
                     for (int c = nd.n - 1; c >= 0; --c) {
                         float tn = l.r.tmin, tf = l.r.tbest;
                         for (int a = 0; a < 3; ++a) {
@@ -519,8 +526,15 @@ static SimOut simulate(const Wide& w, const std::vector<Tri>& tris, uint32_t nra
                             tn = std::max(tn, t0); tf = std::min(tf, t1);
                         }
                         if (tn > tf) continue;
-                        if (nd.child[c] >= 0) ng.mask |= (uint8_t)(1u << c);
+                        if (nd.child[c] >= 0) { ng.mask |= (uint8_t)(1u << c); ctn[c] = tn; }
                         else for (int k = 0; k < nd.ntri[c]; ++k) nt.tri[nt.n++] = nd.tri[c][k];
+                    }
+                    if (pol.cull_stale && ng.mask) {  // bound of the group that will be pushed: all members but the first visited
+                        int first = -1, bp = -1;
+                        for (int c = 0; c < nd.n; ++c) if (ng.mask >> c & 1) { const int pr = nd.slot[c] ^ l.r.oct; if (pr > bp) { bp = pr; first = c; } }
+                        float m = FLT_MAX;
+                        for (int c = 0; c < nd.n; ++c) if ((ng.mask >> c & 1) && c != first) m = std::min(m, ctn[c]);
+                        ng.bound = m;
                     }
                     l.G = ng;
                     if (nt.n) {
@@ -529,6 +543,7 @@ static SimOut simulate(const Wide& w, const std::vector<Tri>& tris, uint32_t nra
                     }
                 }
                 if (nl) { s.wnode += 1; s.nodes += nl; }
+                }
                 // triangle step
                 int pending = 0; bool starving = false;
                 for (auto& l : lane) if (l.active && l.T.n) { ++pending; if (!l.G.mask) starving = true; }
@@ -558,7 +573,8 @@ static SimOut simulate(const Wide& w, const std::vector<Tri>& tris, uint32_t nra
     for (auto& x : th) x.join();
     SimOut s;
     for (auto& p : part) { s.warp_iters += p.warp_iters; s.lane_iters += p.lane_iters; s.wnode += p.wnode; s.wtri += p.wtri; s.nodes += p.nodes; s.tris += p.tris; }
-    s.cost = (63.0 * s.warp_iters + 240.0 * s.wnode + 74.0 * s.wtri * (1.0 + 0.6 * (pol.tris_per_step - 1))) / nrays;
+    s.cost = ((63.0 + 22.0 * (pol.node_steps - 1)) * s.warp_iters + (240.0 + (pol.cull_stale ? 16.0 : 0.0)) * s.wnode +
+              74.0 * s.wtri * (1.0 + 0.6 * (pol.tris_per_step - 1))) / nrays;
     return s;
 }
 
@@ -615,9 +631,14 @@ int main(int argc, char** argv) {
             report_sim(w, tris, nrays, Policy{"triangle step every 2nd iteration", 2, 1, 1});
             report_sim(w, tris, nrays, Policy{"2 triangle tests per step", 1, 1, 2});
             report_sim(w, tris, nrays, Policy{"all pending triangles per step", 1, 1, 16});
-            for (int th : {4, 8, 12, 16})
+            report_sim(w, tris, nrays, Policy{"2 node steps per iteration", 1, 1, 1, 2});
+            report_sim(w, tris, nrays, Policy{"3 node steps per iteration", 1, 1, 1, 3});
+            report_sim(w, tris, nrays, Policy{"2 node steps, 2 triangle tests", 1, 1, 2, 2});
+            report_sim(w, tris, nrays, Policy{"stale groups culled (+16 instr per node step)", 1, 1, 1, 1, true});
+            report_sim(w, tris, nrays, Policy{"2 node steps + stale groups culled", 1, 1, 1, 2, true});
+            for (int th : {8})
                 { char nm[64]; snprintf(nm, sizeof nm, "step when >= %d lanes pending or one starves", th); report_sim(w, tris, nrays, Policy{nm, 1, th, 1}); }
-            for (int th : {8, 16})
+            for (int th : {8})
                 { char nm[64]; snprintf(nm, sizeof nm, ">= %d lanes or starving, 2 tests per step", th); report_sim(w, tris, nrays, Policy{nm, 1, th, 2}); }
             return 0;
         }
