@@ -17,7 +17,6 @@ read-back inside the timed region); `roofline` describes the traversal kernel; `
 host cores on a bounded sample of the same workload. Only the cpu_baseline / --impl reference legs touch oracle/.
 """
 import argparse
-import ctypes
 import importlib
 import json
 import os
