@@ -5,17 +5,22 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, as the checker
 // or the reported CPU baseline — never as the thing measured as "ours" or shipped.
 //
-// PARITY STATUS: *partially pinned*.
+// PARITY STATUS: pinned against the reference's own sources, except the driver's traversal.
 //   - The integer RNG (pcg, pcg2d, seed, rand) is pinned by KAT-1, derived
 //     independently from shaders/common.glsl and re-derived in tests/test_oracle_kat.py.
 //   - The scene input (loader semantics, main.cpp:28-58) is pinned by running the reference's
 //     own vendored tinyobjloader (oracle/_ref, built from /root/reference where it lies) and
 //     committing its output as tests/golden/cornell_scene.json.
-//   - The rendered pixels are PARITY UNPINNED: the reference has no tests, no golden images
-//     and no CPU path, and its Vulkan RT build cannot run in this image (no Vulkan headers,
-//     loader, ICD or glslc). The driver's BVH traversal / triangle test is
-//     closed source. This file restates the shader text; no reference output exists to check
-//     the restatement against.
+//   - Everything the shader text states (seed, camera, sampling, closest-hit, miss, path update,
+//     sample mean, running mean in float and rgba8) is pinned BIT FOR BIT against the reference's
+//     own shader text compiled as C++ (oracle/_ref/libref_shade.so: shaders/*.glsl|rgen|rchit|rmiss
+//     read where they lie, through the mechanical transform oracle/glsl_to_cpp.py, under
+//     oracle/glsl_shim.h); tests/test_ref_shade.py compares live in the build container and
+//     against the committed golden images tests/golden/ref_shade_*.npz everywhere else.
+//   - PARITY UNPINNED, and unpinnable here: the driver's BVH traversal / triangle test behind
+//     traceRayEXT (closed source; the Vulkan RT build cannot run in this image).
+//     Its contract (closest opaque hit in [tmin,tmax], no culling, barycentrics of v1,v2) is what
+//     both sides implement; the shader-text library is given this file's intersector.
 //
 // What follows which reference lines (paths relative to the reference checkout):
 //   pcg / pcg2d / rand            shaders/common.glsl:13-19, 21-31, 33-37
@@ -548,6 +553,22 @@ void orc_intersect(void* scene, const float* rays, uint32_t n, int precision, in
     for (int i = 1; i < nthreads; ++i) th.emplace_back(worker);
     worker();
     for (auto& t : th) t.join();
+}
+
+// The oracle's f32 intersector with the callback contract of oracle/glsl_shim.h (ref_intersect_fn): lets the
+// reference's compiled shader text (oracle/_ref/libref_shade.so) trace through the oracle's BVH, so that the two
+// renders of a big scene differ only where this restatement of the shader text differs from the text.
+// user = the scene handle; bit 0 of the handle's alignment is free, so brute force is selected by orc_intersect_cb_brute.
+struct RefHitOut { float t, u, v; uint32_t prim; };
+void orc_intersect_cb(void* scene, const float* o, float tmin, const float* d, float tmax, RefHitOut* out) {
+    const Scene& s = *static_cast<Scene*>(scene);
+    HitR<float> h = intersect<float>(s, {o[0], o[1], o[2]}, {d[0], d[1], d[2]}, tmin, tmax, false);
+    *out = {h.t, h.u, h.v, h.prim};
+}
+void orc_intersect_cb_brute(void* scene, const float* o, float tmin, const float* d, float tmax, RefHitOut* out) {
+    const Scene& s = *static_cast<Scene*>(scene);
+    HitR<float> h = intersect<float>(s, {o[0], o[1], o[2]}, {d[0], d[1], d[2]}, tmin, tmax, true);
+    *out = {h.t, h.u, h.v, h.prim};
 }
 
 // One shade step for n paths in f32 (stage-level parity of the shade kernel).

@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB_PATH = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
 REF_LOADER_PATH = os.path.join(ORACLE_DIR, "_ref", "libref_loader.so")
+REF_SHADE_PATH = os.path.join(ORACLE_DIR, "_ref", "libref_shade.so")
 MISS = 0xFFFFFFFF
 
 
@@ -50,7 +51,7 @@ def build(force=False):
     if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(
             os.path.join(ORACLE_DIR, "oracle.cpp")):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
-    if os.path.isdir("/root/reference") and not os.path.exists(REF_LOADER_PATH):
+    if os.path.isdir("/root/reference") and not (os.path.exists(REF_LOADER_PATH) and os.path.exists(REF_SHADE_PATH)):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "_ref"])
 
 
@@ -76,6 +77,8 @@ def lib():
         L.orc_generate_rays.restype = None; L.orc_generate_rays.argtypes = [C.POINTER(OrcParams), C.c_uint32, vp, vp]
         L.orc_intersect.restype = None
         L.orc_intersect.argtypes = [vp, vp, C.c_uint32, C.c_int, C.c_int, C.c_int, vp]
+        for name in ("orc_intersect_cb", "orc_intersect_cb_brute"):
+            getattr(L, name).restype = None
         L.orc_shade.restype = None
         L.orc_shade.argtypes = [vp, C.POINTER(OrcParams), vp, vp, vp, C.c_uint32, vp, vp, vp, vp, vp]
         L.orc_soup.restype = None; L.orc_soup.argtypes = [C.c_uint32, C.c_uint32, C.c_float, vp, vp, vp]
@@ -195,3 +198,50 @@ def ref_load_obj(obj_path, mtl_dir):
                         C.byref(ni), C.byref(nf), shape_tris, C.byref(ns), err, 1024)
     assert rc == 0
     return verts, idx, faces, list(shape_tris[:ns.value])
+
+
+# ------------------------------------------------------------------------------------------ the reference's shader text
+_ref_shade = None
+
+
+def ref_shade_available():
+    return os.path.exists(REF_SHADE_PATH)
+
+
+def ref_shade_lib():
+    """oracle/_ref/libref_shade.so: the reference's shaders/*.glsl|rgen|rchit|rmiss compiled as C++ (oracle/glsl_shim.h)."""
+    global _ref_shade
+    if _ref_shade is None:
+        build()
+        L = C.CDLL(REF_SHADE_PATH)
+        vp = C.c_void_p
+        L.ref_shade_render.restype = C.c_uint64
+        L.ref_shade_render.argtypes = ([vp, vp, C.c_uint32, vp] + [C.c_uint32] * 4 + [C.c_int] * 4 + [vp, vp, C.c_int, vp])
+        L.ref_pcg.restype = C.c_uint32; L.ref_pcg.argtypes = [C.POINTER(C.c_uint32)]
+        L.ref_pcg2d.restype = None; L.ref_pcg2d.argtypes = [C.POINTER(C.c_uint32)] * 2
+        L.ref_rand.restype = C.c_float; L.ref_rand.argtypes = [C.POINTER(C.c_uint32)]
+        L.ref_sample_direction.restype = None; L.ref_sample_direction.argtypes = [C.c_float, C.c_float, vp, vp]
+        _ref_shade = L
+    return _ref_shade
+
+
+def ref_shade_render(verts, indices, faces, width, height, frames=1, spp=0, depth=0, rgba8=False, rows=(0, 0),
+                     scene=None, brute=True, nthreads=0, image=None, first_frame=0):
+    """`frames` launches traceRaysKHR(width, height, 1) of the reference's shader text with push constant frame =
+    first_frame.. over one storage image. spp / depth = 0 keep the literals of the text (32 / 8). scene: an oracle
+    Scene whose intersector answers traceRayEXT (brute force or its BVH); None = the library's own brute force."""
+    L = ref_shade_lib()
+    verts = np.ascontiguousarray(verts, np.float32)
+    indices = np.ascontiguousarray(indices, np.uint32)
+    faces = np.ascontiguousarray(faces, np.float32)
+    if image is None:
+        image = np.zeros((height, width, 4), np.float32)
+    fn, user = None, None
+    if scene is not None:
+        fn = C.cast(lib().orc_intersect_cb_brute if brute else lib().orc_intersect_cb, C.c_void_p)
+        user = scene.h
+    rays = 0
+    for f in range(first_frame, first_frame + frames):
+        rays += L.ref_shade_render(_ptr(verts), _ptr(indices), len(indices), _ptr(faces), width, height, rows[0], rows[1], f,
+                                   spp, depth, int(rgba8), fn, user, nthreads, _ptr(image))
+    return image, int(rays)
