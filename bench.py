@@ -13,10 +13,15 @@ after the last step, inside the timed region.
 
 One JSON line on stdout (rank 0). `value` is whole-job Mray/s with everything resident in HBM; `e2e` is the same
 metric through the public API with host buffers (mesh upload from pinned host memory + build + per-step image
-read-back inside the timed region); `roofline` describes the traversal kernel; `cpu_baseline` is the oracle on the
-host cores on a bounded sample of the same workload. Only the cpu_baseline / --impl reference legs touch oracle/.
+read-back inside the timed region, the read-back of frame f overlapping the trace of frame f+1 as a present loop
+would run it); `roofline` describes the traversal kernel: what binds it (instruction issue, by ncu), its DRAM floor
+against the measured HBM peak, and — only when profiles/k_trace_traffic.json holds an ncu capture of THIS csrc/ and
+workload — the measured DRAM traffic; `cpu_baseline` is the oracle on the host cores on a bounded sample of the same
+workload. Only the cpu_baseline / --impl reference legs touch oracle/. With N > 1 the gathered image is verified
+against a single-tile re-render after the timed regions (`allgather_verified`).
 """
 import argparse
+import hashlib
 import importlib
 import json
 import os
@@ -24,6 +29,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 
 import numpy as np
 
@@ -127,6 +133,16 @@ class Dist:
         t = self._tensor([float(x)], torch.float64)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return float(t.item())
+
+    def gather_floats(self, x):
+        """[x of rank 0, x of rank 1, ...] on every rank."""
+        if not self.active:
+            return [float(x)]
+        import torch
+        t = self._tensor([float(x)], torch.float64)
+        out = [torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
 
     def broadcast_bytes(self, data, nbytes):
         """rank 0's `data` (bytes of length nbytes) to everyone."""
@@ -244,28 +260,41 @@ def cpu_sample_params(O, w, frame):
 
 
 def cpu_baseline(w, steps=1, warmup=0):
-    """Oracle on all host cores over a bounded sample: CPU_SAMPLE_ROWS rows x full width x CPU_SAMPLE_SPP spp per step."""
+    """The reference's algorithm on all host cores over a bounded sample: CPU_SAMPLE_ROWS rows x full width x
+    CPU_SAMPLE_SPP spp per step. kind "reference": the reference's OWN shader text compiled as C++
+    (oracle/_ref/libref_shade.so, built from /root/reference/shaders where they lie) does everything the reference's
+    source states; traceRayEXT — the driver's closed-source traversal — is answered by the oracle's BVH. Workloads the
+    shader text cannot express (another camera, instance transforms: SURVEY T11/T12) and boxes without that library
+    run the oracle's restatement instead (kind "port")."""
     O, scene = oracle_scene(w)
     cores = int(O.lib().orc_hardware_threads())
     img = np.zeros((w["height"], w["width"], 4), np.float32)
+    use_text = O.ref_shade_available() and not w.get("instances") and "cam_origin" not in w
     rays_total, secs = 0, 0.0
     for s in range(warmup + steps):
         p, rows = cpu_sample_params(O, w, s)
         t0 = time.perf_counter()
-        _, rays = scene.render(p, 32, nthreads=cores, image=img)
+        if use_text:
+            _, rays = O.ref_shade_render(scene.verts, scene.indices, scene.faces, w["width"], w["height"], 1, CPU_SAMPLE_SPP,
+                                         w["depth"], False, (0, 0), scene, False, cores, img, s, w["height"] // rows)
+        else:
+            _, rays = scene.render(p, 32, nthreads=cores, image=img)
         dt = time.perf_counter() - t0
         if s >= warmup:
             rays_total += rays
             secs += dt
-    return {"value": rays_total / secs / 1e6, "unit": METRIC, "cores": cores, "kind": "port",
+    return {"value": rays_total / secs / 1e6, "unit": METRIC, "cores": cores, "kind": "reference" if use_text else "port",
             "sample": f"{rows} rows spread uniformly over the {w['width']}x{w['height']} image x {CPU_SAMPLE_SPP} spp x depth "
-                      f"{w['depth']} per step, {steps} step(s): {rays_total} rays in {secs:.2f} s (oracle's own median-split BVH)"}, \
+                      f"{w['depth']} per step, {steps} step(s): {rays_total} rays in {secs:.2f} s ("
+                      + ("the reference's shader text compiled as C++, traceRayEXT answered by the oracle's median-split BVH)"
+                         if use_text else "oracle's restatement, own median-split BVH)")}, \
         rays_total, secs
 
 
 def run_reference(args):
     """--impl reference: the reference has no CPU path and its Vulkan build cannot run in this image, so this arm
-    times the CPU restatement of its algorithm (oracle/) on the host cores; rank 0 only."""
+    times the reference's shader text compiled as C++ over the oracle's BVH (cpu_baseline above; the oracle's
+    restatement where the text cannot express the workload) on the host cores; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -283,6 +312,71 @@ def run_reference(args):
     _RESULT_LINE.append(json.dumps(out))
 
 
+# ------------------------------------------------------------------------------------------ ncu evidence
+def csrc_hash():
+    """sha256 over the CUDA sources the library is built from: an ncu capture describes THIS code or it is not used."""
+    d = os.path.join(ROOT, "single-file-vulkan-pathtracing_b200", "csrc")
+    h = hashlib.sha256()
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".cpp", ".h")):
+            h.update(name.encode())
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_capture(workload, n_gpus):
+    """The k_trace entry of profiles/k_trace_traffic.json (written by profiles/summarize.py traffic from an ncu capture
+    of `bench.py --workload W`, all bounces of a frame) for this workload, GPU count and csrc hash, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k_trace_traffic.json")) as f:
+            entries = json.load(f)
+    except (OSError, ValueError):
+        return None
+    for e in entries:
+        if e.get("workload") == workload and int(e.get("n_gpus", 1)) == n_gpus and e.get("csrc_hash") == csrc_hash():
+            return e
+    return None
+
+
+def verify_allgather(bpt, pt, d, w, params, tile, build_scene, stream):
+    """N > 1: the image NCCL assembled must be the single-GPU image. Two frames are rendered tiled and all-gathered;
+    every rank checksums the full image (all ranks must hold the same bytes), and rank 0 re-renders, on a second
+    context as ordinary contiguous tiles, eight row blocks that belong to OTHER ranks and compares them bit for bit."""
+    W, H = w["width"], w["height"]
+    pt.clear_image()
+    for f in range(2):
+        pt.trace(params(f))
+    pt.allgather_image(W, H)
+    img = pt.read_image(W, H)
+    crc = float(zlib.crc32(img.tobytes()))
+    crcs = d.gather_floats(crc)
+    ok = len(set(crcs)) == 1
+    detail = {"crc_equal_on_all_ranks": ok, "rows_checked": 0}
+    if d.rank == 0:
+        block = tile["tile_block"]
+        nblocks = H // block
+        # row blocks of the other ranks, spread over the image
+        cand = [b for b in range(nblocks) if b % d.world != 0]
+        pick = [cand[i * len(cand) // 8] for i in range(8)] if len(cand) >= 8 else cand
+        pt2 = bpt.PathTracer(d.local_rank, stream.cuda_stream)
+        build_scene(pt2)
+        same = True
+        for b in pick:
+            pt2.clear_image()
+            for f in range(2):
+                pt2.trace(bpt.default_params(W, H, w["spp"], w["depth"], f, tile_y0=b * block, tile_rows=block, **camera_kwargs(w)))
+            part = pt2.read_image(W, H)[b * block:(b + 1) * block]
+            same = same and bool(np.array_equal(part, img[b * block:(b + 1) * block]))
+            detail["rows_checked"] += block
+        pt2.close()
+        detail["foreign_rows_bit_identical"] = same
+        ok = ok and same
+    ok = d.max(0.0 if ok else 1.0) == 0.0
+    pt.clear_image()
+    return ok, detail
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -297,6 +391,10 @@ def run_ours(args):
     for o in args.opt:
         k, v = o.split("=")
         pt.set_option(int(k), int(v))
+    lanes = 2
+    for o in args.opt:
+        if o.split("=")[0] == str(bpt.OPT_STREAMS):
+            lanes = int(o.split("=")[1])
     W, H, K, WU = w["width"], w["height"], args.steps, args.warmup
     tile = tile_kwargs(H, d.world, d.rank)
 
@@ -304,16 +402,18 @@ def run_ours(args):
         return bpt.default_params(W, H, w["spp"], w["depth"], frame, **tile, **camera_kwargs(w))
 
     # ---- scene + build (once per job; reported, not part of `value`)
-    if w["tris"]:
-        pt.upload_soup(w["tris"], w["seed"])
-    else:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import oracle_lib as O  # fixture loader only (tests/golden/cornell_scene.json)
-        verts, idx, faces, _ = O.load_cornell_golden()
-        pt.upload_mesh(verts, idx, faces)
-        if w.get("instances"):
-            pt.set_instances(instance_grid(w["instances"]))
-    info = pt.build_accel()
+    def build_scene(t):
+        if w["tris"]:
+            t.upload_soup(w["tris"], w["seed"])
+        else:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib as O  # fixture loader only (tests/golden/cornell_scene.json)
+            verts, idx, faces, _ = O.load_cornell_golden()
+            t.upload_mesh(verts, idx, faces)
+            if w.get("instances"):
+                t.set_instances(instance_grid(w["instances"]))
+        return t.build_accel()
+    info = build_scene(pt)
     build_ms = pt.stats().build_ms
     if d.active:
         uid = d.broadcast_bytes(bpt.PathTracer.nccl_unique_id() if d.rank == 0 else b"", bpt.NCCL_UNIQUE_ID_BYTES)
@@ -326,7 +426,6 @@ def run_ours(args):
     if d.active:
         pt.allgather_image(W, H)
     pt.sync()
-    pt.set_option(bpt.OPT_PROFILE, 1)   # two CUDA events around every traversal launch
     pt.reset_stats()
     clocks = ClockSampler(d.local_rank) if d.rank == 0 else None
     time.sleep(0.3 if clocks else 0.0)
@@ -346,14 +445,31 @@ def run_ours(args):
     st = pt.stats()
     # the slowest and the fastest rank's own frames (all-gather excluded): a gap between them is rank imbalance or a
     # slow GPU, not the sharding (every rank gets the same rows modulo 8-row blocks)
-    rank_frames_ms = {"min": -d.max(-st.frame_ms), "max": d.max(st.frame_ms)}
+    rank_frames_ms = d.gather_floats(st.frame_ms)
+    rank_region_ms = d.gather_floats(ms_own)
     if os.environ.get("BPT_BENCH_DEBUG"):
-        print(f"[rank {d.rank}] timed region {ms_own:.2f} ms, traversal kernels {st.trace_kernel_ms:.2f} ms, "
-              f"frames {st.frame_ms:.2f} ms, rays {st.rays_traced}", file=sys.stderr, flush=True)
+        print(f"[rank {d.rank}] timed region {ms_own:.2f} ms, frames {st.frame_ms:.2f} ms, rays {st.rays_traced}",
+              file=sys.stderr, flush=True)
     clk = clocks.stop(t0, t1) if clocks else None
     rays = d.sum(st.rays_traced)
     paths = d.sum(st.paths)
     value = rays / (ms * 1e-3) / 1e6
+    kernel_launches = int(st.kernel_launches)
+
+    # ---- per-kernel timing of the traversal kernel: the same K frames again with ONE sample lane, two CUDA events
+    # around every traversal launch on its stream (with several lanes in flight the kernels of different lanes share
+    # the SMs and an event pair around one of them also counts the time it waits for the others)
+    pt.set_option(bpt.OPT_STREAMS, 1)
+    pt.set_option(bpt.OPT_PROFILE, 1)
+    pt.reset_stats()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record(stream)
+    for _ in range(K):
+        pt.trace(params(frame)); frame += 1
+    k1.record(stream)
+    torch.cuda.synchronize()
+    st = pt.stats()
+    single_lane_ms = k0.elapsed_time(k1)
 
     # ---- traversal-kernel roofline (rank 0's kernel): per-ray node/triangle fetch counts from one instrumented frame
     pt.set_option(bpt.OPT_PROFILE, 0)
@@ -362,40 +478,57 @@ def run_ours(args):
     pt.trace(params(frame)); frame += 1
     sc = pt.stats()
     pt.set_option(bpt.OPT_COUNT_TRAVERSAL, 0)
+    pt.set_option(bpt.OPT_STREAMS, lanes)
     nodes_per_ray = sc.nodes_visited / max(sc.rays_traced, 1)
     tris_per_ray = sc.tris_tested / max(sc.rays_traced, 1)
-    # algorithmic bytes: 32 B ray + 16 B hit + one 64 B record per node visited and per triangle tested
-    # (the triangle record's second half is only read when the ray reaches the triangle's plane; counted in full)
-    bytes_per_ray = 48.0 + 64.0 * nodes_per_ray + 64.0 * tris_per_ray
-    requested_per_ray = bytes_per_ray
+    # Requested bytes (SURVEY 8d "modelled"): 32 B ray + 16 B hit + one 64 B record per node visited and per triangle
+    # tested. Almost all of them are served by L1/L2 (ncu: L2 hit rate 83-90 %), so this is NOT DRAM traffic and is
+    # reported under its own name only.
+    requested_per_ray = 48.0 + 64.0 * nodes_per_ray + 64.0 * tris_per_ray
     launches = max(st.trace_launches, 1)
     avg_launch_ms = st.trace_kernel_ms / launches
-    achieved = bytes_per_ray * st.rays_traced / max(st.trace_kernel_ms * 1e-3, 1e-12) / 1e9
+    kernel_s = max(st.trace_kernel_ms * 1e-3, 1e-12)
+    rays_per_launch = st.rays_traced / launches
+    # Algorithmic DRAM bytes of one launch (the floor): every ray record read and every hit record written once
+    # (48 B per ray), and every acceleration-structure record the launch touches fetched from DRAM once — at most the
+    # whole record array, at most one record per visit.
+    bvh_bytes = float(info.bytes_nodes + info.bytes_tris)
+    algo_per_launch = 48.0 * rays_per_launch + min(bvh_bytes, 64.0 * (nodes_per_ray + tris_per_ray) * rays_per_launch)
+    achieved = algo_per_launch / max(avg_launch_ms * 1e-3, 1e-12) / 1e9
     peak, peak_src = 6650.0, "fallback"
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except (OSError, KeyError, ValueError):
         pass
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "trace_kernel_traffic.json")) as f:
-            tj = json.load(f)
-        if tj.get("workload") == w["name"]:
-            traffic = tj.get("dram_bytes_per_launch")
-    except (OSError, ValueError):
-        pass
-    roofline = {"kernel": "k_trace (persistent BVH8 traversal)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_ray": bytes_per_ray, "requested_bytes_per_ray": requested_per_ray,
-                "compulsory_bytes_per_ray": 48.0,
-                "compulsory_frac": 48.0 * st.rays_traced / max(st.trace_kernel_ms * 1e-3, 1e-12) / 1e9 / peak,
+    cap = ncu_capture(w["name"], d.world)
+    traffic = cap["dram_bytes_per_launch"] if cap else None
+    roofline = {"kernel": "k_trace (persistent BVH8 traversal)",
+                # what binds the kernel by ncu (profiles/*_k_trace_ncu_*.txt): instruction issue and the ALU pipe; DRAM
+                # throughput is a few per cent of peak. `achieved`/`frac` are the kernel's algorithmic DRAM bytes per
+                # launch over its measured duration against the measured HBM peak: far below 1 because the kernel is
+                # not an HBM-bound kernel on this machine (the hot top of the BVH lives in the 126 MB L2).
+                "bound": "issue", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_per_launch, "compulsory_bytes_per_ray": 48.0,
+                "hbm_frac_ncu": (traffic / max(avg_launch_ms * 1e-3, 1e-12) / 1e9 / peak) if traffic else None,
+                "issue_frac": cap.get("issue_active_frac") if cap else None,
+                "alu_pipe_frac": cap.get("alu_pipe_frac") if cap else None,
+                "l2_hit_rate": cap.get("l2_hit_rate") if cap else None,
+                "ncu_capture": ({"file": cap.get("source"), "csrc_hash": cap.get("csrc_hash"), "launches": cap.get("launches")}
+                                if cap else f"no capture of csrc {csrc_hash()} / {w['name']} / {d.world} GPU(s) under profiles/"),
+                "requested_bytes_per_ray": requested_per_ray,
+                "requested_frac": requested_per_ray * st.rays_traced / kernel_s / 1e9 / peak,
                 "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
                 "lanes_per_node_step": sc.nodes_visited / max(sc.warp_node_steps, 1),
                 "lanes_per_tri_step": sc.tris_tested / max(sc.warp_tri_steps, 1), "avg_launch_ms": avg_launch_ms,
-                "launches": int(st.trace_launches), "rays_per_launch": st.rays_traced / launches,
-                "trace_share_of_step": st.trace_kernel_ms / max(e0.elapsed_time(e1), 1e-9)}
-    ranks = {"frames_ms_min": rank_frames_ms["min"], "frames_ms_max": rank_frames_ms["max"], "timed_region_ms": ms}
+                "launches": int(st.trace_launches), "rays_per_launch": rays_per_launch,
+                "mrays_trace_kernel": st.rays_traced / kernel_s / 1e6,
+                "timing": "K frames with one sample lane, CUDA events around every launch on its stream",
+                "trace_share_of_step": st.trace_kernel_ms / max(single_lane_ms, 1e-9),
+                "ms_per_step_single_lane": single_lane_ms / K}
+    ranks = {"frames_ms": rank_frames_ms, "timed_region_ms": rank_region_ms,
+             "frames_ms_min": min(rank_frames_ms), "frames_ms_max": max(rank_frames_ms)}
 
     # ---- end to end through the public API with host buffers
     e2e = None
@@ -417,15 +550,20 @@ def run_ours(args):
             pt.set_instances(instance_grid(w["instances"]))
         pt.build_accel()
         if dbg: print(f"[rank {d.rank}] +build {1e3 * (time.perf_counter() - tw0):.1f} ms", file=sys.stderr, flush=True)
+        himg2 = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+        host_frames = [himg_np, himg2.numpy()]
         for s in range(K):
             pt.trace(params(s))
             if d.active:
                 pt.allgather_image(W, H)
             if d.rank == 0:
-                pt.read_image(W, H, out=himg_np)     # D2H: the frame the reference would present (one presenter)
-            else:
-                pt.sync()
+                # D2H of the frame the reference would present (one presenter), double-buffered: the copy of frame s runs
+                # on the copy stream while frame s+1 is traced; the host only waits for the copy of frame s-1
+                pt.read_wait()
+                pt.read_image_async(host_frames[s & 1])
             if dbg: print(f"[rank {d.rank}] +step {s} {1e3 * (time.perf_counter() - tw0):.1f} ms", file=sys.stderr, flush=True)
+        pt.read_wait()
+        pt.sync()
         e1.record(stream)
         torch.cuda.synchronize(); d.barrier()
         tw1 = time.perf_counter()
@@ -434,9 +572,14 @@ def run_ours(args):
         e2e = {"value": d.sum(s2.rays_traced) / (ems * 1e-3) / 1e6, "unit": METRIC,
                "h2d_bytes_per_step": int(nt * 72 / K), "d2h_bytes_per_step": int(W * H * 16),
                "includes": f"mesh upload from pinned host memory + BVH build (once, amortised over {K} steps) + per-step "
-                           "bpt_trace" + (" + all-gather" if d.active else "") + " + full-image read-back to pinned host memory"
+                           "bpt_trace" + (" + all-gather" if d.active else "") + " + full-image read-back to pinned host memory (double-buffered, "
+                           "overlapping the next step's trace)"
                            + (" on rank 0 (the presenter)" if d.active else ""),
                "ms_total": ems}
+
+    verified, vdetail = None, None
+    if d.active:
+        verified, vdetail = verify_allgather(bpt, pt, d, w, params, tile, build_scene, stream)
 
     cpu = None
     if d.rank == 0 and d.world == 1 and not args.no_cpu_baseline:
@@ -448,13 +591,15 @@ def run_ours(args):
                "data": "synthetic", "ranks": ranks,
                "config": {"workload": w["name"], "baseline_config": w["config"], "tris": info.num_tris, "instances": info.num_instances, "width": W, "height": H,
                           "spp_per_step": w["spp"], "depth": w["depth"], "sampler": "uniform hemisphere (reference)",
+                          "sample_lanes": lanes,
                           "tiling": (f"{tile['tile_block']}-row blocks round-robin over {d.world} GPUs + 1 NCCL all-gather"
                                      if tile else "single tile"),
                           "l2": "working set per step (path queues + BVH) is far larger than the 126 MB L2; no flush needed",
                           "bvh8_nodes": info.num_nodes8, "bvh_bytes": int(info.bytes_nodes + info.bytes_tris),
                           **({"options": args.opt} if args.opt else {})},
                "samples_per_s": paths / (ms * 1e-3), "rays": int(rays), "paths": int(paths), "build_ms": build_ms,
-               "gpu_launches": int(st.kernel_launches), "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
+               "gpu_launches": kernel_launches, "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+               **({"allgather_verified": verified, "allgather_check": vdetail} if d.active else {})}
         _RESULT_LINE.append(json.dumps(out))
     pt.close()
     d.close()

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BPT_ABI_VERSION 1
+#define BPT_ABI_VERSION 2
 
 /* error codes */
 #define BPT_OK            0
@@ -124,8 +124,9 @@ typedef struct bpt_accel_info {
 #define BPT_OPT_COUNT_TRAVERSAL  2 /* 1: use the instrumented traversal kernel (nodes/tris)  */
 #define BPT_OPT_SMEM_TOP_NODES   3 /* stage the whole BVH in shared memory (TMA) when it has at most
                                       this many nodes and fits (0 = never stage)             */
-#define BPT_OPT_TRACE_CTAS_PER_SM 4 /* persistent grid = 148 * this                          */
-#define BPT_OPT_SORT_RAYS        5 /* reserved                                               */
+#define BPT_OPT_STREAMS          4 /* sample lanes per pass (1..4, default 2): the samples of a pass are split into this many
+                                      independent wavefronts on their own CUDA streams, so the tail of one lane's persistent
+                                      traversal launch is filled by the other lanes' kernels; results do not depend on it */
 #define BPT_OPT_USE_GRAPH        6 /* 1: capture a frame's launch list as a CUDA graph and replay it while only the
                                       frame index changes (pays off for launch-bound, small frames)             */
 #define BPT_OPT_PASS_PATHS       10 /* target paths per sample pass: a pass carries min(spp, this / tile pixels)
@@ -176,7 +177,9 @@ int bpt_upload_soup(bpt_context* ctx, uint32_t ntris, uint32_t seed);
 
 /* ---- build: replaces Accel(...) -> buildAccelerationStructuresKHR (main.cpp:416-450,
  *      called for the BLAS at :512 and the TLAS at :538). The mesh level is rebuilt only after a new mesh was
- *      uploaded; bpt_set_instances + bpt_build_accel rebuilds the instance level alone (moving instances). */
+ *      uploaded; bpt_set_instances + bpt_build_accel rebuilds the instance level alone (moving instances).
+ *      Like the reference's build (oneTimeSubmit + queue.waitIdle, main.cpp:224-238) the call returns when the
+ *      structure is complete: the host reads the scene bounds and the per-level node counts back. */
 int bpt_build_accel(bpt_context* ctx);
 int bpt_accel_info_get(bpt_context* ctx, bpt_accel_info* out);
 
@@ -194,6 +197,14 @@ int bpt_sync(bpt_context* ctx);
 int bpt_read_image(bpt_context* ctx, float* rgba, size_t nfloats);
 /* BGRA8 view as the reference's B8G8R8A8Unorm image would hold it (main.cpp:483). Syncs. */
 int bpt_read_image_bgra8(bpt_context* ctx, uint8_t* bgra, size_t nbytes);
+/* Present path without a stall (main.cpp:661-683 copies the image to the swapchain and then waits for the queue;
+ * here the copy of frame f overlaps the trace of frame f+1): enqueues a device->host copy of the image as it is after
+ * everything enqueued so far, on a copy stream of the context. The next bpt_trace may be enqueued at once; the kernel
+ * that writes the image again (and bpt_allgather_image) waits for the copy on the device. `rgba` / `bgra` must stay valid
+ * (and should be pinned) until bpt_read_wait returns. One copy may be pending per context. */
+int bpt_read_image_async(bpt_context* ctx, float* rgba, size_t nfloats);
+int bpt_read_image_bgra8_async(bpt_context* ctx, uint8_t* bgra, size_t nbytes);
+int bpt_read_wait(bpt_context* ctx); /* host-visible completion of the pending copy (no-op if none) */
 /* device pointer of the float4 image (valid until the next resize); for interop/present. */
 int bpt_image_device_ptr(bpt_context* ctx, void** dptr, size_t* nbytes);
 /* zero the image and restart accumulation (a fresh outputImage). */
@@ -208,6 +219,16 @@ int bpt_reset_stats(bpt_context* ctx);
  * hits : n records of 4 words  {t, u, v, prim}; prim = 0xffffffff on miss; for
  *        multi-instance scenes prim = instance * ntris + primitive. */
 int bpt_trace_rays(bpt_context* ctx, const float* rays, uint32_t n, void* hits);
+/* One closest-hit / miss + path-update step for n paths, alone (closesthit.rchit:50-65, miss.rmiss:8-12,
+ * raygen.rgen:76-83): the stage-level view of the shade kernel, for parity tests. Host arrays:
+ *   in : rays n*8 (as above), hits n*4 words (only t and prim are read: u, v are re-derived from the original
+ *        vertices as the frame loop does), weight n*3, seed n
+ *   out: contrib n*3 (= weight * emission or weight * sky: what raygen.rgen:76 adds to `color`), new_rays n*8,
+ *        new_weight n*3, new_seed n, alive n bytes (0: the path ended on a miss; its other outputs are zero)
+ * p supplies sky, tmin, tmax and the sampler; the next segment is always sampled (as raygen.rgen:78-80 does). */
+int bpt_shade_step(bpt_context* ctx, const bpt_params* p, uint32_t n, const float* rays, const void* hits,
+                   const float* weight, const uint32_t* seed, float* contrib, float* new_rays, float* new_weight,
+                   uint32_t* new_seed, uint8_t* alive);
 /* primary rays + seeds of sample `sample_in_frame` for the tile in p
  * (raygen.rgen:47-57). rays: tile_pixels*8 floats, seeds: tile_pixels uint32 (post-jitter
  * RNG state). */
@@ -240,7 +261,8 @@ int bpt_nccl_init(bpt_context* ctx, const uint8_t id[BPT_NCCL_UNIQUE_ID_BYTES],
  * interleaved split of bpt_params.tile_block with tile_nranks == nranks, tile_rank == rank
  * (the tiling of the last bpt_trace decides). */
 int bpt_allgather_image(bpt_context* ctx, uint32_t width, uint32_t height);
-/* contiguous row split used by every caller: rank r gets rows [y0, y0+rows). */
+/* contiguous row split used by every caller: rank r gets rows [y0, y0+rows), height / nranks each; the last rank
+ * also takes the height % nranks remaining rows (bpt_allgather_image needs an even split and says so). */
 void bpt_tile_rows(uint32_t height, int rank, int nranks, uint32_t* y0, uint32_t* rows);
 
 #ifdef __cplusplus

@@ -104,11 +104,13 @@ extern "C" {
 
 // One vkCmdTraceRaysKHR(width, height, 1) (main.cpp:659) with push constant `frame` over the storage image `image`
 // (width*height*4 floats, read-modify-write; rgba8 != 0: the reference's unorm8 image, else a float image).
-// rows [row0, row1) only (0,0 = all): every invocation is independent, so a subset is a subset of the same launch.
+// rows row0, row0 + row_step, ... < row1 only (row1 = 0: to the last row): every invocation is independent, so a subset
+// of the rows is a subset of the same launch.
 // spp_override / depth_override: 0 = the literals of the shader text (32, 8). intersect: NULL = built-in brute force.
 // Returns the number of traceRayEXT calls.
 uint64_t ref_shade_render(const float* verts, const uint32_t* indices, uint32_t nindices, const float* faces,
-                          uint32_t width, uint32_t height, uint32_t row0, uint32_t row1, int frame, int spp_override,
+                          uint32_t width, uint32_t height, uint32_t row0, uint32_t row1, uint32_t row_step, int frame,
+                          int spp_override,
                           int depth_override, int rgba8, glsl::ref_intersect_fn intersect, void* user, int nthreads,
                           float* image) {
     rchit::vertices.data = verts;
@@ -125,6 +127,7 @@ uint64_t ref_shade_render(const float* verts, const uint32_t* indices, uint32_t 
     glsl::g_spp_override = spp_override;
     glsl::g_depth_override = depth_override;
     if (row1 == 0 || row1 > height) row1 = height;
+    if (row_step == 0) row_step = 1;
     if (nthreads <= 0) nthreads = int(std::max(1u, std::thread::hardware_concurrency()));
     std::atomic<uint32_t> next{row0};
     std::atomic<uint64_t> total{0};
@@ -132,7 +135,7 @@ uint64_t ref_shade_render(const float* verts, const uint32_t* indices, uint32_t 
         t_rays = 0;
         glsl::gl_LaunchSizeEXT = glsl::uvec3(width, height, 1);
         for (;;) {
-            const uint32_t y = next.fetch_add(1);
+            const uint32_t y = next.fetch_add(row_step);
             if (y >= row1) break;
             for (uint32_t x = 0; x < width; ++x) {
                 glsl::gl_LaunchIDEXT = glsl::uvec3(x, y, 0);

@@ -3,10 +3,20 @@
 
     python profiles/summarize.py launches gpurun_out/launches.csv            > profiles/<tag>_launches.txt
     python profiles/summarize.py kernel   gpurun_out/prof_trace.ncu-rep      > profiles/<tag>_k_trace_ncu.txt
+    python profiles/summarize.py traffic  gpurun_out/prof_trace.ncu-rep WORKLOAD N_GPUS   (updates profiles/k_trace_traffic.json)
+    python profiles/summarize.py sass     single-file-vulkan-pathtracing_b200/lib/libbpt.so > profiles/k_trace.sass
+
+`traffic` averages, over ALL captured k_trace launches (capture every bounce of a frame: `-k regex:k_trace -s <first
+launch of a timed frame> -c <launches per frame>`), the DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum), the
+duration and the issue / ALU-pipe / L2-hit figures, and stores them with the sha256 of csrc/ the capture was made
+from: bench.py prints `roofline.traffic` only when that hash is the hash of the code it runs.
 """
 import collections
 import csv
 import io
+import json
+import os
+import re
 import subprocess
 import sys
 
@@ -51,5 +61,61 @@ def kernel(path):
             print(f"{k:72s} {units[i]:16s} " + "  ".join(d[i] for d in data))
 
 
+def _num(x):
+    try:
+        return float(x.replace(",", ""))
+    except ValueError:
+        return float("nan")
+
+
+def traffic(path, workload, n_gpus):
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.dirname(here))
+    import bench
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = lambda k: [_num(d[hdr.index(k)]) for d in data]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    def nbytes(k):
+        u = units[hdr.index(k)]
+        return [v * scale.get(u, 1.0) for v in col(k)]
+    tscale = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0}
+    dur = [v * tscale.get(units[hdr.index("gpu__time_duration.sum")], 1e-9) for v in col("gpu__time_duration.sum")]
+    dram = [a + b for a, b in zip(nbytes("dram__bytes_read.sum"), nbytes("dram__bytes_write.sum"))]
+    wavg = lambda k: sum(v * t for v, t in zip(col(k), dur)) / sum(dur) / 100.0 if k in hdr else None
+    entry = {"workload": workload, "n_gpus": int(n_gpus), "csrc_hash": bench.csrc_hash(), "source": os.path.basename(path),
+             "kernel": data[0][hdr.index("Kernel Name")][:80], "launches": len(data),
+             "dram_bytes_per_launch": sum(dram) / len(dram), "dram_bytes_total": sum(dram),
+             "duration_ms_per_launch_under_ncu": 1e3 * sum(dur) / len(dur),
+             "dram_gbs_under_ncu": sum(dram) / sum(dur) / 1e9,
+             "issue_active_frac": wavg("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+             "alu_pipe_frac": wavg("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+             "fma_pipe_frac": wavg("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+             "l2_hit_rate": wavg("lts__t_sector_hit_rate.pct"),
+             "dram_pct_of_peak_ncu": wavg("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+             "per_launch": [{"ms": 1e3 * t, "dram_bytes": b} for t, b in zip(dur, dram)]}
+    out = os.path.join(here, "k_trace_traffic.json")
+    try:
+        entries = json.load(open(out))
+    except (OSError, ValueError):
+        entries = []
+    entries = [e for e in entries if (e["workload"], e["n_gpus"]) != (workload, int(n_gpus))] + [entry]
+    json.dump(entries, open(out, "w"), indent=1)
+    print(json.dumps({k: v for k, v in entry.items() if k != "per_launch"}, indent=1))
+
+
+def sass(lib):
+    """SASS of the traversal kernel instance the big scenes run (global records, one level, no counters)."""
+    txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    blocks = re.split(r"(?=\t\tFunction : )", txt)
+    for b in blocks:
+        m = re.match(r"\t\tFunction : (\S+)", b)
+        if m and "k_trace" in m.group(1) and "Lb0ELb0ELb0E" in m.group(1):
+            print(b.rstrip())
+            return
+    raise SystemExit("k_trace<.., false, false, false> not found")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "kernel": kernel, "traffic": traffic, "sass": sass}[sys.argv[1]](*sys.argv[2:])

@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libbpt.so")
 MISS = 0xFFFFFFFF
 ACCUM_FLOAT4, ACCUM_RGBA8 = 0, 1
 SAMPLER_UNIFORM, SAMPLER_COSINE = 0, 1
-OPT_PROFILE, OPT_COUNT_TRAVERSAL, OPT_SMEM_TOP_NODES, OPT_TRACE_CTAS_PER_SM = 1, 2, 3, 4
+OPT_PROFILE, OPT_COUNT_TRAVERSAL, OPT_SMEM_TOP_NODES, OPT_STREAMS = 1, 2, 3, 4
 OPT_TRACE_REFILL_BELOW, OPT_TRACE_STEPS_PER_REFILL, OPT_PASS_PATHS, OPT_TRACE_STAGED_TRIS_PER_STEP = 8, 9, 10, 11
 OPT_USE_GRAPH = 6
 OPT_BVH_OPTIMAL_COLLAPSE = 7
@@ -93,11 +93,15 @@ ABI = {
     "bpt_sync": (_i32, [_vp]),
     "bpt_read_image": (_i32, [_vp, _vp, _sz]),
     "bpt_read_image_bgra8": (_i32, [_vp, _vp, _sz]),
+    "bpt_read_image_async": (_i32, [_vp, _vp, _sz]),
+    "bpt_read_image_bgra8_async": (_i32, [_vp, _vp, _sz]),
+    "bpt_read_wait": (_i32, [_vp]),
     "bpt_image_device_ptr": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
     "bpt_clear_image": (_i32, [_vp]),
     "bpt_get_stats": (_i32, [_vp, C.POINTER(Stats)]),
     "bpt_reset_stats": (_i32, [_vp]),
     "bpt_trace_rays": (_i32, [_vp, _vp, _u32, _vp]),
+    "bpt_shade_step": (_i32, [_vp, C.POINTER(Params), _u32] + [_vp] * 9),
     "bpt_generate_rays": (_i32, [_vp, C.POINTER(Params), _u32, _vp, _vp]),
     "bpt_download_accel": (_i32, [_vp, _vp, _vp, _vp]),
     "bpt_download_mesh": (_i32, [_vp, _vp, _vp, _vp]),
@@ -224,6 +228,17 @@ class PathTracer:
         self._check(self._L.bpt_read_image_bgra8(self._h, _ptr(out), out.size))
         return out
 
+    def read_image_async(self, out):
+        """Enqueues the read-back of the image on the context's copy stream into `out` (H x W x 4 float32, ideally pinned);
+        the next trace may be enqueued at once. `out` is valid after read_wait()."""
+        self._check(self._L.bpt_read_image_async(self._h, _ptr(out), out.size))
+
+    def read_image_bgra8_async(self, out):
+        self._check(self._L.bpt_read_image_bgra8_async(self._h, _ptr(out), out.size))
+
+    def read_wait(self):
+        self._check(self._L.bpt_read_wait(self._h))
+
     def image_device_ptr(self):
         p, n = C.c_void_p(), C.c_size_t()
         self._check(self._L.bpt_image_device_ptr(self._h, C.byref(p), C.byref(n)))
@@ -254,6 +269,21 @@ class PathTracer:
         hits = np.zeros(len(rays), HIT_DTYPE)
         self._check(self._L.bpt_trace_rays(self._h, _ptr(rays), len(rays), _ptr(hits)))
         return hits
+
+    def shade_step(self, params, rays, hits, weight, seed):
+        """One closest-hit / miss + path-update step (bpt_shade_step); returns a dict of contrib, ray, weight, seed and alive,
+        one row per path."""
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        n = len(rays)
+        hits = np.ascontiguousarray(hits, HIT_DTYPE)
+        weight = np.ascontiguousarray(weight, np.float32).reshape(n, 3)
+        seed = np.ascontiguousarray(seed, np.uint32)
+        out = dict(contrib=np.zeros((n, 3), np.float32), ray=np.zeros((n, 8), np.float32),
+                   weight=np.zeros((n, 3), np.float32), seed=np.zeros(n, np.uint32), alive=np.zeros(n, np.uint8))
+        self._check(self._L.bpt_shade_step(self._h, C.byref(params), n, _ptr(rays), _ptr(hits), _ptr(weight), _ptr(seed),
+                                           _ptr(out["contrib"]), _ptr(out["ray"]), _ptr(out["weight"]), _ptr(out["seed"]),
+                                           _ptr(out["alive"])))
+        return out
 
     def generate_rays(self, params, sample_in_frame=0):
         rows = (params.height // params.tile_nranks if params.tile_block

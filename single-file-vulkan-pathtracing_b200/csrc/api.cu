@@ -20,6 +20,8 @@
 namespace {
 constexpr uint32_t kMaxDepth = 64;
 static_assert(kCounterStride == kMaxDepth + 1, "counter arrays are kMaxDepth + 1 long");
+constexpr int kMaxLanes = 4;                              // BPT_OPT_STREAMS
+constexpr uint32_t kLaneCounters = 3 * (kMaxDepth + 1);   // counts[], fetch[], shade tile counters[] of one lane
 std::string g_create_error;
 }  // namespace
 
@@ -60,13 +62,21 @@ struct bpt_context {
     float4* image_linear = nullptr;  // row-major copy produced on demand under interleaved tiling
     uint32_t img_w = 0, img_h = 0;
     uint32_t tile_block = 0, tile_nranks = 1, tile_rank = 0;  // tiling of the last bpt_trace
-    uint32_t* counters = nullptr;            // counts[], fetch[], shade tile counters[] (kMaxDepth+1 each; shade.cuh)
+    uint32_t* counters = nullptr;            // per lane: counts[], fetch[], shade tile counters[] (kMaxDepth+1 each; shade.cuh)
+    // sample lanes (BPT_OPT_STREAMS): lane 0 runs on `stream`, lane l > 0 on lane_stream[l-1], forked and joined with events
+    int num_lanes = 2;
+    cudaStream_t lane_stream[kMaxLanes - 1] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes - 1] = {nullptr, nullptr, nullptr};
+    // present path: asynchronous read-back on its own stream (bpt_read_image_async)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_img_ready = nullptr, ev_copy_done = nullptr;
+    bool copy_pending = false;
+    uint8_t* d_bgra = nullptr;               // BGRA8 view of the image, kept with the image (no allocation per read)
     unsigned long long* d_stats = nullptr;   // BPT_STAT_* (trace.cuh)
 
     // options
     bool profile = false, count = false;
     int64_t opt_stage_max_nodes = 1 << 20;  // BPT_OPT_SMEM_TOP_NODES: 0 disables shared-memory staging
-    int ctas_per_sm = 1;
     int refill_below = 30, steps_per_refill = 2, staged_tris_per_step = 2;
     // BPT_OPT_USE_GRAPH: the launch list of a frame captured once as a CUDA graph and replayed while nothing but the
     // frame index changes (the kernels then read the frame index from d_frame)
@@ -184,9 +194,11 @@ int ensure_frame_sum(bpt_context* c, size_t npix) {
 int ensure_image(bpt_context* c, uint32_t w, uint32_t h) {
     if (c->image && c->img_w == w && c->img_h == h) return BPT_OK;
     c->epoch++;
-    cudaFree(c->image); cudaFree(c->image_linear);
-    c->image = nullptr; c->image_linear = nullptr;
+    if (c->copy_pending) { cudaEventSynchronize(c->ev_copy_done); c->copy_pending = false; }
+    cudaFree(c->image); cudaFree(c->image_linear); cudaFree(c->d_bgra);
+    c->image = nullptr; c->image_linear = nullptr; c->d_bgra = nullptr;
     BPT_CUDA_TRY(c, cudaMalloc(&c->image, (size_t)w * h * sizeof(float4)));
+    BPT_CUDA_TRY(c, cudaMalloc(&c->d_bgra, (size_t)w * h * 4));
     BPT_CUDA_TRY(c, cudaMemsetAsync(c->image, 0, (size_t)w * h * sizeof(float4), c->stream));
     c->img_w = w;
     c->img_h = h;
@@ -219,12 +231,19 @@ int check_params(bpt_context* c, const bpt_params* p) {
     return BPT_OK;
 }
 
+// Everything that writes the image (or a view of it a pending asynchronous read-back copies from) waits for that copy
+// on the device first; the host never blocks.
+void wait_pending_copy(bpt_context* c) {
+    if (c->copy_pending) cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0);
+}
+
 // Row-major view of the image: the buffer itself, or its de-interleaved copy (interleaved tiling).
 int row_major_image(bpt_context* c, const float4** out) {
     *out = c->image;
     if (!c->tile_block) return BPT_OK;
     const size_t bytes = (size_t)c->img_w * c->img_h * sizeof(float4);
     if (!c->image_linear) BPT_CUDA_TRY(c, cudaMalloc(&c->image_linear, bytes));
+    wait_pending_copy(c);
     launch_deinterleave(c->image, c->image_linear, c->img_w, c->img_h, c->tile_block, c->tile_nranks, c->stream);
     *out = c->image_linear;
     return BPT_OK;
@@ -248,41 +267,72 @@ TraceArgs make_trace_args(bpt_context* c, const float4* rays, uint4* hits, const
     return a;
 }
 
-void launch_trace(bpt_context* c, const TraceArgs& a) {
+void launch_trace(bpt_context* c, const TraceArgs& a, cudaStream_t st) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->profile) {
         e0 = get_event(c); e1 = get_event(c);
-        cudaEventRecord(e0, c->stream);
+        cudaEventRecord(e0, st);
     }
-    trace_launch(a, (unsigned)(c->num_sms * c->ctas_per_sm), c->staged, c->two_level, c->count, c->stream);
+    trace_launch(a, (unsigned)c->num_sms, c->staged, c->two_level, c->count, st);
     if (c->profile) {
-        cudaEventRecord(e1, c->stream);
+        cudaEventRecord(e1, st);
         c->trace_events.emplace_back(e0, e1);
     }
     c->stats.trace_launches++;
     c->stats.kernel_launches++;
 }
 
-// The launch list of one frame on c's stream: per sample pass one generate, per bounce one traversal + one shade,
-// one gather; then the running mean. frame_dev: null, or the device int the kernels read the frame index from.
+// The launch list of one frame: per sample pass one generate, per bounce one traversal + one shade, one gather; then
+// the running mean. The samples of a pass are dealt to `num_lanes` independent wavefronts ("lanes"), each on its own
+// stream with its own slice of the queues and its own counters: a persistent traversal launch ends with a tail in which
+// most SMs idle while the last rays finish, and per-launch fixed costs that do not shrink with the tile of a GPU; with a
+// second lane in flight the freed SMs pick up the other lane's next kernel at once. A path's colour is collected per
+// path id and folded in sample order by the gather, so the image does not depend on the number of lanes.
+// frame_dev: null, or the device int the kernels read the frame index from (graph capture).
 void enqueue_frame(bpt_context* c, const FrameParams& f, uint32_t npix, uint32_t ns, const int32_t* frame_dev) {
     SceneView sv{c->d_srec, c->d_xforms, c->ntris};
-    uint32_t* counts = c->counters;
-    uint32_t* fetch = c->counters + (kMaxDepth + 1);
     for (uint32_t s0 = 0; s0 < f.spp_per_frame; s0 += ns) {
         const uint32_t n = std::min(ns, f.spp_per_frame - s0);
-        launch_generate(f, frame_dev, s0, n, c->q[0], counts, fetch, f.max_depth + 1, c->stream);
-        c->stats.kernel_launches++;
-        int cur = 0;
-        for (uint32_t d = 0; d < f.max_depth; ++d) {
-            launch_trace(c, make_trace_args(c, c->q[cur].rays, c->hits, counts + d, fetch + d));
-            launch_shade(f, sv, d, c->q[cur], c->hits, c->q[cur ^ 1], counts, fetch, c->path_color, npix * n, c->stream);
+        const uint32_t L = std::min<uint32_t>((uint32_t)c->num_lanes, n);
+        if (L > 1) {
+            cudaEventRecord(c->ev_fork, c->stream);
+            for (uint32_t l = 1; l < L; ++l) cudaStreamWaitEvent(c->lane_stream[l - 1], c->ev_fork, 0);
+        }
+        struct Lane { cudaStream_t st; PathQueue q[2]; uint4* hits; uint32_t *counts, *fetch; uint32_t paths; };
+        Lane lane[kMaxLanes];
+        uint32_t slot0 = 0;
+        for (uint32_t l = 0; l < L; ++l) {
+            const uint32_t nl = n / L + (l < n % L ? 1u : 0u);
+            const size_t off = (size_t)slot0 * npix;  // first path id of the lane
+            Lane& ln = lane[l];
+            ln.st = l ? c->lane_stream[l - 1] : c->stream;
+            for (int k = 0; k < 2; ++k) ln.q[k] = PathQueue{c->q[k].rays + 2 * off, c->q[k].state + off, c->q[k].pixel + off};
+            ln.hits = c->hits + off;
+            ln.counts = c->counters + l * kLaneCounters;
+            ln.fetch = ln.counts + (kMaxDepth + 1);
+            ln.paths = npix * nl;
+            launch_generate(f, frame_dev, s0 + slot0, nl, (uint32_t)off, ln.q[0], ln.counts, ln.fetch, f.max_depth + 1, ln.st);
             c->stats.kernel_launches++;
-            cur ^= 1;
+            slot0 += nl;
+        }
+        // bounce-major issue order, so that the lanes' kernels alternate in the hardware queues
+        for (uint32_t d = 0; d < f.max_depth; ++d)
+            for (uint32_t l = 0; l < L; ++l) {
+                Lane& ln = lane[l];
+                const int cur = (int)(d & 1u);
+                launch_trace(c, make_trace_args(c, ln.q[cur].rays, ln.hits, ln.counts + d, ln.fetch + d), ln.st);
+                launch_shade(f, sv, d, ln.q[cur], ln.hits, ln.q[cur ^ 1], ln.counts, ln.fetch, c->path_color, ln.paths,
+                             (unsigned)c->num_sms, ln.st);
+                c->stats.kernel_launches++;
+            }
+        for (uint32_t l = 1; l < L; ++l) {
+            cudaEventRecord(c->ev_join[l - 1], c->lane_stream[l - 1]);
+            cudaStreamWaitEvent(c->stream, c->ev_join[l - 1], 0);
         }
         launch_gather_pass(npix, n, c->path_color, c->frame_sum, c->stream);
         c->stats.kernel_launches++;
     }
+    if (!frame_dev) wait_pending_copy(c);  // a pending read-back of the previous frame (inside a capture: done by the caller)
     launch_accumulate(f, frame_dev, c->frame_sum, c->image, c->stream);
     c->stats.kernel_launches++;
 }
@@ -360,7 +410,16 @@ int bpt_create(int device, void* stream, bpt_context** out) {
         }
         c->own_stream = true;
     }
-    if ((e = cudaMalloc(&c->counters, 3 * (kMaxDepth + 1) * sizeof(uint32_t))) != cudaSuccess ||
+    for (int l = 0; l < kMaxLanes - 1 && e == cudaSuccess; ++l) {
+        e = cudaStreamCreateWithFlags(&c->lane_stream[l], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join[l], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_img_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming);
+    if (e != cudaSuccess ||
+        (e = cudaMalloc(&c->counters, kMaxLanes * kLaneCounters * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&c->d_stats, BPT_STAT_COUNT * sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaMemsetAsync(c->d_stats, 0, BPT_STAT_COUNT * sizeof(unsigned long long), c->stream)) != cudaSuccess ||
         (e = trace_configure()) != cudaSuccess) {
@@ -376,6 +435,14 @@ void bpt_destroy(bpt_context* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int l = 0; l < kMaxLanes - 1; ++l) {
+        if (c->lane_stream[l]) { cudaStreamSynchronize(c->lane_stream[l]); cudaStreamDestroy(c->lane_stream[l]); }
+        if (c->ev_join[l]) cudaEventDestroy(c->ev_join[l]);
+    }
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (cudaEvent_t ev : {c->ev_fork, c->ev_img_ready, c->ev_copy_done})
+        if (ev) cudaEventDestroy(ev);
+    cudaFree(c->d_bgra);
     if (c->nccl_comm) bpt_nccl_comm_destroy(c->nccl_comm);
     free_scene(c);
     free_paths(c);
@@ -416,15 +483,14 @@ int bpt_set_option(bpt_context* c, int option, int64_t value) {
             if (value < 1 || value > 16) return bpt_fail(c, BPT_E_INVALID, "triangle tests per step must be in [1,16]");
             c->staged_tris_per_step = (int)value;
             return BPT_OK;
-        case BPT_OPT_TRACE_CTAS_PER_SM:
-            if (value != 1) return bpt_fail(c, BPT_E_INVALID, "the traversal kernel runs one 1024-thread CTA per SM");
-            c->ctas_per_sm = 1;
+        case BPT_OPT_STREAMS:
+            if (value < 1 || value > kMaxLanes) return bpt_fail(c, BPT_E_INVALID, "sample lanes must be in [1,%d]", kMaxLanes);
+            c->num_lanes = (int)value;
             return BPT_OK;
         case BPT_OPT_PASS_PATHS:
             if (value < 1) return bpt_fail(c, BPT_E_INVALID, "paths per pass must be >= 1");
             c->pass_paths = value;
             return BPT_OK;
-        case BPT_OPT_SORT_RAYS: return bpt_fail(c, BPT_E_INVALID, "option %d is reserved", option);
         case BPT_OPT_USE_GRAPH: c->use_graph = value != 0; return BPT_OK;
         case BPT_OPT_BVH_OPTIMAL_COLLAPSE:  // takes effect at the next build of a changed mesh
             c->optimal_collapse = value != 0;
@@ -518,14 +584,7 @@ int bpt_set_instances(bpt_context* c, const float* xforms3x4, uint32_t n) {
     return BPT_OK;
 }
 
-int bpt_build_accel(bpt_context* c) {
-    if (!c) return BPT_E_INVALID;
-    if (c->ntris == 0) return bpt_fail(c, BPT_E_STATE, "bpt_build_accel before bpt_upload_mesh");
-    cudaSetDevice(c->device);
-    c->built = false; c->built_nodes_ok = false; c->staged = false;
-    c->epoch++;
-    cudaEvent_t e0 = get_event(c), e1 = get_event(c);
-    cudaEventRecord(e0, c->stream);
+static int build_accel_on_stream(bpt_context* c) {
     // Mesh level (the reference's BLAS, main.cpp:512): only when the mesh changed. Moving the instances
     // (bpt_set_instances + bpt_build_accel) rebuilds just the instance level below, like a TLAS rebuild.
     if (!c->mesh_built) {
@@ -568,13 +627,27 @@ int bpt_build_accel(bpt_context* c) {
     }
     if (depth > (uint32_t)kTraceMaxDepth)
         return bpt_fail(c, BPT_E_STATE, "BVH8 depth %u exceeds the traversal stack", depth);
-    cudaEventRecord(e1, c->stream);
-    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    BPT_CUDA_TRY(c, cudaGetLastError());
+    return BPT_OK;
+}
+
+int bpt_build_accel(bpt_context* c) {
+    if (!c) return BPT_E_INVALID;
+    if (c->ntris == 0) return bpt_fail(c, BPT_E_STATE, "bpt_build_accel before bpt_upload_mesh");
+    cudaSetDevice(c->device);
+    c->built = false; c->built_nodes_ok = false; c->staged = false;
+    c->epoch++;
+    cudaEvent_t e0 = get_event(c), e1 = get_event(c);
+    cudaEventRecord(e0, c->stream);
+    int rc = build_accel_on_stream(c);
+    cudaError_t e = cudaEventRecord(e1, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    c->event_pool.push_back(e0); c->event_pool.push_back(e1);  // on every path: the pool owns them
+    if (rc != BPT_OK) return rc;
+    BPT_CUDA_TRY(c, e);
     c->stats.build_ms = ms;
-    c->event_pool.push_back(e0); c->event_pool.push_back(e1);
     c->built_nodes_ok = true;
     plan_staging(c);
     c->built = true;
@@ -615,6 +688,7 @@ int bpt_trace(bpt_context* c, const bpt_params* p) {
     if ((rc = ensure_image(c, f.width, f.height)) != BPT_OK) return rc;
     if (f.tile_block != c->tile_block || (f.tile_block && (f.tile_nranks != c->tile_nranks || f.tile_rank != c->tile_rank))) {
         // the storage layout of the image buffer changes with the tiling: start from a fresh image
+        wait_pending_copy(c);
         BPT_CUDA_TRY(c, cudaMemsetAsync(c->image, 0, (size_t)f.width * f.height * sizeof(float4), c->stream));
         c->tile_block = f.tile_block;
         c->tile_nranks = f.tile_block ? f.tile_nranks : 1;
@@ -649,6 +723,7 @@ int bpt_trace(bpt_context* c, const bpt_params* p) {
             c->graph_epoch = c->epoch;
         }
         launch_set_i32(c->d_frame, f.frame, c->stream);
+        wait_pending_copy(c);
         BPT_CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, c->stream));
         c->stats.kernel_launches += c->graph_kernel_launches + 1;
         c->stats.trace_launches += c->graph_trace_launches;
@@ -692,13 +767,46 @@ int bpt_read_image_bgra8(bpt_context* c, uint8_t* bgra, size_t nbytes) {
     const float4* img = nullptr;
     int rc = row_major_image(c, &img);
     if (rc) return rc;
-    uint8_t* d = nullptr;
-    BPT_CUDA_TRY(c, cudaMalloc(&d, npix * 4));
-    launch_image_to_bgra8(img, d, npix, c->stream);
-    cudaError_t e = cudaMemcpyAsync(bgra, d, npix * 4, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(d);
-    BPT_CUDA_TRY(c, e);
+    wait_pending_copy(c);
+    launch_image_to_bgra8(img, c->d_bgra, npix, c->stream);
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(bgra, c->d_bgra, npix * 4, cudaMemcpyDeviceToHost, c->stream));
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return BPT_OK;
+}
+
+// Asynchronous read-back: the copy runs on the context's copy stream behind an event of the main stream, so the next
+// frame's kernels overlap it; whoever writes the image next waits for ev_copy_done on the device (wait_pending_copy).
+static int read_async(bpt_context* c, void* host, size_t have, bool bgra8) {
+    if (!c || !host) return BPT_E_INVALID;
+    if (!c->image) return bpt_fail(c, BPT_E_STATE, "no image yet");
+    const size_t npix = (size_t)c->img_w * c->img_h;
+    const size_t need = bgra8 ? npix * 4 : npix * 4 * sizeof(float);
+    if (have < need) return bpt_fail(c, BPT_E_INVALID, "buffer holds %zu bytes, image needs %zu", have, need);
+    cudaSetDevice(c->device);
+    const float4* img = nullptr;
+    int rc = row_major_image(c, &img);
+    if (rc) return rc;
+    const void* src = img;
+    if (bgra8) {
+        wait_pending_copy(c);
+        launch_image_to_bgra8(img, c->d_bgra, npix, c->stream);
+        src = c->d_bgra;
+    }
+    BPT_CUDA_TRY(c, cudaEventRecord(c->ev_img_ready, c->stream));
+    BPT_CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_img_ready, 0));
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(host, src, need, cudaMemcpyDeviceToHost, c->copy_stream));
+    BPT_CUDA_TRY(c, cudaEventRecord(c->ev_copy_done, c->copy_stream));
+    c->copy_pending = true;
+    return BPT_OK;
+}
+int bpt_read_image_async(bpt_context* c, float* rgba, size_t nfloats) { return read_async(c, rgba, nfloats * sizeof(float), false); }
+int bpt_read_image_bgra8_async(bpt_context* c, uint8_t* bgra, size_t nbytes) { return read_async(c, bgra, nbytes, true); }
+int bpt_read_wait(bpt_context* c) {
+    if (!c) return BPT_E_INVALID;
+    if (!c->copy_pending) return BPT_OK;
+    cudaSetDevice(c->device);
+    BPT_CUDA_TRY(c, cudaEventSynchronize(c->ev_copy_done));
+    c->copy_pending = false;
     return BPT_OK;
 }
 
@@ -717,6 +825,7 @@ int bpt_image_device_ptr(bpt_context* c, void** dptr, size_t* nbytes) {
 int bpt_clear_image(bpt_context* c) {
     if (!c) return BPT_E_INVALID;
     cudaSetDevice(c->device);
+    wait_pending_copy(c);
     if (c->image) BPT_CUDA_TRY(c, cudaMemsetAsync(c->image, 0, (size_t)c->img_w * c->img_h * sizeof(float4), c->stream));
     if (c->frame_sum) BPT_CUDA_TRY(c, cudaMemsetAsync(c->frame_sum, 0, c->cap_pixels * sizeof(float4), c->stream));
     return BPT_OK;
@@ -767,7 +876,7 @@ int bpt_trace_rays(bpt_context* c, const float* rays, uint32_t n, void* hits) {
     BPT_CUDA_TRY(c, cudaMemcpyAsync(c->q[0].rays, rays, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
     BPT_CUDA_TRY(c, cudaMemcpyAsync(counts, &init[0], 4, cudaMemcpyHostToDevice, c->stream));
     BPT_CUDA_TRY(c, cudaMemcpyAsync(fetch, &init[1], 4, cudaMemcpyHostToDevice, c->stream));
-    launch_trace(c, make_trace_args(c, c->q[0].rays, c->hits, counts, fetch));
+    launch_trace(c, make_trace_args(c, c->q[0].rays, c->hits, counts, fetch), c->stream);
     launch_refine_hits(SceneView{c->d_srec, c->d_xforms, c->ntris}, c->q[0].rays, c->hits, n, c->stream);
     BPT_CUDA_TRY(c, cudaMemcpyAsync(hits, c->hits, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -785,12 +894,67 @@ int bpt_generate_rays(bpt_context* c, const bpt_params* p, uint32_t sample_in_fr
     if ((rc = ensure_paths(c, npix)) != BPT_OK) return rc;
     uint32_t* counts = c->counters;
     uint32_t* fetch = c->counters + (kMaxDepth + 1);
-    launch_generate(f, nullptr, sample_in_frame, 1, c->q[0], counts, fetch, f.max_depth + 1, c->stream);
+    launch_generate(f, nullptr, sample_in_frame, 1, 0u, c->q[0], counts, fetch, f.max_depth + 1, c->stream);
     std::vector<float4> st(npix);
     BPT_CUDA_TRY(c, cudaMemcpyAsync(rays, c->q[0].rays, (size_t)npix * 32, cudaMemcpyDeviceToHost, c->stream));
     BPT_CUDA_TRY(c, cudaMemcpyAsync(st.data(), c->q[0].state, (size_t)npix * 16, cudaMemcpyDeviceToHost, c->stream));
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     for (uint32_t i = 0; i < npix; ++i) memcpy(&seeds[i], &st[i].w, 4);
+    return BPT_OK;
+}
+
+int bpt_shade_step(bpt_context* c, const bpt_params* p, uint32_t n, const float* rays, const void* hits, const float* weight,
+                   const uint32_t* seed, float* contrib, float* new_rays, float* new_weight, uint32_t* new_seed, uint8_t* alive) {
+    if (!c || !rays || !hits || !weight || !seed || !contrib || !new_rays || !new_weight || !new_seed || !alive) return BPT_E_INVALID;
+    int rc = check_params(c, p);
+    if (rc) return rc;
+    if (!c->built) return bpt_fail(c, BPT_E_STATE, "bpt_shade_step before bpt_build_accel");
+    if (n == 0) return BPT_OK;
+    cudaSetDevice(c->device);
+    if ((rc = ensure_paths(c, n)) != BPT_OK) return rc;
+    FrameParams f = to_frame(p);
+    f.max_depth = 2;  // shade bounce 0 of 2: the next segment is sampled, as raygen.rgen:78-80 always does
+    std::vector<float4> st(n);
+    std::vector<uint32_t> pix(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        st[i] = make_float4(weight[3 * (size_t)i], weight[3 * (size_t)i + 1], weight[3 * (size_t)i + 2], 0.f);
+        memcpy(&st[i].w, &seed[i], 4);
+        pix[i] = i;
+    }
+    uint32_t* counts = c->counters;
+    uint32_t* fetch = c->counters + (kMaxDepth + 1);
+    const uint32_t init[2] = {n, 0u};
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(c->q[0].rays, rays, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(c->q[0].state, st.data(), (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(c->q[0].pixel, pix.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(c->hits, hits, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(counts, init, 8, cudaMemcpyHostToDevice, c->stream));          // counts[0] = n, counts[1] = 0
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(fetch + kCounterStride, init + 1, 4, cudaMemcpyHostToDevice, c->stream));  // tile counter of bounce 0
+    launch_shade(f, SceneView{c->d_srec, c->d_xforms, c->ntris}, 0u, c->q[0], c->hits, c->q[1], counts, fetch, c->path_color, n,
+                 (unsigned)c->num_sms, c->stream);
+    uint32_t m = 0;
+    std::vector<float4> col(n), orays(2 * (size_t)n), ost(n);
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(&m, counts + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(col.data(), c->path_color, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    BPT_CUDA_TRY(c, cudaMemsetAsync(c->path_color, 0, (size_t)n * 16, c->stream));  // the per-path colours are zero between passes
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    BPT_CUDA_TRY(c, cudaGetLastError());
+    if (m > n) return bpt_fail(c, BPT_E_STATE, "shade step produced %u survivors of %u paths", m, n);
+    if (m) {
+        BPT_CUDA_TRY(c, cudaMemcpy(orays.data(), c->q[1].rays, (size_t)m * 32, cudaMemcpyDeviceToHost));
+        BPT_CUDA_TRY(c, cudaMemcpy(ost.data(), c->q[1].state, (size_t)m * 16, cudaMemcpyDeviceToHost));
+        BPT_CUDA_TRY(c, cudaMemcpy(pix.data(), c->q[1].pixel, (size_t)m * 4, cudaMemcpyDeviceToHost));
+    }
+    memset(new_rays, 0, (size_t)n * 32); memset(new_weight, 0, (size_t)n * 12); memset(new_seed, 0, (size_t)n * 4); memset(alive, 0, n);
+    for (uint32_t i = 0; i < n; ++i) { contrib[3 * (size_t)i] = col[i].x; contrib[3 * (size_t)i + 1] = col[i].y; contrib[3 * (size_t)i + 2] = col[i].z; }
+    for (uint32_t j = 0; j < m; ++j) {  // the survivors were compacted: scatter them back to their path
+        const uint32_t i = pix[j];
+        if (i >= n) return bpt_fail(c, BPT_E_STATE, "shade step returned path id %u of %u", i, n);
+        memcpy(new_rays + 8 * (size_t)i, &orays[2 * (size_t)j], 32);
+        memcpy(new_weight + 3 * (size_t)i, &ost[j], 12);
+        memcpy(new_seed + i, &ost[j].w, 4);
+        alive[i] = 1;
+    }
     return BPT_OK;
 }
 
@@ -852,7 +1016,7 @@ void bpt_tile_rows(uint32_t height, int rank, int nranks, uint32_t* y0, uint32_t
     if (nranks < 1) nranks = 1;
     uint32_t per = height / (uint32_t)nranks;
     if (y0) *y0 = per * (uint32_t)rank;
-    if (rows) *rows = per;
+    if (rows) *rows = rank == nranks - 1 ? height - per * (uint32_t)rank : per;
 }
 
 int bpt_nccl_unique_id(uint8_t id[BPT_NCCL_UNIQUE_ID_BYTES]) {
@@ -884,6 +1048,7 @@ int bpt_allgather_image(bpt_context* c, uint32_t width, uint32_t height) {
     // contiguous and interleaved tilings both keep rank r's rows at row r*height/nranks of the buffer
     uint32_t y0, rows;
     bpt_tile_rows(height, c->rank, c->nranks, &y0, &rows);
+    wait_pending_copy(c);  // the gather overwrites the other ranks' rows a pending read-back may still be copying
     size_t count = (size_t)rows * width * 4;  // floats per rank
     std::string err;
     // in place: this rank's tile already sits at its slot of the buffer (K12 wrote it there)

@@ -599,8 +599,9 @@ cudaError_t bvh8_build(Bvh8& b, cudaStream_t st) {
     const uint32_t n = b.n;
     cudaError_t e;
     k_morton_keys<<<grid_for(n), kBlock, 0, st>>>(b.plo, b.phi, n, b.bounds, b.keys);
-    // K3: sort the 62 significant bits (30-bit morton + 32-bit primitive id)
-    uint64_t* sorted = radix_sort_u64(b.keys, b.keys_tmp, n, 0, 62, b.sort_tmp, b.sort_tmp_bytes, st);
+    // K3: sort the 30 Morton bits [32,62) only (4 digit passes): the primitive id in the low word starts out ascending
+    // and the sort is stable, so equal Morton codes stay ordered by primitive id (the duplicate tie-break, T9)
+    uint64_t* sorted = radix_sort_u64(b.keys, b.keys_tmp, n, 32, 62, b.sort_tmp, b.sort_tmp_bytes, st);
     if (sorted != b.keys) { uint64_t* t = b.keys; b.keys = b.keys_tmp; b.keys_tmp = t; }
     if ((e = cudaMemsetAsync(b.arrive, 0, sizeof(uint32_t) * n, st)) != cudaSuccess) return e;
     if (n > 1) k_lbvh_hierarchy<<<grid_for(n - 1), kBlock, 0, st>>>(b.keys, n, b.left, b.right, b.parent, b.first, b.last);

@@ -3,6 +3,7 @@
 
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -24,13 +25,21 @@ Api g_api;
 std::once_flag g_once;
 
 void load() {
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    // BPT_NCCL_LIB names the library to load instead of the default sonames (a site-specific build; the tests use it
+    // to exercise the NCCL-missing path)
+    const char* override_name = getenv("BPT_NCCL_LIB");
+    const char* names[] = {override_name && *override_name ? override_name : "libnccl.so.2",
+                           override_name && *override_name ? nullptr : "libnccl.so"};
+    std::string why;
     for (const char* n : names) {
+        if (!n) continue;
         g_api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
         if (g_api.handle) break;
+        const char* e = dlerror();  // one call: dlerror() clears the message it returns
+        if (why.empty()) why = e ? e : "unknown";
     }
     if (!g_api.handle) {
-        g_api.load_error = std::string("cannot dlopen libnccl.so.2: ") + (dlerror() ? dlerror() : "unknown");
+        g_api.load_error = std::string("cannot dlopen ") + names[0] + ": " + why;
         return;
     }
 #define SYM(field, name)                                                              \

@@ -35,8 +35,8 @@ constexpr float kTwoPi = 6.2831855f, kPi = 3.1415927f, kPdf = 0.15915494f;
 // ---------------------------------------------------------------- K9
 // frame_dev: when non-null, the frame index is read from device memory instead of p.frame, so that a captured CUDA
 // graph of a frame's launches can be replayed for every frame (api.cu, BPT_OPT_USE_GRAPH).
-__global__ void k_generate(FrameParams p, const int32_t* __restrict__ frame_dev, uint32_t s0, uint32_t ns, PathQueue q,
-                           uint32_t* counts, uint32_t* fetch, uint32_t ncounters) {
+__global__ void k_generate(FrameParams p, const int32_t* __restrict__ frame_dev, uint32_t s0, uint32_t ns, uint32_t path_base,
+                           PathQueue q, uint32_t* counts, uint32_t* fetch, uint32_t ncounters) {
     if (frame_dev) p.frame = *frame_dev;
     const uint32_t npix = tile_local_rows(p) * p.width;
     const uint32_t npaths = npix * ns;  // one pass carries samples s0 .. s0+ns-1 of every tile pixel
@@ -64,7 +64,7 @@ __global__ void k_generate(FrameParams p, const int32_t* __restrict__ frame_dev,
     q.rays[2 * (size_t)i] = make_float4(o.x, o.y, o.z, p.tmin);
     q.rays[2 * (size_t)i + 1] = make_float4(d.x, d.y, d.z, p.tmax);
     q.state[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
-    q.pixel[i] = i;  // path id of the pass: slot * npix + tile-local pixel
+    q.pixel[i] = path_base + i;  // path id of the pass: (sample slot of the pass) * npix + tile-local pixel
 }
 
 // ---------------------------------------------------------------- K11
@@ -334,18 +334,19 @@ inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kBlock - 1) / kBlo
 
 }  // namespace
 
-void launch_generate(const FrameParams& p, const int32_t* frame_dev, uint32_t s0, uint32_t ns, PathQueue q, uint32_t* counts,
-                     uint32_t* fetch, uint32_t ncounters, cudaStream_t st) {
+void launch_generate(const FrameParams& p, const int32_t* frame_dev, uint32_t s0, uint32_t ns, uint32_t path_base, PathQueue q,
+                     uint32_t* counts, uint32_t* fetch, uint32_t ncounters, cudaStream_t st) {
     const uint64_t threads = std::max<uint64_t>((uint64_t)tile_local_rows(p) * p.width * ns, ncounters);  // the first threads also reset the counters
-    k_generate<<<grid_for(threads), kBlock, 0, st>>>(p, frame_dev, s0, ns, q, counts, fetch, ncounters);
+    k_generate<<<grid_for(threads), kBlock, 0, st>>>(p, frame_dev, s0, ns, path_base, q, counts, fetch, ncounters);
 }
 void launch_gather_pass(uint32_t npix, uint32_t ns, float4* path_color, float4* frame_sum, cudaStream_t st) {
     k_gather_pass<<<grid_for(npix), kBlock, 0, st>>>(npix, ns, path_color, frame_sum);
 }
 void launch_shade(const FrameParams& p, const SceneView& s, uint32_t depth, PathQueue in, const uint4* hits,
-                  PathQueue out, uint32_t* counts, uint32_t* fetch, float4* path_color, uint32_t max_paths, cudaStream_t st) {
+                  PathQueue out, uint32_t* counts, uint32_t* fetch, float4* path_color, uint32_t max_paths, unsigned num_sms,
+                  cudaStream_t st) {
     const unsigned full = grid_for(max_paths);
-    k_shade<<<std::min(full, 148u * 16u), kBlock, 0, st>>>(p, s, depth, in, hits, out, counts, fetch + kCounterStride + depth,
+    k_shade<<<std::min(full, num_sms * 16u), kBlock, 0, st>>>(p, s, depth, in, hits, out, counts, fetch + kCounterStride + depth,
                                                             path_color);
 }
 static __global__ void k_set_i32(int32_t* dst, int32_t v) { *dst = v; }

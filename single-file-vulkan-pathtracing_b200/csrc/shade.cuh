@@ -47,17 +47,19 @@ struct PathQueue {
     uint32_t* pixel;
 };
 
-// one pass = samples s0..s0+ns-1 of every tile pixel; path id = slot * tile_pixels + tile-local pixel
+// one lane of a pass = samples s0..s0+ns-1 of every tile pixel; path id = path_base + slot * tile_pixels + tile-local
+// pixel (path_base = the lane's first sample slot of the pass * tile_pixels; q, counts, fetch are the lane's own)
 // frame_dev (may be null): device int that overrides p.frame (graph replay)
-void launch_generate(const FrameParams& p, const int32_t* frame_dev, uint32_t s0, uint32_t ns, PathQueue q, uint32_t* counts,
-                     uint32_t* fetch, uint32_t ncounters, cudaStream_t st);
+void launch_generate(const FrameParams& p, const int32_t* frame_dev, uint32_t s0, uint32_t ns, uint32_t path_base, PathQueue q,
+                     uint32_t* counts, uint32_t* fetch, uint32_t ncounters, cudaStream_t st);
 void launch_set_i32(int32_t* dst, int32_t v, cudaStream_t st);
 // folds the per-sample colours of a finished pass into the frame sum (sample order) and clears them
 void launch_gather_pass(uint32_t npix, uint32_t ns, float4* path_color, float4* frame_sum, cudaStream_t st);
 // depth: index of the bounce being shaded; counts[depth] paths in `in`, survivors appended to `out`
 // and counted in counts[depth+1]. path_color: per-path radiance of the pass (indexed by path id).
 void launch_shade(const FrameParams& p, const SceneView& s, uint32_t depth, PathQueue in, const uint4* hits,
-                  PathQueue out, uint32_t* counts, uint32_t* fetch, float4* path_color, uint32_t max_paths, cudaStream_t st);
+                  PathQueue out, uint32_t* counts, uint32_t* fetch, float4* path_color, uint32_t max_paths, unsigned num_sms,
+                  cudaStream_t st);
 // re-derives (u,v) of every hit from the original vertices (what k_shade does internally)
 void launch_refine_hits(const SceneView& s, const float4* rays, uint4* hits, uint32_t n, cudaStream_t st);
 void launch_accumulate(const FrameParams& p, const int32_t* frame_dev, float4* frame_sum, float4* image, cudaStream_t st);

@@ -216,7 +216,7 @@ def ref_shade_lib():
         L = C.CDLL(REF_SHADE_PATH)
         vp = C.c_void_p
         L.ref_shade_render.restype = C.c_uint64
-        L.ref_shade_render.argtypes = ([vp, vp, C.c_uint32, vp] + [C.c_uint32] * 4 + [C.c_int] * 4 + [vp, vp, C.c_int, vp])
+        L.ref_shade_render.argtypes = ([vp, vp, C.c_uint32, vp] + [C.c_uint32] * 5 + [C.c_int] * 4 + [vp, vp, C.c_int, vp])
         L.ref_pcg.restype = C.c_uint32; L.ref_pcg.argtypes = [C.POINTER(C.c_uint32)]
         L.ref_pcg2d.restype = None; L.ref_pcg2d.argtypes = [C.POINTER(C.c_uint32)] * 2
         L.ref_rand.restype = C.c_float; L.ref_rand.argtypes = [C.POINTER(C.c_uint32)]
@@ -226,7 +226,7 @@ def ref_shade_lib():
 
 
 def ref_shade_render(verts, indices, faces, width, height, frames=1, spp=0, depth=0, rgba8=False, rows=(0, 0),
-                     scene=None, brute=True, nthreads=0, image=None, first_frame=0):
+                     scene=None, brute=True, nthreads=0, image=None, first_frame=0, row_step=1):
     """`frames` launches traceRaysKHR(width, height, 1) of the reference's shader text with push constant frame =
     first_frame.. over one storage image. spp / depth = 0 keep the literals of the text (32 / 8). scene: an oracle
     Scene whose intersector answers traceRayEXT (brute force or its BVH); None = the library's own brute force."""
@@ -242,6 +242,6 @@ def ref_shade_render(verts, indices, faces, width, height, frames=1, spp=0, dept
         user = scene.h
     rays = 0
     for f in range(first_frame, first_frame + frames):
-        rays += L.ref_shade_render(_ptr(verts), _ptr(indices), len(indices), _ptr(faces), width, height, rows[0], rows[1], f,
-                                   spp, depth, int(rgba8), fn, user, nthreads, _ptr(image))
+        rays += L.ref_shade_render(_ptr(verts), _ptr(indices), len(indices), _ptr(faces), width, height, rows[0], rows[1], row_step,
+                                   f, spp, depth, int(rgba8), fn, user, nthreads, _ptr(image))
     return image, int(rays)

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(L, s), s
     assert sorted(bpt.ABI) == syms, set(syms) ^ set(bpt.ABI)
-    assert L.bpt_abi_version() == 1
+    assert L.bpt_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
@@ -44,7 +44,7 @@ def test_default_params_are_the_reference_constants():
 
 
 def test_tile_rows_partition():
-    for h, n in ((4096, 8), (1024, 4), (256, 2), (1080, 1)):
+    for h, n in ((4096, 8), (1024, 4), (256, 2), (1080, 1), (1080, 7), (5, 3)):  # incl. heights the ranks do not divide
         rows = [bpt.tile_rows(h, r, n) for r in range(n)]
         assert rows[0][0] == 0 and sum(r[1] for r in rows) == h
         for a, b in zip(rows, rows[1:]):
@@ -68,3 +68,26 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", "Makefile")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.lower(), (dirpath, f)
+
+
+def test_nccl_missing_is_an_error_code_not_a_crash():
+    """when libnccl cannot be loaded, bpt_nccl_unique_id must return BPT_E_NCCL with a message (it used to
+    call dlerror() twice and build a std::string from NULL). The loader is a process-wide once: run in a subprocess."""
+    import subprocess
+    import sys
+    code = (
+        "import importlib, ctypes as C\n"
+        f"import sys; sys.path.insert(0, {ROOT!r})\n"
+        "bpt = importlib.import_module('single-file-vulkan-pathtracing_b200')\n"
+        "L = bpt.load_library()\n"
+        "buf = (C.c_uint8 * 128)()\n"
+        "rc = L.bpt_nccl_unique_id(buf)\n"
+        "msg = L.bpt_last_error(None).decode()\n"
+        "assert rc == -3, rc\n"
+        "assert 'cannot dlopen /nonexistent/libnccl-missing.so' in msg, msg\n"
+        "rc2 = L.bpt_nccl_unique_id(buf)\n"
+        "assert rc2 == -3\n"
+        "print('OK', msg)\n")
+    env = dict(os.environ, BPT_NCCL_LIB="/nonexistent/libnccl-missing.so")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "OK" in r.stdout, (r.returncode, r.stdout, r.stderr)

@@ -22,7 +22,44 @@ def pt_soup10m():
     pt.close()
 
 
-def test_soup10m_closest_hits_match_the_oracle(pt_soup10m):
+@pytest.fixture(scope="module")
+def oracle_soup10m():
+    verts, idx, faces = O.soup(10_000_000, 0x5EED0002)
+    return O.Scene(verts, idx, faces)
+
+
+def crop_parity(pt, scene, w, h, rows, spp, frames=1, depth=8, **cam):
+    """The GPU image of rows [rows[0], rows[1]) of the full w x h launch against the oracle's, same seeds (T3: a pixel's
+    samples depend on its global coordinates and the global sample index only). Returns (rel-L2, fraction of pixels that
+    differ by more than 1e-5 relative, rays gpu, rays oracle)."""
+    kw = dict(tile_y0=rows[0], tile_rows=rows[1] - rows[0], **cam)
+    pt.clear_image(); pt.reset_stats()
+    ref = np.zeros((h, w, 4), np.float32)
+    rays = 0
+    for f in range(frames):
+        pt.trace(bpt.default_params(w, h, spp, depth, f, **kw))
+        rays += scene.render(O.default_params(w, h, spp, depth, f, **kw), 32, image=ref)[1]
+    img = pt.read_image(w, h)[rows[0]:rows[1]]
+    ref = ref[rows[0]:rows[1]]
+    st = pt.stats()
+    pt.clear_image()
+    bad = np.abs(img - ref).max(-1) > 1e-5 * (1 + np.abs(ref).max(-1))
+    return O.rel_l2(img, ref), float(bad.mean()), int(st.rays_traced), rays
+
+
+def test_cfg4_soup10m_4096_crop_image_parity(pt_soup10m, oracle_soup10m):
+    """BASELINE config 4 at its stated size — 10 M soup, 4096 x 4096, depth 8 — rows 2046..2049 of the full launch at
+    4 spp against the oracle. A path whose ray grazes a triangle edge within float rounding may take the neighbouring
+    triangle on one side only (Woop-form test in the traversal kernel vs Moeller-Trumbore in the oracle) and then
+    diverges completely; with 65 k paths in the crop a handful of such paths dominate the rel-L2, so the per-pixel
+    agreement rate is asserted next to it."""
+    err, bad, rg, ro = crop_parity(pt_soup10m, oracle_soup10m, 4096, 4096, (2046, 2050), 4)
+    print(f"cfg4 crop: rel-L2 {err:.3e}, pixels differing {bad:.3e}, rays {rg} vs {ro}")
+    assert abs(rg - ro) <= 2e-4 * ro
+    assert bad <= 2e-3 and err <= 2e-2
+
+
+def test_soup10m_closest_hits_match_the_oracle(pt_soup10m, oracle_soup10m):
     rng = np.random.default_rng(7)
     n = 100_000
     o = rng.uniform((-1.1, -2.1, -1.1), (1.1, 0.1, 1.1), (n, 3)).astype(np.float32)
@@ -30,8 +67,7 @@ def test_soup10m_closest_hits_match_the_oracle(pt_soup10m):
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     rays = np.concatenate([o, np.full((n, 1), 1e-3, np.float32), d, np.full((n, 1), 1e4, np.float32)], 1)
     gpu = pt_soup10m.trace_rays(rays)
-    verts, idx, faces = O.soup(10_000_000, 0x5EED0002)
-    ref = O.Scene(verts, idx, faces).intersect(rays, 64)
+    ref = oracle_soup10m.intersect(rays, 64)
     same = gpu["prim"] == ref["prim"]
     assert 1.0 - same.mean() <= 5e-4
     hit = same & (ref["prim"] != O.MISS)
@@ -105,3 +141,40 @@ def test_cornell1000_instances_full_count(cornell):
         return q
     same = canon(gpu["prim"]) == canon(ref["prim"])
     assert 1.0 - same.mean() <= 5e-4 and (ref["prim"] != O.MISS).mean() > 0.3
+
+
+def test_cfg3_soup1m_1080p_crop_image_parity():
+    """BASELINE config 3 at its stated size — 1 M soup (seed 0x5EED0001), 1920 x 1080, depth 8 — rows 536..543 of the
+    full launch at 8 spp against the oracle; plus build invariants of the 1 M-triangle structure's counts."""
+    verts, idx, faces = O.soup(1_000_000, 0x5EED0001)
+    scene = O.Scene(verts, idx, faces)
+    with bpt.PathTracer(0) as pt:
+        pt.upload_soup(1_000_000, 0x5EED0001)
+        info = pt.build_accel()
+        assert info.num_tris == 1_000_000 and info.num_records == info.num_nodes8 + 1_000_000
+        err, bad, rg, ro = crop_parity(pt, scene, 1920, 1080, (536, 544), 8)
+    print(f"cfg3 crop: rel-L2 {err:.3e}, pixels differing {bad:.3e}, rays {rg} vs {ro}")
+    assert abs(rg - ro) <= 2e-4 * ro
+    assert bad <= 2e-3 and err <= 2e-2
+
+
+def test_cfg5_cornell1000_2048_crop_image_parity(cornell):
+    """BASELINE config 5 at its stated size — 1000 instances (10 x 10 x 10, pitch 2.5), 2048 x 2048, depth 8, camera at
+    z = 55 as bench.py frames it — rows 1020..1027 of the full launch, 32 spp (one frame of the text's constant)."""
+    n = 10
+    c = 0.5 * (n - 1) * 2.5
+    g = np.stack(np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij"), -1).reshape(-1, 3)
+    xf = np.zeros((n ** 3, 3, 4), np.float32)
+    xf[:, 0, 0] = xf[:, 1, 1] = xf[:, 2, 2] = 1.0
+    xf[:, :, 3] = g * 2.5 - c
+    xf = xf.reshape(-1, 12)
+    scene = O.Scene(*cornell, xforms=xf)
+    cam = dict(cam_origin=(0.0, -1.0, 55.0), cam_target=(0.0, -1.0, 52.0))
+    with bpt.PathTracer(0) as pt:
+        pt.upload_mesh(*cornell)
+        pt.set_instances(xf)
+        pt.build_accel()
+        err, bad, rg, ro = crop_parity(pt, scene, 2048, 2048, (1020, 1028), 32, **cam)
+    print(f"cfg5 crop: rel-L2 {err:.3e}, pixels differing {bad:.3e}, rays {rg} vs {ro}")
+    assert abs(rg - ro) <= 2e-4 * ro
+    assert err <= 1e-3

@@ -627,3 +627,151 @@ def test_error_paths(cornell):
                 pt.trace(bpt.default_params(**args))
     with pytest.raises(bpt.BptError):
         bpt.PathTracer(99)
+
+
+# ------------------------------------------------------------------------------------------ K11 alone (stage level)
+def test_shade_step_matches_oracle(pt_cornell, cornell_oracle, soup20k):
+    """bpt_shade_step = closesthit.rchit:50-65 / miss.rmiss:8-12 + raygen.rgen:76-83 for a batch of paths, nothing else:
+    an error that cancels in an image mean (rand order, weight update, emission before the break) shows here per path.
+    Integer work (seeds, alive flags) and everything made of + - * / sqrt is bit-exact (shade.cu is built without FMA
+    contraction, the oracle too); only sinf/cosf may differ from the host libm in the last bits -> direction 1e-6
+    absolute, weight 2e-6 relative."""
+    def check(pt, scene, rays, sampler):
+        hits = pt.trace_rays(rays)                       # (t, u, v) as shading re-derives them from the vertices
+        rng = np.random.default_rng(17)
+        w = rng.uniform(0.05, 1.5, (len(rays), 3)).astype(np.float32)
+        seed = rng.integers(0, 2 ** 32, len(rays), dtype=np.uint32)
+        seed[:4] = (0, 1, 0xFFFFFFFF, 0x80000000)
+        g = pt.shade_step(bpt.default_params(64, 64, 1, 8, sampler=sampler), rays, hits, w, seed)
+        r = scene.shade(O.default_params(64, 64, 1, 8, sampler=sampler), hits, w, seed)
+        assert np.array_equal(g["alive"], r["alive"]) and 0.2 < g["alive"].mean() < 1.0
+        assert np.array_equal(g["contrib"].view(np.uint32), r["contrib"].view(np.uint32))
+        assert (g["contrib"] != 0).any(axis=1).sum() > 100            # sky on misses, Ke on the light
+        a = g["alive"].astype(bool)
+        assert np.array_equal(g["seed"][a], r["seed"][a])             # two rands consumed, in order (r1 then r2)
+        assert np.array_equal(g["ray"][a][:, :4].view(np.uint32), r["ray"][a][:, :4].view(np.uint32))   # position, tmin
+        assert np.array_equal(g["ray"][a][:, 7], r["ray"][a][:, 7])                                       # tmax
+        assert np.abs(g["ray"][a][:, 4:7] - r["ray"][a][:, 4:7]).max() <= 1e-6
+        np.testing.assert_allclose(g["weight"][a], r["weight"][a], rtol=2e-6, atol=1e-7)
+        assert (g["ray"][~a] == 0).all() and (g["weight"][~a] == 0).all()
+        return a.sum()
+
+    for sampler in (bpt.SAMPLER_UNIFORM, bpt.SAMPLER_COSINE):
+        assert check(pt_cornell, cornell_oracle, random_rays(50_000, 21), sampler) > 20_000
+    verts, idx, faces, scene = soup20k
+    with bpt.PathTracer(0) as pt:
+        pt.upload_mesh(verts, idx, faces)
+        pt.build_accel()
+        check(pt, scene, random_rays(50_000, 22), bpt.SAMPLER_UNIFORM)
+        # ragged sizes incl. 1 path
+        for n in (1, 31, 257):
+            check_small = pt.shade_step(bpt.default_params(8, 8, 1, 8), random_rays(n, n), pt.trace_rays(random_rays(n, n)),
+                                        np.ones((n, 3), np.float32), np.arange(n, dtype=np.uint32))
+            assert len(check_small["alive"]) == n
+
+
+# ------------------------------------------------------------------------------------------ the reference's shader text
+def golden(name):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    return g["image"], int(g["rays"])
+
+
+def test_cfg1_against_the_reference_shader_text(pt_cornell):
+    """BASELINE config 1 (256 x 256, 1 spp, depth 2) against the image the reference's OWN shader text produces
+    (tests/golden/ref_shade_cfg1_*.npz: shaders/*.glsl|rgen|rchit|rmiss compiled as C++, oracle/ref_shade_glue.cpp).
+    rel-L2 <= 1e-3 (north_star); same number of traceRayEXT calls."""
+    ref, rays = golden("ref_shade_cfg1_256x256_1spp_depth2")
+    pt_cornell.clear_image(); pt_cornell.reset_stats()
+    img = pt_cornell.render(bpt.default_params(256, 256, 1, 2))
+    assert pt_cornell.stats().rays_traced == rays
+    assert O.rel_l2(img, ref) <= 1e-3
+    bad = np.abs(img - ref).max(-1) > 1e-5 * (1 + np.abs(ref).max(-1))
+    assert bad.mean() < 1e-3, bad.sum()
+
+
+def test_cfg2_full_size_rows_against_the_reference_shader_text(pt_cornell):
+    """BASELINE config 2 at its stated size: 1024 x 1024, 256 spp (8 frames of the text's 32), depth 8 — rows 508..515 of
+    the full launch against the reference's shader text (golden), rel-L2 <= 1e-3."""
+    ref, rays = golden("ref_shade_cfg2_1024x1024_rows508_516_8frames")
+    pt_cornell.clear_image(); pt_cornell.reset_stats()
+    for f in range(8):
+        pt_cornell.trace(bpt.default_params(1024, 1024, 32, 8, f, tile_y0=508, tile_rows=8))
+    img = pt_cornell.read_image(1024, 1024)[508:516]
+    st = pt_cornell.stats()
+    assert st.paths == 8 * 1024 * 256 and abs(st.rays_traced - rays) <= 1e-4 * rays
+    err = O.rel_l2(img, ref)
+    assert err <= 1e-3, err
+    pt_cornell.clear_image()
+
+
+def test_text_defaults_rgba8_against_the_reference_shader_text(pt_cornell):
+    """The reference as it ships — 32 spp, depth 8, rgba8 storage image, three frames — at 64 x 64: quantised levels
+    equal the shader text's except where a float sits on a rounding boundary."""
+    ref, _ = golden("ref_shade_text_64x64_3frames_rgba8")
+    pt_cornell.clear_image()
+    for f in range(3):
+        pt_cornell.trace(bpt.default_params(64, 64, 32, 8, f, accum_mode=bpt.ACCUM_RGBA8))
+    q = np.rint(pt_cornell.read_image(64, 64) * 255).astype(np.int32)
+    qr = np.rint(ref * 255).astype(np.int32)
+    assert np.abs(q - qr).max() <= 1 and (q != qr).mean() < 2e-3
+    pt_cornell.clear_image()
+
+
+# ------------------------------------------------------------------------------------------ lanes, async read-back
+def test_sample_lanes_do_not_change_the_image(pt_cornell):
+    """BPT_OPT_STREAMS: the samples of a pass run as 1..4 independent wavefronts on their own streams; the image is
+    bit-identical (per-path colours are folded in sample order), also under graph replay and with odd sample counts."""
+    imgs = []
+    for lanes in (1, 2, 3, 4):
+        pt_cornell.set_option(bpt.OPT_STREAMS, lanes)
+        pt_cornell.clear_image(); pt_cornell.reset_stats()
+        imgs.append(pt_cornell.render(bpt.default_params(160, 96, 7, 6), frames=2).copy())
+        st = pt_cornell.stats()
+        assert st.paths == 2 * 160 * 96 * 7
+        assert st.trace_launches == 2 * 6 * min(lanes, 7)
+    for im in imgs[1:]:
+        assert np.array_equal(im, imgs[0])
+    pt_cornell.set_option(bpt.OPT_STREAMS, 3)
+    pt_cornell.set_option(bpt.OPT_USE_GRAPH, 1)
+    pt_cornell.clear_image()
+    assert np.array_equal(pt_cornell.render(bpt.default_params(160, 96, 7, 6), frames=2), imgs[0])
+    pt_cornell.set_option(bpt.OPT_USE_GRAPH, 0)
+    pt_cornell.set_option(bpt.OPT_STREAMS, 2)
+    with pytest.raises(bpt.BptError):
+        pt_cornell.set_option(bpt.OPT_STREAMS, 5)
+    pt_cornell.clear_image()
+
+
+def test_async_read_back_overlaps_the_next_frame(pt_cornell):
+    """bpt_read_image_async: frame f is copied out while frame f+1 is traced; every copy equals the synchronous read of
+    the same frame, in float and BGRA8, with and without interleaved tiling."""
+    import torch
+    for tile in ({}, dict(tile_block=8, tile_nranks=2, tile_rank=1)):
+        p = lambda f: bpt.default_params(128, 96, 4, 6, f, **tile)
+        pt_cornell.clear_image()
+        want, want8 = [], []
+        for f in range(4):
+            pt_cornell.trace(p(f))
+            want.append(pt_cornell.read_image(128, 96).copy())
+            want8.append(pt_cornell.read_image_bgra8(128, 96).copy())
+        pt_cornell.clear_image()
+        bufs = [torch.empty((96, 128, 4), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+        bufs8 = [torch.empty((96, 128, 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(2)]
+        pt_cornell.trace(p(0))
+        for f in range(4):
+            pt_cornell.read_image_async(bufs[f & 1])
+            if f + 1 < 4:
+                pt_cornell.trace(p(f + 1))          # enqueued while the copy of frame f is in flight
+            pt_cornell.read_wait()
+            assert np.array_equal(bufs[f & 1], want[f]), f
+        pt_cornell.clear_image()
+        pt_cornell.trace(p(0))
+        for f in range(4):
+            pt_cornell.read_image_bgra8_async(bufs8[f & 1])
+            if f + 1 < 4:
+                pt_cornell.trace(p(f + 1))
+            pt_cornell.read_wait()
+            assert np.array_equal(bufs8[f & 1], want8[f]), f
+    pt_cornell.read_wait()                           # nothing pending: no-op
+    pt_cornell.clear_image()

@@ -100,7 +100,9 @@ def test_reference_arm_prints_the_contract_line():
     assert len(r.stdout.strip().splitlines()) == 1, r.stdout   # stdout carries the JSON line and nothing else
     line = json.loads(r.stdout.strip())
     assert line["impl"] == "reference" and line["metric"] == "Mray/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # the reference's shader text compiled as C++ where oracle/_ref/libref_shade.so exists, else the oracle's restatement
+    assert line["cpu_baseline"]["kind"] == ("reference" if O.ref_shade_available() else "port")
+    assert line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     # rank != 0 of a torchrun launch prints nothing and exits 0
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
