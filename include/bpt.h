@@ -46,6 +46,15 @@ extern "C" {
 /* sampler modes */
 #define BPT_SAMPLER_UNIFORM 0 /* raygen.rgen:23-30,79 — uniform hemisphere, pdf 1/2pi (PARITY)    */
 #define BPT_SAMPLER_COSINE  1 /* opt-in, NOT same-seed comparable with the reference              */
+/* Non-parity estimator switches (bpt_params.rr_start_depth, .nee; both 0 = the reference's estimator). They estimate
+ * the same integral as the reference's loop (raygen.rgen:62-84, truncated at max_depth segments) with less variance
+ * or less work, consume extra random numbers, and are therefore validated by convergence, never by same-seed equality:
+ *   rr_start_depth = k > 0 : Russian roulette after the hit of segment d >= k-1 (0-based): the path survives with
+ *       probability q = min(1, max(w.r, w.g, w.b)) of its updated weight (one more rand(seed)) and w /= q.
+ *   nee = 1 : next-event estimation. At every hit whose next segment would be traced, one point on the emissive
+ *       triangles (Ke != 0; chosen with probability proportional to area, uniform on the triangle: three rand(seed)
+ *       before the two of the bounce) is connected by a shadow ray; Ke of a triangle hit by a BOUNCE ray is then not
+ *       added again (camera rays still add it). Single-level scenes only. */
 
 typedef struct bpt_context bpt_context; /* opaque; owns all device memory */
 
@@ -79,6 +88,8 @@ typedef struct bpt_params {
     uint32_t tile_block;
     uint32_t tile_nranks;
     uint32_t tile_rank;
+    uint32_t rr_start_depth; /* 0 = off (reference); see "Non-parity estimator switches"   */
+    uint32_t nee;            /* 0 = off (reference)                                         */
 } bpt_params;
 
 /* Counters of the last bpt_trace / since bpt_reset_stats. */
@@ -127,6 +138,8 @@ typedef struct bpt_accel_info {
 #define BPT_OPT_STREAMS          4 /* sample lanes per pass (1..4, default 2): the samples of a pass are split into this many
                                       independent wavefronts on their own CUDA streams, so the tail of one lane's persistent
                                       traversal launch is filled by the other lanes' kernels; results do not depend on it */
+#define BPT_OPT_TRACE_BLOCK      5 /* threads per traversal CTA: 1024 (one persistent CTA per SM) or 256 (four per SM, scenes in
+                                      global memory only): smaller CTAs hand their SM share back earlier in a launch's tail */
 #define BPT_OPT_USE_GRAPH        6 /* 1: capture a frame's launch list as a CUDA graph and replay it while only the
                                       frame index changes (pays off for launch-bound, small frames)             */
 #define BPT_OPT_PASS_PATHS       10 /* target paths per sample pass: a pass carries min(spp, this / tile pixels)

@@ -106,6 +106,7 @@ struct orc_params {
     float tmin, tmax;
     uint32_t accum_mode, sampler;
     uint32_t tile_block, tile_nranks, tile_rank;  // interleaved tiling (include/bpt.h)
+    uint32_t rr_start_depth, nee;                 // non-parity estimator switches (include/bpt.h)
 };
 
 // the image rows a tile covers, in tile-local order (contiguous rows, or round-robin row blocks)
@@ -138,7 +139,36 @@ struct Scene {
     std::vector<BNode> nodes;
     std::vector<uint32_t> order;  // slot -> world prim id
     bool has_bvh = false;
+    // next-event estimation (bpt_params.nee): the emissive triangles in primitive order, the cumulative
+    // distribution of their areas (float(cumulative / total), both summed in double) and the total area
+    std::vector<uint32_t> lights;
+    std::vector<float> light_cdf;
+    float light_area = 0.0f;
 };
+
+// Area-proportional table of the emissive triangles; libbpt builds the same table from the same arrays
+// (api.cu build_light_table): areas in double from the float vertices, 0.5 * |(v1-v0) x (v2-v0)|.
+void build_lights(Scene& s) {
+    s.lights.clear(); s.light_cdf.clear(); s.light_area = 0.0f;
+    std::vector<double> cum;
+    double total = 0.0;
+    for (uint32_t i = 0; i < s.tris.size(); ++i) {
+        const float* f = &s.faces[6 * size_t(i % s.ntris_mesh)];
+        if (f[3] == 0.0f && f[4] == 0.0f && f[5] == 0.0f) continue;
+        const Tri& t = s.tris[i];
+        const double e1[3] = {double(t.v1[0]) - t.v0[0], double(t.v1[1]) - t.v0[1], double(t.v1[2]) - t.v0[2]};
+        const double e2[3] = {double(t.v2[0]) - t.v0[0], double(t.v2[1]) - t.v0[1], double(t.v2[2]) - t.v0[2]};
+        const double c[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+        const double area = 0.5 * std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+        if (!(area > 0.0)) continue;
+        total += area;
+        s.lights.push_back(i);
+        cum.push_back(total);
+    }
+    for (double c : cum) s.light_cdf.push_back(float(c / total));
+    if (!s.light_cdf.empty()) s.light_cdf.back() = 1.0f;
+    s.light_area = float(total);
+}
 
 void build_bvh(Scene& s) {
     const uint32_t n = static_cast<uint32_t>(s.tris.size());
@@ -398,6 +428,7 @@ V3<R> trace_pixel(const Scene& s, const orc_params& p, uint32_t px, uint32_t py,
         V3<R> o, d;
         camera_ray<R>(p, px, py, seed, o, d);
         V3<R> w{1, 1, 1};
+        R pdf_prev = R(0);  // NEE: solid-angle pdf the current segment's direction was sampled with
         for (uint32_t depth = 0; depth < p.max_depth; ++depth) {
             HitR<R> h = intersect<R>(s, o, d, R(p.tmin), R(p.tmax), brute);
             ++rays;
@@ -407,15 +438,63 @@ V3<R> trace_pixel(const Scene& s, const orc_params& p, uint32_t px, uint32_t py,
             }
             V3<R> pos, n, brdf, emi;
             closest_hit<R>(s, h.prim, h.u, h.v, pos, n, brdf, emi);
-            color = color + w * emi;                      // raygen.rgen:76
+            if (!(p.nee && depth > 0)) {
+                color = color + w * emi;                  // raygen.rgen:76
+            } else if (emi.x != R(0) || emi.y != R(0) || emi.z != R(0)) {
+                // NEE: a bounce ray found an emitter the previous vertex also sampled by area: balance heuristic between
+                // the bounce pdf it was drawn with (pdf_prev) and the area sampler's solid-angle pdf for this point
+                R cy = std::fabs(dot(d, n));
+                R pl = cy > R(0) && s.light_area > 0.0f ? h.t * h.t / (cy * R(s.light_area)) : R(0);
+                color = color + w * emi * (pdf_prev / (pdf_prev + pl));
+            }
+            if (p.nee && depth + 1 < p.max_depth && !s.lights.empty()) {
+                // next-event estimation (include/bpt.h): one area-proportional point on the emissive triangles
+                R rs = R(randf(seed)), ra = R(randf(seed)), rb = R(randf(seed));
+                size_t lo = 0, hi = s.light_cdf.size() - 1;  // first entry with cdf > rs (the last one if rs == 1)
+                while (lo < hi) { size_t mid = (lo + hi) / 2; if (R(s.light_cdf[mid]) > rs) hi = mid; else lo = mid + 1; }
+                const uint32_t lp = s.lights[lo];
+                const Tri& lt = s.tris[lp];
+                V3<R> a{R(lt.v0[0]), R(lt.v0[1]), R(lt.v0[2])}, b{R(lt.v1[0]), R(lt.v1[1]), R(lt.v1[2])}, c{R(lt.v2[0]), R(lt.v2[1]), R(lt.v2[2])};
+                R su = std::sqrt(ra);
+                R bu = su * (R(1) - rb), bv = su * rb, b0 = R(1) - bu - bv;
+                V3<R> y = a * b0 + b * bu + c * bv;
+                V3<R> l = y - pos;
+                R r2l = dot(l, l);
+                if (lp != h.prim && r2l > R(0)) {
+                    R rl = std::sqrt(r2l);
+                    V3<R> wd = l / rl;
+                    V3<R> ny = -normalize(cross(b - a, c - a));
+                    R cx = dot(wd, n), cy = std::fabs(dot(wd, ny));
+                    if (cx > R(0) && cy > R(0)) {
+                        ++rays;
+                        HitR<R> sh = intersect<R>(s, pos, wd, R(p.tmin), rl * R(0.999f), brute);
+                        if (sh.prim == MISS) {
+                            const float* lf = &s.faces[6 * size_t(lp % s.ntris_mesh)];
+                            V3<R> ke{R(lf[3]), R(lf[4]), R(lf[5])};
+                            // balance heuristic: f / (p_light + p_bounce), both solid-angle pdfs of this direction
+                            R pl = r2l / (cy * R(s.light_area));
+                            R pb = p.sampler == 1 ? cx / Consts<R>::pi : Consts<R>::pdf;
+                            color = color + w * brdf * ke * (cx / (pl + pb));
+                        }
+                    }
+                }
+            }
             o = pos;                                      // :77
             R r1 = R(randf(seed));
             R r2 = R(randf(seed));
             d = sample_direction<R>(r1, r2, n, p.sampler);  // :78
             if (p.sampler == 1) {
                 w = w * (brdf * Consts<R>::pi);           // cosine pdf cancels the cosine
+                pdf_prev = dot(d, n) / Consts<R>::pi;
             } else {
                 w = w * (brdf * dot(d, n) / Consts<R>::pdf);  // :79-80
+                pdf_prev = Consts<R>::pdf;
+            }
+            if (p.rr_start_depth && depth + 1 >= p.rr_start_depth) {   // Russian roulette (include/bpt.h)
+                R q = std::min(R(1), std::max(w.x, std::max(w.y, w.z)));
+                R r3 = R(randf(seed));
+                if (!(r3 < q)) break;
+                w = w / q;
             }
         }
     }
@@ -479,6 +558,7 @@ void* orc_scene_create(const float* verts, uint32_t nverts, const uint32_t* idx,
         }
     }
     if (s->tris.size() > brute_threshold) build_bvh(*s);
+    build_lights(*s);
     return s;
 }
 void orc_scene_destroy(void* s) { delete static_cast<Scene*>(s); }

@@ -17,13 +17,16 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbpt.so")
+# BPT_LIB_VARIANT=name loads lib/libbpt_name.so (a `make VARIANT=name` build of csrc/: A/B experiments on the GPU box)
+_VARIANT = os.environ.get("BPT_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, "lib", "libbpt%s.so" % ("_" + _VARIANT if _VARIANT else ""))
 MISS = 0xFFFFFFFF
 ACCUM_FLOAT4, ACCUM_RGBA8 = 0, 1
 SAMPLER_UNIFORM, SAMPLER_COSINE = 0, 1
 OPT_PROFILE, OPT_COUNT_TRAVERSAL, OPT_SMEM_TOP_NODES, OPT_STREAMS = 1, 2, 3, 4
 OPT_TRACE_REFILL_BELOW, OPT_TRACE_STEPS_PER_REFILL, OPT_PASS_PATHS, OPT_TRACE_STAGED_TRIS_PER_STEP = 8, 9, 10, 11
 OPT_USE_GRAPH = 6
+OPT_TRACE_BLOCK = 5
 OPT_BVH_OPTIMAL_COLLAPSE = 7
 NCCL_UNIQUE_ID_BYTES = 128
 
@@ -42,6 +45,7 @@ class Params(C.Structure):
         ("cam_origin", C.c_float * 3), ("cam_target", C.c_float * 3), ("sky", C.c_float * 3),
         ("tmin", C.c_float), ("tmax", C.c_float), ("accum_mode", C.c_uint32), ("sampler", C.c_uint32),
         ("tile_block", C.c_uint32), ("tile_nranks", C.c_uint32), ("tile_rank", C.c_uint32),
+        ("rr_start_depth", C.c_uint32), ("nee", C.c_uint32),
     ]
 
 

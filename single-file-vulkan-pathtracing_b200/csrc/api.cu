@@ -21,7 +21,7 @@ namespace {
 constexpr uint32_t kMaxDepth = 64;
 static_assert(kCounterStride == kMaxDepth + 1, "counter arrays are kMaxDepth + 1 long");
 constexpr int kMaxLanes = 4;                              // BPT_OPT_STREAMS
-constexpr uint32_t kLaneCounters = 3 * (kMaxDepth + 1);   // counts[], fetch[], shade tile counters[] of one lane
+constexpr uint32_t kLaneCounters = 4 * (kMaxDepth + 1);   // counts[], fetch[], shade tile counters[], shadow fetch[] of one lane
 std::string g_create_error;
 }  // namespace
 
@@ -62,6 +62,17 @@ struct bpt_context {
     float4* image_linear = nullptr;  // row-major copy produced on demand under interleaved tiling
     uint32_t img_w = 0, img_h = 0;
     uint32_t tile_block = 0, tile_nranks = 1, tile_rank = 0;  // tiling of the last bpt_trace
+    // next-event estimation (bpt_params.nee): light table of the uploaded mesh (built on first use) and per-path buffers
+    uint32_t* d_light_prims = nullptr;
+    float* d_light_cdf = nullptr;
+    uint32_t nlights = 0;
+    float light_area = 0.f;
+    bool lights_built = false;
+    float4* shadow_rays = nullptr;           // 2 per path
+    float4* shadow_contrib = nullptr;
+    uint4* shadow_hits = nullptr;
+    float* pdf_prev = nullptr;               // per path id
+    size_t cap_nee = 0;
     uint32_t* counters = nullptr;            // per lane: counts[], fetch[], shade tile counters[] (kMaxDepth+1 each; shade.cuh)
     // sample lanes (BPT_OPT_STREAMS): lane 0 runs on `stream`, lane l > 0 on lane_stream[l-1], forked and joined with events
     int num_lanes = 2;
@@ -78,6 +89,7 @@ struct bpt_context {
     bool profile = false, count = false;
     int64_t opt_stage_max_nodes = 1 << 20;  // BPT_OPT_SMEM_TOP_NODES: 0 disables shared-memory staging
     int refill_below = 30, steps_per_refill = 2, staged_tris_per_step = 2;
+    int trace_block = kTraceBlock;  // BPT_OPT_TRACE_BLOCK
     // BPT_OPT_USE_GRAPH: the launch list of a frame captured once as a CUDA graph and replayed while nothing but the
     // frame index changes (the kernels then read the frame index from d_frame)
     bool use_graph = false;
@@ -152,6 +164,7 @@ void free_scene(bpt_context* c) {
     c->ninst = 1;
     c->built = false;
     c->mesh_built = false;
+    c->lights_built = false;
 }
 void free_paths(bpt_context* c) {
     for (auto& q : c->q) {
@@ -161,6 +174,72 @@ void free_paths(bpt_context* c) {
     cudaFree(c->hits); cudaFree(c->path_color);
     c->hits = nullptr; c->path_color = nullptr;
     c->cap_paths = 0;
+    cudaFree(c->shadow_rays); cudaFree(c->shadow_contrib); cudaFree(c->shadow_hits); cudaFree(c->pdf_prev);
+    c->shadow_rays = nullptr; c->shadow_contrib = nullptr; c->shadow_hits = nullptr; c->pdf_prev = nullptr;
+    c->cap_nee = 0;
+}
+
+// per-path buffers of next-event estimation, as large as the path queues
+int ensure_nee(bpt_context* c) {
+    if (c->cap_nee >= c->cap_paths) return BPT_OK;
+    c->epoch++;
+    cudaFree(c->shadow_rays); cudaFree(c->shadow_contrib); cudaFree(c->shadow_hits); cudaFree(c->pdf_prev);
+    c->shadow_rays = nullptr; c->shadow_contrib = nullptr; c->shadow_hits = nullptr; c->pdf_prev = nullptr;
+    c->cap_nee = 0;
+    const size_t n = c->cap_paths;
+    BPT_CUDA_TRY(c, cudaMalloc(&c->shadow_rays, n * 2 * sizeof(float4)));
+    BPT_CUDA_TRY(c, cudaMalloc(&c->shadow_contrib, n * sizeof(float4)));
+    BPT_CUDA_TRY(c, cudaMalloc(&c->shadow_hits, n * sizeof(uint4)));
+    BPT_CUDA_TRY(c, cudaMalloc(&c->pdf_prev, n * sizeof(float)));
+    c->cap_nee = n;
+    return BPT_OK;
+}
+
+// Light table of next-event estimation: the emissive triangles (Ke != 0, area > 0) in primitive order and the cumulative
+// distribution of their areas. Areas in double from the float vertices, cdf = float(cumulative / total), last entry 1 —
+// the definition the CPU checker of the tests uses for the same switch. Built on the host from the uploaded arrays.
+int build_light_table(bpt_context* c) {
+    if (c->lights_built) return BPT_OK;
+    std::vector<float> verts(3 * (size_t)c->nverts), faces(6 * (size_t)c->nfaces);
+    std::vector<uint32_t> idx(c->nidx);
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    BPT_CUDA_TRY(c, cudaMemcpy(verts.data(), c->d_verts, verts.size() * 4, cudaMemcpyDeviceToHost));
+    BPT_CUDA_TRY(c, cudaMemcpy(idx.data(), c->d_idx, idx.size() * 4, cudaMemcpyDeviceToHost));
+    BPT_CUDA_TRY(c, cudaMemcpy(faces.data(), c->d_faces, faces.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> prims;
+    std::vector<double> cum;
+    double total = 0.0;
+    for (uint32_t t = 0; t < c->ntris; ++t) {
+        const float* f = &faces[6 * (size_t)t];
+        if (f[3] == 0.0f && f[4] == 0.0f && f[5] == 0.0f) continue;
+        const float* a = &verts[3 * (size_t)idx[3 * (size_t)t]];
+        const float* b = &verts[3 * (size_t)idx[3 * (size_t)t + 1]];
+        const float* d = &verts[3 * (size_t)idx[3 * (size_t)t + 2]];
+        const double e1[3] = {(double)b[0] - a[0], (double)b[1] - a[1], (double)b[2] - a[2]};
+        const double e2[3] = {(double)d[0] - a[0], (double)d[1] - a[1], (double)d[2] - a[2]};
+        const double x[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+        const double area = 0.5 * std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+        if (!(area > 0.0)) continue;
+        total += area;
+        prims.push_back(t);
+        cum.push_back(total);
+    }
+    std::vector<float> cdf(cum.size());
+    for (size_t i = 0; i < cum.size(); ++i) cdf[i] = (float)(cum[i] / total);
+    if (!cdf.empty()) cdf.back() = 1.0f;
+    cudaFree(c->d_light_prims); cudaFree(c->d_light_cdf);
+    c->d_light_prims = nullptr; c->d_light_cdf = nullptr;
+    c->nlights = (uint32_t)prims.size();
+    c->light_area = (float)total;
+    if (c->nlights) {
+        BPT_CUDA_TRY(c, cudaMalloc(&c->d_light_prims, prims.size() * 4));
+        BPT_CUDA_TRY(c, cudaMalloc(&c->d_light_cdf, cdf.size() * 4));
+        BPT_CUDA_TRY(c, cudaMemcpy(c->d_light_prims, prims.data(), prims.size() * 4, cudaMemcpyHostToDevice));
+        BPT_CUDA_TRY(c, cudaMemcpy(c->d_light_cdf, cdf.data(), cdf.size() * 4, cudaMemcpyHostToDevice));
+    }
+    c->lights_built = true;
+    c->epoch++;
+    return BPT_OK;
 }
 
 int ensure_paths(bpt_context* c, size_t n) {
@@ -228,6 +307,8 @@ int check_params(bpt_context* c, const bpt_params* p) {
     if ((uint64_t)rows * p->width > 0x7fffffffull) return bpt_fail(c, BPT_E_INVALID, "tile too large");
     if (p->accum_mode > BPT_ACCUM_RGBA8) return bpt_fail(c, BPT_E_INVALID, "bad accum_mode");
     if (p->sampler > BPT_SAMPLER_COSINE) return bpt_fail(c, BPT_E_INVALID, "bad sampler");
+    if (p->rr_start_depth > kMaxDepth) return bpt_fail(c, BPT_E_INVALID, "rr_start_depth must be in [0,%u]", kMaxDepth);
+    if (p->nee > 1) return bpt_fail(c, BPT_E_INVALID, "bad nee switch");
     return BPT_OK;
 }
 
@@ -264,6 +345,7 @@ TraceArgs make_trace_args(bpt_context* c, const float4* rays, uint4* hits, const
     a.staged_tris_per_step = c->staged_tris_per_step;
     a.magic = 0x47000000u;
     a.stat = c->d_stats;
+    a.count_rays = 1;
     return a;
 }
 
@@ -273,7 +355,7 @@ void launch_trace(bpt_context* c, const TraceArgs& a, cudaStream_t st) {
         e0 = get_event(c); e1 = get_event(c);
         cudaEventRecord(e0, st);
     }
-    trace_launch(a, (unsigned)c->num_sms, c->staged, c->two_level, c->count, st);
+    trace_launch(a, (unsigned)c->num_sms, c->trace_block, c->staged, c->two_level, c->count, st);
     if (c->profile) {
         cudaEventRecord(e1, st);
         c->trace_events.emplace_back(e0, e1);
@@ -291,6 +373,8 @@ void launch_trace(bpt_context* c, const TraceArgs& a, cudaStream_t st) {
 // frame_dev: null, or the device int the kernels read the frame index from (graph capture).
 void enqueue_frame(bpt_context* c, const FrameParams& f, uint32_t npix, uint32_t ns, const int32_t* frame_dev) {
     SceneView sv{c->d_srec, c->d_xforms, c->ntris};
+    const bool nee = f.nee && c->nlights > 0;
+    const NeeView nv{c->d_light_prims, c->d_light_cdf, c->nlights, c->light_area, f.nee ? c->pdf_prev : nullptr};
     for (uint32_t s0 = 0; s0 < f.spp_per_frame; s0 += ns) {
         const uint32_t n = std::min(ns, f.spp_per_frame - s0);
         const uint32_t L = std::min<uint32_t>((uint32_t)c->num_lanes, n);
@@ -298,7 +382,8 @@ void enqueue_frame(bpt_context* c, const FrameParams& f, uint32_t npix, uint32_t
             cudaEventRecord(c->ev_fork, c->stream);
             for (uint32_t l = 1; l < L; ++l) cudaStreamWaitEvent(c->lane_stream[l - 1], c->ev_fork, 0);
         }
-        struct Lane { cudaStream_t st; PathQueue q[2]; uint4* hits; uint32_t *counts, *fetch; uint32_t paths; };
+        struct Lane { cudaStream_t st; PathQueue q[2]; uint4* hits; uint32_t *counts, *fetch; uint32_t paths;
+                      float4 *srays, *scontrib; uint4* shits; };
         Lane lane[kMaxLanes];
         uint32_t slot0 = 0;
         for (uint32_t l = 0; l < L; ++l) {
@@ -308,6 +393,9 @@ void enqueue_frame(bpt_context* c, const FrameParams& f, uint32_t npix, uint32_t
             ln.st = l ? c->lane_stream[l - 1] : c->stream;
             for (int k = 0; k < 2; ++k) ln.q[k] = PathQueue{c->q[k].rays + 2 * off, c->q[k].state + off, c->q[k].pixel + off};
             ln.hits = c->hits + off;
+            ln.srays = nee ? c->shadow_rays + 2 * off : nullptr;
+            ln.scontrib = nee ? c->shadow_contrib + off : nullptr;
+            ln.shits = nee ? c->shadow_hits + off : nullptr;
             ln.counts = c->counters + l * kLaneCounters;
             ln.fetch = ln.counts + (kMaxDepth + 1);
             ln.paths = npix * nl;
@@ -321,7 +409,19 @@ void enqueue_frame(bpt_context* c, const FrameParams& f, uint32_t npix, uint32_t
                 Lane& ln = lane[l];
                 const int cur = (int)(d & 1u);
                 launch_trace(c, make_trace_args(c, ln.q[cur].rays, ln.hits, ln.counts + d, ln.fetch + d), ln.st);
-                launch_shade(f, sv, d, ln.q[cur], ln.hits, ln.q[cur ^ 1], ln.counts, ln.fetch, c->path_color, ln.paths,
+                if (nee && d + 1 < f.max_depth) {
+                    // next-event estimation: shadow rays of this bounce's hits, traced like any other ray; the unoccluded
+                    // ones add their light sample to the path's colour before the bounce is shaded
+                    launch_nee(f, sv, nv, d, ln.q[cur], ln.hits, ln.counts, ln.srays, ln.scontrib, c->d_stats + BPT_STAT_RAYS,
+                               ln.paths, (unsigned)c->num_sms, ln.st);
+                    TraceArgs sa = make_trace_args(c, ln.srays, ln.shits, ln.counts + d, ln.fetch + 2 * (kMaxDepth + 1) + d);
+                    sa.count_rays = 0;
+                    launch_trace(c, sa, ln.st);
+                    launch_nee_resolve(d, ln.counts, ln.shits, ln.scontrib, ln.q[cur].pixel, c->path_color, ln.paths,
+                                       (unsigned)c->num_sms, ln.st);
+                    c->stats.kernel_launches += 2;
+                }
+                launch_shade(f, sv, nv, d, ln.q[cur], ln.hits, ln.q[cur ^ 1], ln.counts, ln.fetch, c->path_color, ln.paths,
                              (unsigned)c->num_sms, ln.st);
                 c->stats.kernel_launches++;
             }
@@ -442,7 +542,7 @@ void bpt_destroy(bpt_context* c) {
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (cudaEvent_t ev : {c->ev_fork, c->ev_img_ready, c->ev_copy_done})
         if (ev) cudaEventDestroy(ev);
-    cudaFree(c->d_bgra);
+    cudaFree(c->d_bgra); cudaFree(c->d_light_prims); cudaFree(c->d_light_cdf);
     if (c->nccl_comm) bpt_nccl_comm_destroy(c->nccl_comm);
     free_scene(c);
     free_paths(c);
@@ -483,6 +583,10 @@ int bpt_set_option(bpt_context* c, int option, int64_t value) {
             if (value < 1 || value > 16) return bpt_fail(c, BPT_E_INVALID, "triangle tests per step must be in [1,16]");
             c->staged_tris_per_step = (int)value;
             return BPT_OK;
+        case BPT_OPT_TRACE_BLOCK:
+            if (value != kTraceBlock && value != kTraceBlockSmall) return bpt_fail(c, BPT_E_INVALID, "traversal CTA size must be %d or %d", kTraceBlock, kTraceBlockSmall);
+            c->trace_block = (int)value;
+            return BPT_OK;
         case BPT_OPT_STREAMS:
             if (value < 1 || value > kMaxLanes) return bpt_fail(c, BPT_E_INVALID, "sample lanes must be in [1,%d]", kMaxLanes);
             c->num_lanes = (int)value;
@@ -513,7 +617,7 @@ static int adopt_mesh(bpt_context* c, const void* verts, uint32_t nverts, const 
         cudaFree(c->d_xforms); cudaFree(c->d_xforms_inv);
         c->d_xforms = nullptr; c->d_xforms_inv = nullptr;
         c->ninst = 1;
-        c->built = false; c->mesh_built = false;
+        c->built = false; c->mesh_built = false; c->lights_built = false;
     } else {
         free_scene(c);
         BPT_CUDA_TRY(c, cudaMalloc(&c->d_verts, (size_t)nverts * 12));
@@ -686,6 +790,11 @@ int bpt_trace(bpt_context* c, const bpt_params* p) {
     if ((rc = ensure_paths(c, (size_t)npix * ns)) != BPT_OK) return rc;
     if ((rc = ensure_frame_sum(c, npix)) != BPT_OK) return rc;
     if ((rc = ensure_image(c, f.width, f.height)) != BPT_OK) return rc;
+    if (f.nee) {
+        if (c->two_level) return bpt_fail(c, BPT_E_INVALID, "next-event estimation supports single-level scenes only");
+        if ((rc = build_light_table(c)) != BPT_OK) return rc;
+        if ((rc = ensure_nee(c)) != BPT_OK) return rc;
+    }
     if (f.tile_block != c->tile_block || (f.tile_block && (f.tile_nranks != c->tile_nranks || f.tile_rank != c->tile_rank))) {
         // the storage layout of the image buffer changes with the tiling: start from a fresh image
         wait_pending_copy(c);
@@ -914,6 +1023,7 @@ int bpt_shade_step(bpt_context* c, const bpt_params* p, uint32_t n, const float*
     if ((rc = ensure_paths(c, n)) != BPT_OK) return rc;
     FrameParams f = to_frame(p);
     f.max_depth = 2;  // shade bounce 0 of 2: the next segment is sampled, as raygen.rgen:78-80 always does
+    f.nee = 0;        // a single step has no previous vertex: camera-ray semantics (emission is added in full)
     std::vector<float4> st(n);
     std::vector<uint32_t> pix(n);
     for (uint32_t i = 0; i < n; ++i) {
@@ -930,8 +1040,8 @@ int bpt_shade_step(bpt_context* c, const bpt_params* p, uint32_t n, const float*
     BPT_CUDA_TRY(c, cudaMemcpyAsync(c->hits, hits, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
     BPT_CUDA_TRY(c, cudaMemcpyAsync(counts, init, 8, cudaMemcpyHostToDevice, c->stream));          // counts[0] = n, counts[1] = 0
     BPT_CUDA_TRY(c, cudaMemcpyAsync(fetch + kCounterStride, init + 1, 4, cudaMemcpyHostToDevice, c->stream));  // tile counter of bounce 0
-    launch_shade(f, SceneView{c->d_srec, c->d_xforms, c->ntris}, 0u, c->q[0], c->hits, c->q[1], counts, fetch, c->path_color, n,
-                 (unsigned)c->num_sms, c->stream);
+    launch_shade(f, SceneView{c->d_srec, c->d_xforms, c->ntris}, NeeView{nullptr, nullptr, 0u, 0.f, nullptr}, 0u, c->q[0], c->hits,
+                 c->q[1], counts, fetch, c->path_color, n, (unsigned)c->num_sms, c->stream);
     uint32_t m = 0;
     std::vector<float4> col(n), orays(2 * (size_t)n), ost(n);
     BPT_CUDA_TRY(c, cudaMemcpyAsync(&m, counts + 1, 4, cudaMemcpyDeviceToHost, c->stream));

@@ -44,7 +44,8 @@ __global__ void k_generate(FrameParams p, const int32_t* __restrict__ frame_dev,
     if (i < ncounters) {  // queue lengths and fetch counters of this sample pass
         counts[i] = i == 0 ? npaths : 0u;
         fetch[i] = 0u;
-        fetch[kCounterStride + i] = 0u;  // tile counters of k_shade
+        fetch[kCounterStride + i] = 0u;      // tile counters of k_shade
+        fetch[2 * kCounterStride + i] = 0u;  // fetch counters of the shadow-ray launches
     }
     if (i >= npaths) return;
     const uint32_t slot = i / npix, pl = i - slot * npix;
@@ -138,7 +139,8 @@ __global__ void k_refine_hits(SceneView s, const float4* __restrict__ rays, uint
 // path_color[path id] collects `color` of one sample (raygen.rgen:76); k_gather_pass folds the samples of a pass into
 // the frame sum in sample order, so the result does not depend on how many samples a pass carries.
 __global__ void __launch_bounds__(kBlock, 4) k_shade(FrameParams p, SceneView s, uint32_t depth, PathQueue in, const uint4* __restrict__ hits,
-                        PathQueue out, uint32_t* counts, uint32_t* tile_ctr, float4* path_color) {
+                        PathQueue out, uint32_t* counts, uint32_t* tile_ctr, float4* path_color, float* pdf_prev,
+                        float light_area) {
     // The host does not know how many paths are still alive, so a grid of a few waves per SM pulls 256-path tiles
     // from a counter, in order (one block per 256 slots of the FULL queue would launch and retire half a million
     // mostly empty blocks per bounce; a strided or chunked loop would interleave distant paths in the compacted
@@ -184,7 +186,15 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(FrameParams p, SceneView s,
             const V3 nrm = -normalize(cross(v1 - v0, v2 - v0));      // :58, :43-48
             const V3 kd = sr.kd, ke = sr.ke;
             if (ke.x != 0.0f || ke.y != 0.0f || ke.z != 0.0f) {      // raygen.rgen:76 (adding 0 is exact)
-                const V3 c = w * ke;
+                V3 c = w * ke;
+                if (p.nee && depth > 0u) {
+                    // next-event estimation: the previous vertex sampled this emitter by area as well; balance heuristic
+                    // between the pdf the bounce direction was drawn with and the area sampler's pdf for this point
+                    const float cy = fabsf(dot(V3{rd.x, rd.y, rd.z}, nrm));
+                    const float pl = cy > 0.0f && light_area > 0.0f ? t * t / (cy * light_area) : 0.0f;
+                    const float pp = pdf_prev[pix];
+                    c = c * (pp / (pp + pl));
+                }
                 float4 acc = path_color[pix];
                 acc.x += c.x; acc.y += c.y; acc.z += c.z;
                 path_color[pix] = acc;
@@ -206,12 +216,19 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(FrameParams p, SceneView s,
                     l = V3{cosf(kTwoPi * r2) * sr, sinf(kTwoPi * r2) * sr, r1};
                 }
                 const V3 d = l.x * T + l.y * B + l.z * nrm;          // :38
+                if (p.nee) pdf_prev[pix] = p.sampler == BPT_SAMPLER_COSINE ? dot(d, nrm) / kPi : kPdf;
                 if (p.sampler == BPT_SAMPLER_COSINE) w = w * (brdf * kPi);
                 else w = w * (brdf * dot(d, nrm) / kPdf);            // :79-80
+                alive = true;
+                if (p.rr_start_depth && depth + 1u >= p.rr_start_depth) {   // Russian roulette (bpt.h), not the reference
+                    const float q = fminf(1.0f, fmaxf(w.x, fmaxf(w.y, w.z)));
+                    const float r3 = bpt_rand(seed);
+                    if (!(r3 < q)) alive = false;
+                    else w = w / q;
+                }
                 nro = make_float4(pos.x, pos.y, pos.z, p.tmin);
                 nrd = make_float4(d.x, d.y, d.z, p.tmax);
                 nst = make_float4(w.x, w.y, w.z, __uint_as_float(seed));
-                alive = true;
             }
         }
     }
@@ -229,6 +246,84 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(FrameParams p, SceneView s,
             out.pixel[j] = pix;
         }
     }
+    }
+}
+
+// ---------------------------------------------------------------- next-event estimation (bpt.h; not the reference)
+// One thread per path of bounce `depth`'s queue; the formulas are the ones the CPU checker states for the same switch,
+// in the same order, so that both agree with the same seeds.
+__global__ void __launch_bounds__(kBlock) k_nee(FrameParams p, SceneView s, NeeView nv, uint32_t depth, PathQueue in,
+                                                const uint4* __restrict__ hits, const uint32_t* __restrict__ counts,
+                                                float4* __restrict__ shadow_rays, float4* __restrict__ shadow_contrib,
+                                                unsigned long long* ray_stat) {
+    const uint32_t n = counts[depth];
+    uint32_t cast = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 so = make_float4(0.f, 0.f, 0.f, p.tmin), sd = make_float4(0.f, 0.f, 1.f, -1.0f);  // tmax < tmin: no connection
+        float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint4 h = hits[i];
+        if (h.w != BPT_MISS && depth + 1u < p.max_depth) {
+            const float4 st = in.state[i];
+            uint32_t seed = __float_as_uint(st.w);
+            const V3 w{st.x, st.y, st.z};
+            const ShadeRec sr = load_rec(s, h.w, nullptr);
+            const float4 ro = in.rays[2 * (size_t)i], rd = in.rays[2 * (size_t)i + 1];
+            float u, v, t = __uint_as_float(h.x);
+            barycentrics(V3{ro.x, ro.y, ro.z}, V3{rd.x, rd.y, rd.z}, sr.v0, sr.v1, sr.v2, u, v, t);
+            const float b0 = 1.0f - u - v;
+            const V3 pos = sr.v0 * b0 + sr.v1 * u + sr.v2 * v;
+            const V3 nrm = -normalize(cross(sr.v1 - sr.v0, sr.v2 - sr.v0));
+            const V3 brdf = sr.kd / kPi;
+            const float rs = bpt_rand(seed), ra = bpt_rand(seed), rb = bpt_rand(seed);
+            in.state[i].w = __uint_as_float(seed);
+            uint32_t lo = 0, hi = nv.nlights - 1u;  // first entry with cdf > rs (the last one if rs == 1)
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) / 2u;
+                if (__ldg(nv.light_cdf + mid) > rs) hi = mid; else lo = mid + 1u;
+            }
+            const uint32_t lp = __ldg(nv.light_prims + lo);
+            const ShadeRec lr = load_rec(s, lp, nullptr);
+            const float su = sqrtf(ra);
+            const float bu = su * (1.0f - rb), bv = su * rb, lb0 = 1.0f - bu - bv;
+            const V3 y = lr.v0 * lb0 + lr.v1 * bu + lr.v2 * bv;
+            const V3 l = y - pos;
+            const float r2l = dot(l, l);
+            if (lp != h.w && r2l > 0.0f) {
+                const float rl = sqrtf(r2l);
+                const V3 wd = l / rl;
+                const V3 ny = -normalize(cross(lr.v1 - lr.v0, lr.v2 - lr.v0));
+                const float cx = dot(wd, nrm), cy = fabsf(dot(wd, ny));
+                if (cx > 0.0f && cy > 0.0f) {
+                    const float pl = r2l / (cy * nv.light_area);
+                    const float pb = p.sampler == BPT_SAMPLER_COSINE ? cx / kPi : kPdf;
+                    const V3 c = w * brdf * lr.ke * (cx / (pl + pb));
+                    so = make_float4(pos.x, pos.y, pos.z, p.tmin);
+                    sd = make_float4(wd.x, wd.y, wd.z, rl * 0.999f);
+                    sc = make_float4(c.x, c.y, c.z, 1.0f);
+                    ++cast;
+                }
+            }
+        }
+        shadow_rays[2 * (size_t)i] = so;
+        shadow_rays[2 * (size_t)i + 1] = sd;
+        shadow_contrib[i] = sc;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cast += __shfl_xor_sync(FULL, cast, o);
+    if ((threadIdx.x & 31u) == 0u && cast) atomicAdd(ray_stat, (unsigned long long)cast);
+}
+
+__global__ void k_nee_resolve(uint32_t depth, const uint32_t* __restrict__ counts, const uint4* __restrict__ shadow_hits,
+                              const float4* __restrict__ shadow_contrib, const uint32_t* __restrict__ pixel,
+                              float4* __restrict__ path_color) {
+    const uint32_t n = counts[depth];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 c = shadow_contrib[i];
+        if (c.w == 0.0f || shadow_hits[i].w != BPT_MISS) continue;  // no connection, or something is in the way
+        const uint32_t pix = pixel[i];
+        float4 acc = path_color[pix];
+        acc.x += c.x; acc.y += c.y; acc.z += c.z;
+        path_color[pix] = acc;
     }
 }
 
@@ -342,12 +437,23 @@ void launch_generate(const FrameParams& p, const int32_t* frame_dev, uint32_t s0
 void launch_gather_pass(uint32_t npix, uint32_t ns, float4* path_color, float4* frame_sum, cudaStream_t st) {
     k_gather_pass<<<grid_for(npix), kBlock, 0, st>>>(npix, ns, path_color, frame_sum);
 }
-void launch_shade(const FrameParams& p, const SceneView& s, uint32_t depth, PathQueue in, const uint4* hits,
+void launch_shade(const FrameParams& p, const SceneView& s, const NeeView& nv, uint32_t depth, PathQueue in, const uint4* hits,
                   PathQueue out, uint32_t* counts, uint32_t* fetch, float4* path_color, uint32_t max_paths, unsigned num_sms,
                   cudaStream_t st) {
     const unsigned full = grid_for(max_paths);
     k_shade<<<std::min(full, num_sms * 16u), kBlock, 0, st>>>(p, s, depth, in, hits, out, counts, fetch + kCounterStride + depth,
-                                                            path_color);
+                                                            path_color, nv.pdf_prev, nv.light_area);
+}
+void launch_nee(const FrameParams& p, const SceneView& s, const NeeView& nv, uint32_t depth, PathQueue in, const uint4* hits,
+                const uint32_t* counts, float4* shadow_rays, float4* shadow_contrib, unsigned long long* ray_stat,
+                uint32_t max_paths, unsigned num_sms, cudaStream_t st) {
+    k_nee<<<std::min(grid_for(max_paths), num_sms * 16u), kBlock, 0, st>>>(p, s, nv, depth, in, hits, counts, shadow_rays,
+                                                                          shadow_contrib, ray_stat);
+}
+void launch_nee_resolve(uint32_t depth, const uint32_t* counts, const uint4* shadow_hits, const float4* shadow_contrib,
+                        const uint32_t* pixel, float4* path_color, uint32_t max_paths, unsigned num_sms, cudaStream_t st) {
+    k_nee_resolve<<<std::min(grid_for(max_paths), num_sms * 16u), kBlock, 0, st>>>(depth, counts, shadow_hits, shadow_contrib,
+                                                                                  pixel, path_color);
 }
 static __global__ void k_set_i32(int32_t* dst, int32_t v) { *dst = v; }
 void launch_set_i32(int32_t* dst, int32_t v, cudaStream_t st) { k_set_i32<<<1, 1, 0, st>>>(dst, v); }

@@ -12,6 +12,7 @@ struct FrameParams {
     float tmin, tmax;
     uint32_t accum_mode, sampler;
     uint32_t tile_block, tile_nranks, tile_rank;
+    uint32_t rr_start_depth, nee;
 };
 
 // Row bookkeeping of a tile (bpt_params.tile_*): l is the tile-local row.
@@ -36,8 +37,20 @@ struct SceneView {
 };
 void launch_shade_records(const float* verts, const uint32_t* idx, const float* faces, uint32_t ntris, float4* out, cudaStream_t st);
 
+// Next-event estimation (bpt_params.nee, include/bpt.h; not the reference's estimator): the emissive triangles in primitive
+// order with the cumulative distribution of their areas, and per path id the solid-angle pdf its current segment's direction
+// was sampled with (the balance heuristic needs it when a bounce ray finds an emitter).
+struct NeeView {
+    const uint32_t* light_prims;
+    const float* light_cdf;   // float(cumulative area / total area), last entry 1
+    uint32_t nlights;
+    float light_area;         // total area of the emissive triangles
+    float* pdf_prev;          // null when next-event estimation is off
+};
+
 // Per-pass device counters: counts[d] = length of bounce d's queue, fetch[d] = ray fetch counter of bounce d's traversal
-// launch, fetch[kCounterStride + d] = tile counter of bounce d's shade launch; k_generate resets all three.
+// launch, fetch[kCounterStride + d] = tile counter of bounce d's shade launch, fetch[2 * kCounterStride + d] = ray fetch
+// counter of bounce d's shadow-ray launch (next-event estimation); k_generate resets all four.
 constexpr uint32_t kCounterStride = 65;  // kMaxDepth + 1 (api.cu)
 
 // One wavefront queue (SoA): ray 2 x float4, state float4 {w.rgb, seed bits}, pixel u32 (= path id of the pass).
@@ -57,9 +70,19 @@ void launch_set_i32(int32_t* dst, int32_t v, cudaStream_t st);
 void launch_gather_pass(uint32_t npix, uint32_t ns, float4* path_color, float4* frame_sum, cudaStream_t st);
 // depth: index of the bounce being shaded; counts[depth] paths in `in`, survivors appended to `out`
 // and counted in counts[depth+1]. path_color: per-path radiance of the pass (indexed by path id).
-void launch_shade(const FrameParams& p, const SceneView& s, uint32_t depth, PathQueue in, const uint4* hits,
+void launch_shade(const FrameParams& p, const SceneView& s, const NeeView& nv, uint32_t depth, PathQueue in, const uint4* hits,
                   PathQueue out, uint32_t* counts, uint32_t* fetch, float4* path_color, uint32_t max_paths, unsigned num_sms,
                   cudaStream_t st);
+// Next-event estimation, run between the traversal and the shade of bounce `depth`: for every path of `in` that hit
+// something, one shadow ray towards an area-sampled point of the emissive triangles (shadow_rays 2 x float4 per path;
+// tmax < 0 marks "no connection") and the radiance it carries if nothing is in the way (shadow_contrib); consumes three
+// rand(seed) per hit (in.state is updated in place) and adds the number of shadow rays to *ray_stat. After the shadow
+// rays were traced, launch_nee_resolve adds the contributions of the unoccluded ones to the paths' colours.
+void launch_nee(const FrameParams& p, const SceneView& s, const NeeView& nv, uint32_t depth, PathQueue in, const uint4* hits,
+                const uint32_t* counts, float4* shadow_rays, float4* shadow_contrib, unsigned long long* ray_stat,
+                uint32_t max_paths, unsigned num_sms, cudaStream_t st);
+void launch_nee_resolve(uint32_t depth, const uint32_t* counts, const uint4* shadow_hits, const float4* shadow_contrib,
+                        const uint32_t* pixel, float4* path_color, uint32_t max_paths, unsigned num_sms, cudaStream_t st);
 // re-derives (u,v) of every hit from the original vertices (what k_shade does internally)
 void launch_refine_hits(const SceneView& s, const float4* rays, uint4* hits, uint32_t n, cudaStream_t st);
 void launch_accumulate(const FrameParams& p, const int32_t* frame_dev, float4* frame_sum, float4* image, cudaStream_t st);

@@ -48,6 +48,11 @@
 namespace {
 
 constexpr int kLocalStack = kTraceLocalStack;
+// (pop + node step) rounds per loop iteration: one triangle step, terminate test and loop overhead per BPT_NODE_STEPS
+// node steps (compile-time: even a trip-count-1 loop changes the register allocation of the kernel)
+#ifndef BPT_NODE_STEPS
+#define BPT_NODE_STEPS 1
+#endif
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---------------------------------------------------------------- TMA / mbarrier (PTX)
@@ -181,13 +186,13 @@ __device__ __forceinline__ uint32_t test_quad(uint32_t xn, uint32_t yn, uint32_t
 // state plus a sentinel, moves the ray into object space (d is NOT renormalised, so t is the same in both spaces) and
 // descends from the mesh root (node 0); popping the sentinel reloads the world-space ray.
 template <int BLOCK, int SSTACK, bool STAGED, bool TWO_LEVEL, bool COUNT>
-__global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
+__global__ void __launch_bounds__(BLOCK, kTraceBlock / BLOCK) k_trace(TraceArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     uint2* slut = reinterpret_cast<uint2*>(smem_raw + 16);  // byte o of slut[b]: bit p = bit (p ^ o) of b
     unsigned char* spool = smem_raw + 16 + 2048;  // ray pools: 32 rays x 48 B ({o,tmin} {d,tmax} {1/d,octant}) per warp
-    uint2* sstack = reinterpret_cast<uint2*>(smem_raw + kTraceSmemFixed);
-    unsigned char* srecs = smem_raw + kTraceSmemFixed + (size_t)SSTACK * BLOCK * sizeof(uint2);  // staged records
+    uint2* sstack = reinterpret_cast<uint2*>(smem_raw + trace_smem_fixed(BLOCK));
+    unsigned char* srecs = smem_raw + trace_smem_fixed(BLOCK) + (size_t)SSTACK * BLOCK * sizeof(uint2);  // staged records
 
     const uint32_t nrays = *a.count_ptr;
     if (nrays == 0u) return;  // uniform across the grid: an exhausted bounce costs one launch and nothing else
@@ -218,7 +223,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
     }
     __syncthreads();
 
-    if (blockIdx.x == 0 && threadIdx.x == 0 && a.stat) atomicAdd(a.stat + BPT_STAT_RAYS, (unsigned long long)nrays);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.stat && a.count_rays) atomicAdd(a.stat + BPT_STAT_RAYS, (unsigned long long)nrays);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t stack_a = smem_u32(sstack + threadIdx.x);  // entry i of this lane: stack_a + i * BLOCK * 8
@@ -311,6 +316,10 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                 if (lane == 0 && m) ++cnt_witer;
                 if (active) ++cnt_liter;
             }
+#if BPT_NODE_STEPS > 1
+#pragma unroll
+            for (int round = 0; round < BPT_NODE_STEPS; ++round) {
+#endif
             // ---------------- pop when out of node work: a node group always, a parked triangle group only when
             //                  none is draining (it stays on the stack until then)
             if (active && !(G.y & 0xff000000u) && sp > 0) {
@@ -393,6 +402,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
                     Tb = v0.lo.w; Tv = valid;
                 }
             }
+#if BPT_NODE_STEPS > 1
+            }
+#endif
             // ---------------- triangle step: one triangle of the lane's pending group
             __syncwarp();
 #pragma unroll 1
@@ -485,31 +497,39 @@ __global__ void __launch_bounds__(BLOCK, 1) k_trace(TraceArgs a) {
 }  // namespace
 
 // shared memory the traversal kernel needs with `staged_recs` records staged
-size_t trace_smem_bytes(uint32_t staged_recs) {
-    return kTraceSmemFixed + (size_t)kTraceSmemStack * kTraceBlock * sizeof(uint2) + (size_t)staged_recs * BPT_REC_BYTES;
+size_t trace_smem_bytes(uint32_t staged_recs, int block) {
+    return trace_smem_fixed(block) + (size_t)kTraceSmemStack * block * sizeof(uint2) + (size_t)staged_recs * BPT_REC_BYTES;
 }
 
 cudaError_t trace_configure() {
     cudaError_t e;
-#define CFG(S, L, C)                                                                                 \
-    if ((e = cudaFuncSetAttribute(k_trace<kTraceBlock, kTraceSmemStack, S, L, C>,                     \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kTraceMaxSmem)) != cudaSuccess) \
+#define CFG(B, S, L, C)                                                                               \
+    if ((e = cudaFuncSetAttribute(k_trace<B, kTraceSmemStack, S, L, C>,                                \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kTraceMaxSmem / (kTraceBlock / B))) != cudaSuccess) \
         return e;
-    CFG(false, false, false) CFG(false, false, true) CFG(true, false, false) CFG(true, false, true)
-    CFG(false, true, false) CFG(false, true, true) CFG(true, true, false) CFG(true, true, true)
+    CFG(kTraceBlock, false, false, false) CFG(kTraceBlock, false, false, true) CFG(kTraceBlock, true, false, false)
+    CFG(kTraceBlock, true, false, true) CFG(kTraceBlock, false, true, false) CFG(kTraceBlock, false, true, true)
+    CFG(kTraceBlock, true, true, false) CFG(kTraceBlock, true, true, true)
+    CFG(kTraceBlockSmall, false, false, false) CFG(kTraceBlockSmall, false, false, true)
+    CFG(kTraceBlockSmall, false, true, false) CFG(kTraceBlockSmall, false, true, true)
 #undef CFG
     return cudaSuccess;
 }
 
-void trace_launch(const TraceArgs& a, unsigned grid, bool staged, bool two_level, bool count, cudaStream_t st) {
-    const size_t smem = trace_smem_bytes(a.staged_recs);
-#define GO(S, L, C) k_trace<kTraceBlock, kTraceSmemStack, S, L, C><<<grid, kTraceBlock, smem, st>>>(a)
+void trace_launch(const TraceArgs& a, unsigned num_sms, int block, bool staged, bool two_level, bool count, cudaStream_t st) {
+    if (staged) block = kTraceBlock;  // the staged instance keeps one copy of the records per SM
+    const size_t smem = trace_smem_bytes(a.staged_recs, block);
+    const unsigned grid = num_sms * (unsigned)(kTraceBlock / block);
+#define GO(B, S, L, C) k_trace<B, kTraceSmemStack, S, L, C><<<grid, B, smem, st>>>(a)
     if (staged) {
-        if (two_level) { if (count) GO(true, true, true); else GO(true, true, false); }
-        else { if (count) GO(true, false, true); else GO(true, false, false); }
+        if (two_level) { if (count) GO(kTraceBlock, true, true, true); else GO(kTraceBlock, true, true, false); }
+        else { if (count) GO(kTraceBlock, true, false, true); else GO(kTraceBlock, true, false, false); }
+    } else if (block == kTraceBlockSmall) {
+        if (two_level) { if (count) GO(kTraceBlockSmall, false, true, true); else GO(kTraceBlockSmall, false, true, false); }
+        else { if (count) GO(kTraceBlockSmall, false, false, true); else GO(kTraceBlockSmall, false, false, false); }
     } else {
-        if (two_level) { if (count) GO(false, true, true); else GO(false, true, false); }
-        else { if (count) GO(false, false, true); else GO(false, false, false); }
+        if (two_level) { if (count) GO(kTraceBlock, false, true, true); else GO(kTraceBlock, false, true, false); }
+        else { if (count) GO(kTraceBlock, false, false, true); else GO(kTraceBlock, false, false, false); }
     }
 #undef GO
 }

@@ -2,10 +2,11 @@
 #pragma once
 #include "common.cuh"
 
-constexpr int kTraceBlock = 1024;      // one persistent CTA of 32 warps per SM
+constexpr int kTraceBlock = 1024;      // threads per SM: one persistent CTA of 32 warps, or 4 CTAs of 8 warps (kTraceBlockSmall)
+constexpr int kTraceBlockSmall = 256;
 constexpr int kTraceSmemStack = 8;     // per-lane stack entries held in shared memory
 constexpr int kTraceMaxSmem = 227 * 1024;
-constexpr int kTraceSmemFixed = 16 + 2048 + kTraceBlock * 48;  // mbarrier + octant permutation table + per-warp ray pools
+__host__ __device__ constexpr int trace_smem_fixed(int block) { return 16 + 2048 + block * 48; }  // mbarrier + octant permutation table + per-warp ray pools
 constexpr int kTraceLocalStack = 40;   // overflow entries per lane in local memory
 // every node step pushes at most one sibling group and one parked triangle group
 constexpr int kTraceMaxDepth = (kTraceSmemStack + kTraceLocalStack) / 2 - 1;
@@ -31,8 +32,10 @@ struct TraceArgs {
     int staged_tris_per_step;      // STAGED instance: triangle tests per lane per iteration (shared-memory records)
     uint32_t magic;                // 0x47000000 (float 32768): byte->float permute constant, see trace.cu byte_f
     unsigned long long* stat;      // BPT_STAT_* counters (may be null when not counting: only [RAYS] is touched)
+    int count_rays;                // 1: add the launch's ray count to stat[RAYS] (0: shadow-ray launches, counted by k_nee)
 };
 
-size_t trace_smem_bytes(uint32_t staged_recs);
+// block: kTraceBlock (one CTA per SM) or kTraceBlockSmall (four per SM; global-memory instance only)
+size_t trace_smem_bytes(uint32_t staged_recs, int block = kTraceBlock);
 cudaError_t trace_configure();
-void trace_launch(const TraceArgs& a, unsigned grid, bool staged, bool two_level, bool count, cudaStream_t st);
+void trace_launch(const TraceArgs& a, unsigned num_sms, int block, bool staged, bool two_level, bool count, cudaStream_t st);

@@ -1,10 +1,18 @@
 // main.cpp — C++20 host application over the C ABI (include/bpt.h), shaped like the reference's main()
-// (reference main.cpp:457-690): load the scene, upload it, build the acceleration structure, then a frame loop that
-// pushes `frame` and traces W x H x spp paths per iteration. What the reference does with Vulkan objects between
-// main.cpp:496 and :641 (BLAS/TLAS descriptions, pipeline, SBT, descriptor set) has no counterpart here: it is
-// bpt_upload_mesh + bpt_build_accel. There is no display server on the target machines, so "present"
-// (main.cpp:661-682) writes the B8G8R8A8 bytes the reference's storage image would hold to a PPM file, and the
-// float4 accumulation to a PFM file.
+// (reference main.cpp:457-690): open the GLFW window, load the scene, upload it, build the acceleration structure, then
+// the frame loop `while (!glfwWindowShouldClose) { glfwPollEvents(); push frame; trace; present; }`. What the reference
+// does with Vulkan objects between main.cpp:496 and :641 (BLAS/TLAS descriptions, pipeline, SBT, descriptor set) has
+// no counterpart here: it is bpt_upload_mesh + bpt_build_accel.
+//
+// Window: the reference's GLFW calls are kept one for one (glfwInit, the two window hints, glfwCreateWindow,
+// glfwWindowShouldClose, glfwPollEvents, glfwDestroyWindow, glfwTerminate: main.cpp:77-80, 647-648, 688-689), built
+// from the GLFW the reference vendors (external/glfw, compiled where it lies: see Makefile). The target machines have
+// no display server, so the window lives on GLFW's null platform, which cannot create a Vulkan surface
+// (external/glfw/src/null_window.c): "present" (main.cpp:661-682) hands the B8G8R8A8 bytes the reference's storage
+// image would hold to present_frame(), which keeps the latest frame and writes it to a PPM file at exit (the float4
+// accumulation goes to a PFM file). The read-back of frame f runs on the context's copy stream while frame f+1 is
+// traced (bpt_read_image_bgra8_async), so the loop never stalls on the copy the way queue.waitIdle() (main.cpp:683) does.
+// `--frames N` closes the window after N frames (glfwSetWindowShouldClose): the headless exit.
 //
 //   bpt_host --obj ../assets/CornellBox-Original.obj [--frames 8] [--width 1024 --height 1024 --spp 32 --depth 8]
 //            [--rgba8-feedback] [--out out]            (tinyobjloader build only, see Makefile)
@@ -20,6 +28,11 @@
 #include <vector>
 
 #include "bpt.h"
+
+#ifdef BPT_HOST_GLFW
+#define GLFW_INCLUDE_NONE  // the reference includes vulkan.hpp first, which has the same effect (main.cpp:8-9)
+#include <GLFW/glfw3.h>
+#endif
 
 #ifdef BPT_HOST_TINYOBJ
 #define TINYOBJLOADER_IMPLEMENTATION
@@ -39,8 +52,9 @@ struct Scene {
 };
 
 #ifdef BPT_HOST_TINYOBJ
-// The loader semantics of reference main.cpp:28-58, restated: tinyobj::LoadObj, negate Y, one vertex per index
-// (the index buffer becomes 0,1,2,...), one {Kd, Ke} record per triangle.
+// Restated from the reference's loadFromFile (main.cpp:28-58), which SURVEY C12 keeps as the input contract:
+// tinyobj::LoadObj, negate Y, one vertex per index (the index buffer becomes 0,1,2,...), one {Kd, Ke} record per
+// triangle.
 Scene load_obj(const std::string& path) {
     tinyobj::attrib_t attrib;
     std::vector<tinyobj::shape_t> shapes;
@@ -116,6 +130,7 @@ void write_pfm(const std::string& path, const std::vector<float>& rgba, uint32_t
 int main(int argc, char** argv) {
     std::string obj, scene_bin, out = "bpt_out";
     int frames = 8, device = 0;
+    bool want_display = false;
     bpt_params p;
     bpt_params_default(&p);  // WIDTH/HEIGHT 1024 (main.cpp:16-17), 32 spp, depth 8, camera, sky: the shader constants
     for (int i = 1; i < argc; ++i) {
@@ -134,9 +149,10 @@ int main(int argc, char** argv) {
         else if (a == "--spp") p.spp_per_frame = (uint32_t)std::atoi(next());
         else if (a == "--depth") p.max_depth = (uint32_t)std::atoi(next());
         else if (a == "--rgba8-feedback") p.accum_mode = BPT_ACCUM_RGBA8;  // raygen.rgen:88-90 on the rgba8 image
+        else if (a == "--display") want_display = true;  // let GLFW pick a real platform (none is compiled in here)
         else if (a == "--help" || a == "-h") {
             std::printf("usage: %s (--obj file.obj | --scene scene.bin) [--frames N] [--width W --height H --spp S --depth D]\n"
-                        "          [--rgba8-feedback] [--device I] [--out prefix]\n", argv[0]);
+                        "          [--rgba8-feedback] [--device I] [--out prefix] [--display]\n", argv[0]);
             return 0;
         } else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
@@ -163,24 +179,65 @@ int main(int argc, char** argv) {
         std::printf("accel: %u BVH8 nodes, depth %u, %s\n", info.num_nodes8, info.max_depth8,
                     info.top_nodes_smem ? "staged in shared memory" : "in global memory");
 
-        std::vector<uint8_t> bgra(size_t(p.width) * p.height * 4);
+        // ---- window (Context::Context, main.cpp:77-80)
+#ifdef BPT_HOST_GLFW
+        if (!want_display) glfwInitHint(GLFW_PLATFORM, GLFW_PLATFORM_NULL);  // no display server: the null platform
+        if (!glfwInit()) throw std::runtime_error("glfwInit failed");
+        glfwWindowHint(GLFW_CLIENT_API, GLFW_NO_API);
+        glfwWindowHint(GLFW_RESIZABLE, GLFW_FALSE);
+        GLFWwindow* window = glfwCreateWindow((int)p.width, (int)p.height, "B200 Pathtracing", nullptr, nullptr);
+        if (!window) throw std::runtime_error("glfwCreateWindow failed");
+        std::printf("window: %ux%u on GLFW platform 0x%x%s\n", p.width, p.height, glfwGetPlatform(),
+                    glfwGetPlatform() == GLFW_PLATFORM_NULL ? " (null: frames are kept in memory and dumped at exit)" : "");
+#endif
+        // present_frame: what copyImage -> swapchain + presentKHR (main.cpp:661-682) do with a finished frame
+        std::vector<uint8_t> shown(size_t(p.width) * p.height * 4);
+        int presented = 0;
+        auto present_frame = [&](const std::vector<uint8_t>& f) { shown = f; ++presented; };
+
+        std::vector<uint8_t> bgra[2] = {std::vector<uint8_t>(shown.size()), std::vector<uint8_t>(shown.size())};
         const auto t0 = std::chrono::steady_clock::now();
-        for (int frame = 0; frame < frames; ++frame) {  // while (!glfwWindowShouldClose) (main.cpp:647)
+        int frame = 0;
+#ifdef BPT_HOST_GLFW
+        while (!glfwWindowShouldClose(window)) {        // main.cpp:647
+            glfwPollEvents();                           // main.cpp:648
+#else
+        for (bool open = frames > 0; open;) {
+#endif
             p.frame = frame;                            // pushConstants(frame) (main.cpp:658)
             check(pt, bpt_trace(pt, &p));               // traceRaysKHR(..., WIDTH, HEIGHT, 1) (main.cpp:659)
-            check(pt, bpt_read_image_bgra8(pt, bgra.data(), bgra.size()));  // copyImage -> swapchain + waitIdle (:661-683)
+            if (frame > 0) {                            // frame - 1 was copied out while this frame was enqueued
+                check(pt, bpt_read_wait(pt));
+                present_frame(bgra[(frame - 1) & 1]);
+            }
+            check(pt, bpt_read_image_bgra8_async(pt, bgra[frame & 1].data(), bgra[frame & 1].size()));  // copyImage (:661-667)
+            ++frame;                                    // main.cpp:684
+            if (frame >= frames) {
+#ifdef BPT_HOST_GLFW
+                glfwSetWindowShouldClose(window, GLFW_TRUE);
+#else
+                open = false;
+#endif
+            }
         }
+        check(pt, bpt_read_wait(pt));
+        if (frame > 0) present_frame(bgra[(frame - 1) & 1]);
+        check(pt, bpt_sync(pt));                        // context.device->waitIdle() (main.cpp:687)
         const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         bpt_stats st;
         check(pt, bpt_get_stats(pt, &st));
-        std::printf("%d frames, %llu rays in %.3f s (%.1f Mray/s incl. per-frame read-back; device %.1f ms)\n", frames,
+        std::printf("%d frames presented, %llu rays in %.3f s (%.1f Mray/s incl. per-frame read-back; device %.1f ms)\n", presented,
                     (unsigned long long)st.rays_traced, secs, st.rays_traced / secs / 1e6, st.frame_ms);
         std::vector<float> rgba(size_t(p.width) * p.height * 4);
         check(pt, bpt_read_image(pt, rgba.data(), rgba.size()));
-        write_ppm_from_bgra(out + ".ppm", bgra, p.width, p.height);
+        write_ppm_from_bgra(out + ".ppm", shown, p.width, p.height);
         write_pfm(out + ".pfm", rgba, p.width, p.height);
         std::printf("wrote %s.ppm and %s.pfm\n", out.c_str(), out.c_str());
         bpt_destroy(pt);
+#ifdef BPT_HOST_GLFW
+        glfwDestroyWindow(window);                      // main.cpp:688
+        glfwTerminate();                                // main.cpp:689
+#endif
     } catch (const std::exception& e) {
         std::fprintf(stderr, "error: %s\n", e.what());
         return 1;

@@ -25,6 +25,7 @@ class OrcParams(C.Structure):
         ("cam_origin", C.c_float * 3), ("cam_target", C.c_float * 3), ("sky", C.c_float * 3),
         ("tmin", C.c_float), ("tmax", C.c_float), ("accum_mode", C.c_uint32), ("sampler", C.c_uint32),
         ("tile_block", C.c_uint32), ("tile_nranks", C.c_uint32), ("tile_rank", C.c_uint32),
+        ("rr_start_depth", C.c_uint32), ("nee", C.c_uint32),
     ]
 
 
@@ -39,6 +40,7 @@ def default_params(width=1024, height=1024, spp=32, depth=8, frame=0, **kw):
     p.tmin, p.tmax = 0.001, 10000.0
     p.accum_mode, p.sampler = 0, 0
     p.tile_block, p.tile_nranks, p.tile_rank = 0, 0, 0
+    p.rr_start_depth, p.nee = 0, 0
     for k, v in kw.items():
         if k in ("cam_origin", "cam_target", "sky"):
             getattr(p, k)[:] = v

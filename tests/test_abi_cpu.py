@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(bpt.Params) == 7 * 4 + 9 * 4 + 2 * 4 + 2 * 4 + 3 * 4
+    assert C.sizeof(bpt.Params) == 7 * 4 + 9 * 4 + 2 * 4 + 2 * 4 + 3 * 4 + 2 * 4
     assert C.sizeof(bpt.Stats) == 13 * 8
     assert C.sizeof(bpt.AccelInfo) == 6 * 4 + 2 * 8 + 2 * 4
     assert bpt.NODE8_DTYPE.itemsize == 64 and bpt.WOOP_DTYPE.itemsize == 64 and bpt.HIT_DTYPE.itemsize == 16

@@ -635,7 +635,8 @@ def test_shade_step_matches_oracle(pt_cornell, cornell_oracle, soup20k):
     an error that cancels in an image mean (rand order, weight update, emission before the break) shows here per path.
     Integer work (seeds, alive flags) and everything made of + - * / sqrt is bit-exact (shade.cu is built without FMA
     contraction, the oracle too); only sinf/cosf may differ from the host libm in the last bits -> direction 1e-6
-    absolute, weight 2e-6 relative."""
+    absolute; the weight multiplies dot(direction, normal), so it inherits that absolute error (2e-5 on weights of
+    order 1) next to 2e-6 relative."""
     def check(pt, scene, rays, sampler):
         hits = pt.trace_rays(rays)                       # (t, u, v) as shading re-derives them from the vertices
         rng = np.random.default_rng(17)
@@ -652,7 +653,7 @@ def test_shade_step_matches_oracle(pt_cornell, cornell_oracle, soup20k):
         assert np.array_equal(g["ray"][a][:, :4].view(np.uint32), r["ray"][a][:, :4].view(np.uint32))   # position, tmin
         assert np.array_equal(g["ray"][a][:, 7], r["ray"][a][:, 7])                                       # tmax
         assert np.abs(g["ray"][a][:, 4:7] - r["ray"][a][:, 4:7]).max() <= 1e-6
-        np.testing.assert_allclose(g["weight"][a], r["weight"][a], rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(g["weight"][a], r["weight"][a], rtol=2e-6, atol=2e-5)
         assert (g["ray"][~a] == 0).all() and (g["weight"][~a] == 0).all()
         return a.sum()
 
@@ -774,4 +775,71 @@ def test_async_read_back_overlaps_the_next_frame(pt_cornell):
             pt_cornell.read_wait()
             assert np.array_equal(bufs8[f & 1], want8[f]), f
     pt_cornell.read_wait()                           # nothing pending: no-op
+    pt_cornell.clear_image()
+
+
+def test_russian_roulette_is_the_same_estimator(pt_cornell, cornell_oracle):
+    """Russian roulette (bpt_params.rr_start_depth) is opt-in and not the reference's estimator. With
+    the same seeds the CUDA path and the oracle's restatement of the SAME rule agree to 1e-3 (it is ordinary shading
+    arithmetic + one more rand per bounce); against the reference's estimator it is validated by convergence: both
+    means agree within Monte-Carlo noise at 2048 spp, and it traces fewer rays."""
+    kw = dict(rr_start_depth=2)
+    pt_cornell.clear_image(); pt_cornell.reset_stats()
+    img = pt_cornell.render(bpt.default_params(96, 96, 8, 8, **kw))
+    rays_rr = pt_cornell.stats().rays_traced
+    ref, rays = cornell_oracle.render(O.default_params(96, 96, 8, 8, **kw), 32)
+    assert O.rel_l2(img, ref) <= 1e-3 and abs(rays_rr - rays) <= 1e-4 * rays
+    pt_cornell.clear_image(); pt_cornell.reset_stats()
+    pt_cornell.render(bpt.default_params(96, 96, 8, 8))
+    assert rays_rr < 0.9 * pt_cornell.stats().rays_traced
+    means = {}
+    for name, extra in (("reference", {}), ("rr", dict(rr_start_depth=3))):
+        pt_cornell.clear_image()
+        im = pt_cornell.render(bpt.default_params(48, 48, 256, 8, **extra), frames=8)[..., :3]
+        means[name] = im.reshape(6, 8, 6, 8, 3).mean(axis=(1, 3))
+    pt_cornell.clear_image()
+    a, b = means["reference"], means["rr"]
+    assert np.isfinite(b).all() and np.linalg.norm(a - b) / np.linalg.norm(a) < 0.08 and not np.array_equal(a, b)
+    with pytest.raises(bpt.BptError):
+        pt_cornell.trace(bpt.default_params(8, 8, 1, 2, rr_start_depth=1000))
+
+
+def test_next_event_estimation(pt_cornell, cornell_oracle, soup20k):
+    """next-event estimation with the balance heuristic (bpt_params.nee) is opt-in and not the
+    reference's estimator. (1) With the same seeds the CUDA wavefront (k_nee -> shadow-ray traversal -> k_nee_resolve ->
+    k_shade) and the oracle's restatement of the SAME rule agree to 1e-3, on the Cornell box and on a soup with 157
+    emitters, for both samplers and with roulette. (2) Against the reference's estimator it is validated by convergence,
+    and with the sky switched off (all light comes from the small emitter) its noise is well below the reference's."""
+    for kw in (dict(nee=1), dict(nee=1, sampler=bpt.SAMPLER_COSINE, rr_start_depth=3)):
+        pt_cornell.clear_image(); pt_cornell.reset_stats()
+        img = pt_cornell.render(bpt.default_params(96, 96, 8, 8, **kw))
+        rays_gpu = pt_cornell.stats().rays_traced
+        ref, rays = cornell_oracle.render(O.default_params(96, 96, 8, 8, **kw), 32)
+        assert O.rel_l2(img, ref) <= 1e-3, kw
+        assert abs(rays_gpu - rays) <= 2e-4 * rays
+    verts, idx, faces, scene = soup20k
+    with bpt.PathTracer(0) as pt:
+        pt.upload_mesh(verts, idx, faces)
+        pt.build_accel()
+        img = pt.render(bpt.default_params(96, 96, 4, 6, nee=1))
+        ref, _ = scene.render(O.default_params(96, 96, 4, 6, nee=1), 32)
+        assert O.rel_l2(img, ref) <= 2e-3
+        pt.set_instances(np.eye(3, 4, dtype=np.float32).reshape(1, 12)); pt.build_accel()
+        with pytest.raises(bpt.BptError):
+            pt.trace(bpt.default_params(8, 8, 1, 2, nee=1))          # single-level scenes only
+    dark = dict(sky=(0.0, 0.0, 0.0))
+    def blocks(frames, f0, **kw):
+        pt_cornell.clear_image()
+        acc = np.zeros((48, 48, 3))
+        for f in range(f0, f0 + frames):                              # independent frames (no running mean): sum by hand
+            pt_cornell.clear_image()
+            p = bpt.default_params(48, 48, 256, 8, 0, **kw)
+            p.frame = f
+            acc += pt_cornell.render(p)[..., :3] * (f + 1)
+        return (acc / frames).reshape(6, 8, 6, 8, 3).mean(axis=(1, 3))
+    truth = blocks(16, 0, **dark)                                     # 4096 spp of the reference's estimator
+    est = {name: [blocks(1, 100 + k, **dark, **kw) for k in range(6)] for name, kw in (("reference", {}), ("nee", dict(nee=1)))}
+    noise = {name: np.mean([np.linalg.norm(e - np.mean(v, axis=0)) for e in v]) for name, v in est.items()}
+    assert np.linalg.norm(np.mean(est["nee"], axis=0) - truth) / np.linalg.norm(truth) < 0.05
+    assert noise["nee"] < 0.75 * noise["reference"], noise
     pt_cornell.clear_image()

@@ -59,3 +59,52 @@ def test_host_app_renders_the_oracle_image(tmp_path, cornell, cornell_oracle):
     assert O.rel_l2(img, ref[..., :3]) <= 1e-3
     ppm = open(str(out) + ".ppm", "rb").read()
     assert ppm.startswith(b"P6\n96 96\n255\n") and len(ppm) == len(b"P6\n96 96\n255\n") + 96 * 96 * 3
+
+
+def write_obj(path, verts, idx, faces):
+    """An OBJ/MTL pair that the reference's loader semantics (tinyobj::LoadObj, negate Y, de-index, per-triangle
+    Kd/Ke; main.cpp:28-58) turn back into exactly these arrays: triangles only, Y stored un-negated, one material per
+    distinct {Kd, Ke}. 9 significant digits round-trip a float32."""
+    verts = np.asarray(verts, np.float32).reshape(-1, 3)
+    faces = np.asarray(faces, np.float32).reshape(-1, 6)
+    idx = np.asarray(idx, np.uint32).reshape(-1, 3)
+    mats = {}
+    mtl = os.path.splitext(path)[0] + ".mtl"
+    with open(path, "w") as f:
+        f.write(f"mtllib {os.path.basename(mtl)}\n")
+        for v in verts:
+            f.write("v %.9g %.9g %.9g\n" % (v[0], -v[1], v[2]))
+        for t, tri in enumerate(idx):
+            key = tuple(float(x) for x in faces[t])
+            name = mats.setdefault(key, f"m{len(mats)}")
+            f.write(f"usemtl {name}\nf {tri[0] + 1} {tri[1] + 1} {tri[2] + 1}\n")
+    with open(mtl, "w") as f:
+        for key, name in mats.items():
+            f.write("newmtl %s\nKd %.9g %.9g %.9g\nKe %.9g %.9g %.9g\n\n" % ((name,) + key))
+
+
+@pytest.mark.gpu
+def test_host_app_obj_path_window_loop_and_overlapped_present(tmp_path, cornell, cornell_oracle):
+    """SURVEY 8(f) rows 1-2 on the box: the --obj path through the reference's vendored tinyobjloader, the reference's
+    GLFW window lifecycle on the null platform (--frames is the headless exit), and the present loop whose read-back of
+    frame f overlaps the trace of frame f+1 — the dumped frame is the LAST frame, and the float image is the oracle's."""
+    help_text = subprocess.run([HOST, "--help"], capture_output=True, text=True).stdout
+    obj = tmp_path / "cornell_tris.obj"
+    write_obj(str(obj), *cornell)
+    out = tmp_path / "img"
+    args = ["--frames", "4", "--width", "80", "--height", "64", "--spp", "4", "--depth", "5", "--rgba8-feedback", "--out", str(out)]
+    r = subprocess.run([HOST, "--obj", str(obj)] + args, capture_output=True, text=True)
+    if "built without tinyobjloader" in r.stderr:
+        pytest.skip("host app was built without the reference tree")
+    assert r.returncode == 0, r.stderr
+    assert "108 vertices, 36 triangles" in r.stdout and "4 frames presented" in r.stdout
+    if "--display" in help_text and "window:" in r.stdout:
+        assert "GLFW platform 0x60005" in r.stdout          # GLFW_PLATFORM_NULL
+    ref = np.zeros((64, 80, 4), np.float32)
+    for frame in range(4):
+        cornell_oracle.render(O.default_params(80, 64, 4, 5, frame, accum_mode=1), 32, image=ref)
+    ppm = open(str(out) + ".ppm", "rb").read()
+    hdr = b"P6\n80 64\n255\n"
+    shown = np.frombuffer(ppm[len(hdr):], np.uint8).reshape(64, 80, 3).astype(np.int32)
+    want = np.rint(ref[..., :3] * 255).astype(np.int32)
+    assert np.abs(shown - want).max() <= 1 and (shown != want).mean() < 5e-3   # the presented frame is frame 3's image
