@@ -175,6 +175,17 @@ int bpt_upload_mesh_device(bpt_context* ctx,
                            const void* d_verts, uint32_t nverts,
                            const void* d_indices, uint32_t nindices,
                            const void* d_faces, uint32_t nfaces);
+/* The scene front-end on the device: what the body of the reference's loadFromFile does on the host (main.cpp:37-57),
+ * from the arrays tinyobj::LoadObj returns (main.cpp:34): every face corner becomes its own vertex with Y negated
+ * (:41-44), the index buffer becomes 0,1,2,... (:45), every face takes {Kd, Ke} of its material (:47-56).
+ *   positions       : attrib.vertices, xyz triples (npositions of them)
+ *   corner_vertex   : index_t::vertex_index of every face corner, all shapes in order (ncorners, a multiple of 3)
+ *   face_material   : mesh.material_ids of every face (ncorners / 3 of them)
+ *   materials_kd_ke : diffuse.rgb, emission.rgb per material (nmaterials of them)
+ * A corner that names no position or a face without a valid material is an error (the reference throws on the latter,
+ * main.cpp:49-51). Equivalent to bpt_upload_mesh of the arrays loadFromFile produces. */
+int bpt_upload_obj_arrays(bpt_context* ctx, const float* positions, uint32_t npositions, const int32_t* corner_vertex,
+                          uint32_t ncorners, const int32_t* face_material, const float* materials_kd_ke, uint32_t nmaterials);
 /* Instance transforms: n row-major 3x4 float matrices (VkTransformMatrixKHR, main.cpp:515-520), object -> world.
  * Call after bpt_upload_mesh (which resets the scene to one identity instance) and before bpt_build_accel: the
  * build then adds an instance-level BVH8 over the instances' world boxes (the reference's TLAS, main.cpp:538) and

@@ -59,4 +59,30 @@ int ref_load_obj(const char* obj_path, const char* mtl_dir, float* verts, uint32
     return 0;
 }
 
+// The RAW arrays tinyobj::LoadObj hands to loadFromFile (main.cpp:34-36), before lines :37-57 run: attrib.vertices,
+// the vertex_index of every face corner (all shapes, in order), the material id of every face and {Kd, Ke} of every
+// material. Same two-call protocol. Pins the input of the device-side front-end (bpt_upload_obj_arrays).
+int ref_load_obj_raw(const char* obj_path, const char* mtl_dir, float* positions, int32_t* corner_vertex, int32_t* face_material,
+                     float* materials_kd_ke, uint32_t* npositions, uint32_t* ncorners, uint32_t* nfaces, uint32_t* nmaterials) {
+    tinyobj::attrib_t attrib;
+    std::vector<tinyobj::shape_t> shapes;
+    std::vector<tinyobj::material_t> materials;
+    std::string warn, e;
+    if (!tinyobj::LoadObj(&attrib, &shapes, &materials, &warn, &e, obj_path, mtl_dir)) return -1;
+    if (positions) std::memcpy(positions, attrib.vertices.data(), attrib.vertices.size() * sizeof(float));
+    uint32_t nc = 0, nf = 0;
+    for (const auto& shape : shapes) {
+        for (const auto& index : shape.mesh.indices) { if (corner_vertex) corner_vertex[nc] = index.vertex_index; ++nc; }
+        for (int m : shape.mesh.material_ids) { if (face_material) face_material[nf] = m; ++nf; }
+    }
+    if (materials_kd_ke)
+        for (size_t m = 0; m < materials.size(); ++m)
+            for (int c = 0; c < 3; ++c) {
+                materials_kd_ke[6 * m + c] = materials[m].diffuse[c];
+                materials_kd_ke[6 * m + 3 + c] = materials[m].emission[c];
+            }
+    *npositions = uint32_t(attrib.vertices.size() / 3); *ncorners = nc; *nfaces = nf; *nmaterials = uint32_t(materials.size());
+    return 0;
+}
+
 }  // extern "C"

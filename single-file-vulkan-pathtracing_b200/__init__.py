@@ -89,6 +89,7 @@ ABI = {
     "bpt_set_option": (_i32, [_vp, _i32, C.c_int64]),
     "bpt_upload_mesh": (_i32, [_vp, _vp, _u32, _vp, _u32, _vp, _u32]),
     "bpt_upload_mesh_device": (_i32, [_vp, _vp, _u32, _vp, _u32, _vp, _u32]),
+    "bpt_upload_obj_arrays": (_i32, [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _u32]),
     "bpt_set_instances": (_i32, [_vp, _vp, _u32]),
     "bpt_upload_soup": (_i32, [_vp, _u32, _u32]),
     "bpt_build_accel": (_i32, [_vp]),
@@ -194,6 +195,17 @@ class PathTracer:
         faces = np.ascontiguousarray(faces, np.float32).reshape(-1, 6)
         self._check(self._L.bpt_upload_mesh(self._h, _ptr(verts), len(verts), _ptr(indices), len(indices),
                                             _ptr(faces), len(faces)))
+
+    def upload_obj_arrays(self, positions, corner_vertex, face_material, materials_kd_ke):
+        """The reference's loadFromFile body on the device (bpt_upload_obj_arrays) from the arrays tinyobj::LoadObj returns."""
+        positions = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        corner_vertex = np.ascontiguousarray(corner_vertex, np.int32).reshape(-1)
+        face_material = np.ascontiguousarray(face_material, np.int32).reshape(-1)
+        materials_kd_ke = np.ascontiguousarray(materials_kd_ke, np.float32).reshape(-1, 6)
+        if len(face_material) * 3 != len(corner_vertex):
+            raise ValueError("one material id per face (3 corners)")
+        self._check(self._L.bpt_upload_obj_arrays(self._h, _ptr(positions), len(positions), _ptr(corner_vertex), len(corner_vertex),
+                                                  _ptr(face_material), _ptr(materials_kd_ke), len(materials_kd_ke)))
 
     def upload_soup(self, ntris, seed):
         self._check(self._L.bpt_upload_soup(self._h, ntris, seed))

@@ -666,6 +666,43 @@ int bpt_upload_soup(bpt_context* c, uint32_t ntris, uint32_t seed) {
     return BPT_OK;
 }
 
+int bpt_upload_obj_arrays(bpt_context* c, const float* positions, uint32_t npositions, const int32_t* corner_vertex, uint32_t ncorners,
+                          const int32_t* face_material, const float* materials_kd_ke, uint32_t nmaterials) {
+    if (!c) return BPT_E_INVALID;
+    if (!positions || !corner_vertex || !face_material || !materials_kd_ke) return bpt_fail(c, BPT_E_INVALID, "NULL scene array");
+    if (ncorners == 0 || ncorners % 3 != 0) return bpt_fail(c, BPT_E_INVALID, "corner count %u is not a positive multiple of 3", ncorners);
+    if (npositions == 0 || nmaterials == 0) return bpt_fail(c, BPT_E_INVALID, "no positions or no materials");
+    cudaSetDevice(c->device);
+    free_scene(c);
+    const uint32_t nfaces = ncorners / 3;
+    float *d_pos = nullptr, *d_mat = nullptr;
+    int32_t *d_cv = nullptr, *d_fm = nullptr;
+    uint32_t* d_bad = nullptr;
+    uint32_t bad = 0;
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    step(cudaMalloc(&d_pos, (size_t)npositions * 12)); step(cudaMalloc(&d_mat, (size_t)nmaterials * 24));
+    step(cudaMalloc(&d_cv, (size_t)ncorners * 4)); step(cudaMalloc(&d_fm, (size_t)nfaces * 4)); step(cudaMalloc(&d_bad, 4));
+    step(cudaMalloc(&c->d_verts, (size_t)ncorners * 12)); step(cudaMalloc(&c->d_idx, (size_t)ncorners * 4));
+    step(cudaMalloc(&c->d_faces, (size_t)nfaces * 24));
+    if (e == cudaSuccess) {
+        step(cudaMemcpyAsync(d_pos, positions, (size_t)npositions * 12, cudaMemcpyHostToDevice, c->stream));
+        step(cudaMemcpyAsync(d_mat, materials_kd_ke, (size_t)nmaterials * 24, cudaMemcpyHostToDevice, c->stream));
+        step(cudaMemcpyAsync(d_cv, corner_vertex, (size_t)ncorners * 4, cudaMemcpyHostToDevice, c->stream));
+        step(cudaMemcpyAsync(d_fm, face_material, (size_t)nfaces * 4, cudaMemcpyHostToDevice, c->stream));
+        step(cudaMemsetAsync(d_bad, 0, 4, c->stream));
+        launch_obj_arrays(d_pos, npositions, d_cv, ncorners, d_fm, d_mat, nmaterials, c->d_verts, c->d_idx, c->d_faces, d_bad, c->stream);
+        step(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, c->stream));
+        step(cudaStreamSynchronize(c->stream));  // the caller's arrays may be freed after return
+        step(cudaGetLastError());
+    }
+    cudaFree(d_pos); cudaFree(d_mat); cudaFree(d_cv); cudaFree(d_fm); cudaFree(d_bad);
+    if (e != cudaSuccess) { free_scene(c); return bpt_fail_cuda(c, e, "bpt_upload_obj_arrays", __FILE__, __LINE__); }
+    if (bad) { free_scene(c); return bpt_fail(c, BPT_E_INVALID, "%u face corners / faces name a position or material that does not exist", bad); }
+    c->nverts = ncorners; c->nidx = ncorners; c->nfaces = nfaces; c->ntris = nfaces;
+    return BPT_OK;
+}
+
 int bpt_set_instances(bpt_context* c, const float* xforms3x4, uint32_t n) {
     if (!c) return BPT_E_INVALID;
     if (n == 0 || !xforms3x4) return bpt_fail(c, BPT_E_INVALID, "need at least one instance transform");

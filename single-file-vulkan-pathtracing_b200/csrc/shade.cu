@@ -425,6 +425,28 @@ __global__ void k_soup(uint32_t ntris, uint32_t seed, float scale, float* __rest
     idx[3 * (size_t)i] = 3 * i; idx[3 * (size_t)i + 1] = 3 * i + 1; idx[3 * (size_t)i + 2] = 3 * i + 2;
 }
 
+// ---------------------------------------------------------------- scene front-end (reference main.cpp:37-57)
+__global__ void k_obj_arrays(const float* __restrict__ positions, uint32_t npositions, const int32_t* __restrict__ corner_vertex,
+                             uint32_t ncorners, const int32_t* __restrict__ face_material, const float* __restrict__ materials,
+                             uint32_t nmaterials, float* __restrict__ verts, uint32_t* __restrict__ idx,
+                             float* __restrict__ faces, uint32_t* __restrict__ bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncorners) return;
+    const int32_t vi = corner_vertex[i];
+    if (vi < 0 || (uint32_t)vi >= npositions) { atomicAdd(bad, 1u); return; }
+    verts[3 * (size_t)i + 0] = positions[3 * (size_t)vi + 0];    // main.cpp:42
+    verts[3 * (size_t)i + 1] = -positions[3 * (size_t)vi + 1];   // :43 (the Y flip)
+    verts[3 * (size_t)i + 2] = positions[3 * (size_t)vi + 2];    // :44
+    idx[i] = i;                                                  // :45
+    if (i % 3u == 0u) {
+        const uint32_t f = i / 3u;
+        const int32_t m = face_material[f];
+        if (m < 0 || (uint32_t)m >= nmaterials) { atomicAdd(bad, 1u); return; }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) faces[6 * (size_t)f + k] = materials[6 * (size_t)m + k];   // :52-55
+    }
+}
+
 inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
 }  // namespace
@@ -465,6 +487,12 @@ void launch_refine_hits(const SceneView& s, const float4* rays, uint4* hits, uin
 }
 void launch_accumulate(const FrameParams& p, const int32_t* frame_dev, float4* frame_sum, float4* image, cudaStream_t st) {
     k_accumulate<<<grid_for((uint64_t)tile_local_rows(p) * p.width), kBlock, 0, st>>>(p, frame_dev, frame_sum, image);
+}
+void launch_obj_arrays(const float* positions, uint32_t npositions, const int32_t* corner_vertex, uint32_t ncorners,
+                       const int32_t* face_material, const float* materials, uint32_t nmaterials, float* verts, uint32_t* idx,
+                       float* faces, uint32_t* bad, cudaStream_t st) {
+    k_obj_arrays<<<grid_for(ncorners), kBlock, 0, st>>>(positions, npositions, corner_vertex, ncorners, face_material, materials,
+                                                        nmaterials, verts, idx, faces, bad);
 }
 void launch_soup(uint32_t ntris, uint32_t seed, float scale, float* verts, uint32_t* idx, float* faces, cudaStream_t st) {
     k_soup<<<grid_for(ntris), kBlock, 0, st>>>(ntris, seed, scale, verts, idx, faces);

@@ -86,6 +86,10 @@ void launch_nee_resolve(uint32_t depth, const uint32_t* counts, const uint4* sha
 // re-derives (u,v) of every hit from the original vertices (what k_shade does internally)
 void launch_refine_hits(const SceneView& s, const float4* rays, uint4* hits, uint32_t n, cudaStream_t st);
 void launch_accumulate(const FrameParams& p, const int32_t* frame_dev, float4* frame_sum, float4* image, cudaStream_t st);
+// the reference's loadFromFile body on the device (main.cpp:37-57); *bad counts corners / faces with an invalid reference
+void launch_obj_arrays(const float* positions, uint32_t npositions, const int32_t* corner_vertex, uint32_t ncorners,
+                       const int32_t* face_material, const float* materials, uint32_t nmaterials, float* verts, uint32_t* idx,
+                       float* faces, uint32_t* bad, cudaStream_t st);
 void launch_soup(uint32_t ntris, uint32_t seed, float scale, float* verts, uint32_t* idx, float* faces, cudaStream_t st);
 void launch_image_to_bgra8(const float4* image, uint8_t* bgra, size_t npix, cudaStream_t st);
 // rank-major (interleaved tiling) image buffer -> row-major image

@@ -33,6 +33,10 @@ def main():
         "faces_hex": [float(x).hex() for x in faces.reshape(-1)],
         "bbox_min": [float(x) for x in verts.min(0)], "bbox_max": [float(x) for x in verts.max(0)],
     }
+    pos, corner, fmat, mats = oracle_lib.ref_load_obj_raw(os.path.join(REF, "assets/CornellBox-Original.obj"),
+                                                         os.path.join(REF, "assets"))
+    out.update({"raw_positions_hex": [float(x).hex() for x in pos.reshape(-1)], "raw_corner_vertex": [int(i) for i in corner],
+                "raw_face_material": [int(i) for i in fmat], "raw_materials_hex": [float(x).hex() for x in mats.reshape(-1)]})
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cornell_scene.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=0)

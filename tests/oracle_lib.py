@@ -182,6 +182,15 @@ def load_cornell_golden():
     return verts, idx, faces, g
 
 
+def load_cornell_raw_golden():
+    """The raw tinyobj arrays of the same asset (fixture fields raw_*): positions, corner vertex indices, face material
+    ids, materials {Kd, Ke} — the input of the reference's loadFromFile body (main.cpp:37-57)."""
+    _, _, _, g = load_cornell_golden()
+    pos = np.array([float.fromhex(h) for h in g["raw_positions_hex"]], np.float32).reshape(-1, 3)
+    mats = np.array([float.fromhex(h) for h in g["raw_materials_hex"]], np.float32).reshape(-1, 6)
+    return pos, np.array(g["raw_corner_vertex"], np.int32), np.array(g["raw_face_material"], np.int32), mats
+
+
 def ref_load_obj(obj_path, mtl_dir):
     """Runs the reference's vendored tinyobjloader (oracle/_ref). Raises if the library is absent."""
     L = C.CDLL(REF_LOADER_PATH)
@@ -247,3 +256,19 @@ def ref_shade_render(verts, indices, faces, width, height, frames=1, spp=0, dept
         rays += L.ref_shade_render(_ptr(verts), _ptr(indices), len(indices), _ptr(faces), width, height, rows[0], rows[1], row_step,
                                    f, spp, depth, int(rgba8), fn, user, nthreads, _ptr(image))
     return image, int(rays)
+
+
+def ref_load_obj_raw(obj_path, mtl_dir):
+    """The raw arrays tinyobj::LoadObj gives the reference's loader (oracle/_ref): positions (n,3), the vertex index of
+    every face corner, the material id of every face, {Kd, Ke} per material."""
+    L = C.CDLL(REF_LOADER_PATH)
+    L.ref_load_obj_raw.restype = C.c_int
+    n = [C.c_uint32() for _ in range(4)]
+    args = [obj_path.encode(), mtl_dir.encode()]
+    assert L.ref_load_obj_raw(*args, None, None, None, None, *[C.byref(x) for x in n]) == 0
+    pos = np.zeros((n[0].value, 3), np.float32)
+    corner = np.zeros(n[1].value, np.int32)
+    fmat = np.zeros(n[2].value, np.int32)
+    mats = np.zeros((n[3].value, 6), np.float32)
+    assert L.ref_load_obj_raw(*args, _ptr(pos), _ptr(corner), _ptr(fmat), _ptr(mats), *[C.byref(x) for x in n]) == 0
+    return pos, corner, fmat, mats

@@ -843,3 +843,31 @@ def test_next_event_estimation(pt_cornell, cornell_oracle, soup20k):
     assert np.linalg.norm(np.mean(est["nee"], axis=0) - truth) / np.linalg.norm(truth) < 0.05
     assert noise["nee"] < 0.75 * noise["reference"], noise
     pt_cornell.clear_image()
+
+
+def test_device_side_scene_front_end(cornell, pt_cornell):
+    """bpt_upload_obj_arrays does on the device what the body of the reference's loadFromFile does on
+    the host (main.cpp:37-57: de-index, negate Y, per-face Kd/Ke) from the RAW arrays the reference's own tinyobjloader
+    returns for the shipped asset (fixture fields raw_*, generated by oracle/_ref/libref_loader.so). The resulting
+    buffers equal the reference loader's output bit for bit, and so does the image."""
+    pos, corner, fmat, mats = O.load_cornell_raw_golden()
+    verts, idx, faces = cornell
+    with bpt.PathTracer(0) as pt:
+        pt.upload_obj_arrays(pos, corner, fmat, mats)
+        gv, gi, gf = pt.download_mesh(len(fmat))
+        assert np.array_equal(gi, idx)
+        assert np.array_equal(gv.view(np.uint32), verts.view(np.uint32))
+        assert np.array_equal(gf.view(np.uint32), faces.view(np.uint32))
+        pt.build_accel()
+        img = pt.render(bpt.default_params(64, 64, 2, 4))
+        pt_cornell.clear_image()
+        assert np.array_equal(img, pt_cornell.render(bpt.default_params(64, 64, 2, 4)))
+        pt_cornell.clear_image()
+        bad = corner.copy(); bad[7] = 1000
+        with pytest.raises(bpt.BptError):
+            pt.upload_obj_arrays(pos, bad, fmat, mats)                  # a corner that names no position
+        badm = fmat.copy(); badm[3] = -1
+        with pytest.raises(bpt.BptError):
+            pt.upload_obj_arrays(pos, corner, badm, mats)               # a face without a material (main.cpp:49-51)
+        with pytest.raises(bpt.BptError):
+            pt.trace(bpt.default_params(8, 8, 1, 1))                    # a failed upload leaves no scene behind
