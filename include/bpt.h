@@ -146,6 +146,9 @@ typedef struct bpt_accel_info {
                                       samples of every tile pixel (default 2^27); results do not depend on it */
 #define BPT_OPT_BVH_OPTIMAL_COLLAPSE 7 /* 1 (default): SAH-optimal binary -> 8-wide collapse (Ylitie et al. 2017, dynamic
                                         programme); 0: greedy, largest surface area first                          */
+#define BPT_OPT_BVH_SAH_SUBTREE  12 /* quality stage of the build (stands in for ePreferFastTrace, main.cpp:419): every subtree of
+                                       the binary LBVH with at most this many triangles (3..32; default 32; 0 = plain LBVH) is
+                                       rebuilt with the full-sweep surface-area heuristic before the collapse to 8-wide nodes */
 #define BPT_OPT_TRACE_REFILL_BELOW 8     /* traversal: refill a warp when fewer lanes than this are live */
 #define BPT_OPT_TRACE_STEPS_PER_REFILL 9 /* traversal: loop iterations between two refill votes           */
 #define BPT_OPT_TRACE_STAGED_TRIS_PER_STEP 11 /* traversal of a shared-memory-staged scene: triangle tests per lane
@@ -270,6 +273,9 @@ int bpt_download_accel(bpt_context* ctx, void* records, uint32_t* rec_prim, floa
 int bpt_download_mesh(bpt_context* ctx, float* verts, uint32_t* indices, float* faces);
 /* sorted 64-bit (morton<<32 | prim) keys of the last build. */
 int bpt_download_morton(bpt_context* ctx, uint64_t* keys, uint32_t n);
+/* primitive of every leaf of the binary hierarchy, in leaf order: the sorted order of the keys, permuted inside the
+ * subtrees the SAH stage rebuilt (BPT_OPT_BVH_SAH_SUBTREE). */
+int bpt_download_leaf_order(bpt_context* ctx, uint32_t* prims, uint32_t n);
 /* binary LBVH: parent-less arrays left[n-1], right[n-1] (child >= n-1 means leaf
  * child-(n-1)), and aabbs[(2n-1)*6] (internal nodes first, then leaves). */
 int bpt_download_lbvh(bpt_context* ctx, uint32_t* left, uint32_t* right, float* aabbs);

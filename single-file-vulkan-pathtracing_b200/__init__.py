@@ -26,6 +26,7 @@ SAMPLER_UNIFORM, SAMPLER_COSINE = 0, 1
 OPT_PROFILE, OPT_COUNT_TRAVERSAL, OPT_SMEM_TOP_NODES, OPT_STREAMS = 1, 2, 3, 4
 OPT_TRACE_REFILL_BELOW, OPT_TRACE_STEPS_PER_REFILL, OPT_PASS_PATHS, OPT_TRACE_STAGED_TRIS_PER_STEP = 8, 9, 10, 11
 OPT_USE_GRAPH = 6
+OPT_BVH_SAH_SUBTREE = 12
 OPT_TRACE_BLOCK = 5
 OPT_BVH_OPTIMAL_COLLAPSE = 7
 NCCL_UNIQUE_ID_BYTES = 128
@@ -111,6 +112,7 @@ ABI = {
     "bpt_download_accel": (_i32, [_vp, _vp, _vp, _vp]),
     "bpt_download_mesh": (_i32, [_vp, _vp, _vp, _vp]),
     "bpt_download_morton": (_i32, [_vp, _vp, _u32]),
+    "bpt_download_leaf_order": (_i32, [_vp, _vp, _u32]),
     "bpt_download_lbvh": (_i32, [_vp, _vp, _vp, _vp]),
     "bpt_nccl_unique_id": (_i32, [_vp]),
     "bpt_nccl_init": (_i32, [_vp, _vp, _i32, _i32]),
@@ -334,6 +336,12 @@ class PathTracer:
         keys = np.zeros(n, np.uint64)
         self._check(self._L.bpt_download_morton(self._h, _ptr(keys), n))
         return keys
+
+    def download_leaf_order(self):
+        n = self.accel_info().num_tris
+        prims = np.zeros(n, np.uint32)
+        self._check(self._L.bpt_download_leaf_order(self._h, _ptr(prims), n))
+        return prims
 
     def download_lbvh(self):
         n = self.accel_info().num_tris

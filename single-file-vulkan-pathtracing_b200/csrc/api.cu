@@ -99,6 +99,7 @@ struct bpt_context {
     uint64_t graph_epoch = 0, epoch = 1;  // epoch moves whenever a buffer a captured graph points at may have moved
     uint64_t graph_kernel_launches = 0, graph_trace_launches = 0;
     bool optimal_collapse = true;  // BPT_OPT_BVH_OPTIMAL_COLLAPSE
+    uint32_t sah_max_leaves = 32;  // BPT_OPT_BVH_SAH_SUBTREE
     int64_t pass_paths = 1ll << 27;  // BPT_OPT_PASS_PATHS: target number of paths per sample pass
 
     // statistics
@@ -600,6 +601,11 @@ int bpt_set_option(bpt_context* c, int option, int64_t value) {
             c->optimal_collapse = value != 0;
             c->mesh_built = false;
             return BPT_OK;
+        case BPT_OPT_BVH_SAH_SUBTREE:  // takes effect at the next build of a changed mesh
+            if (value != 0 && (value < 3 || value > 32)) return bpt_fail(c, BPT_E_INVALID, "SAH subtree size must be 0 or in [3,32]");
+            c->sah_max_leaves = (uint32_t)value;
+            c->mesh_built = false;
+            return BPT_OK;
         default: return bpt_fail(c, BPT_E_INVALID, "unknown option %d", option);
     }
 }
@@ -731,6 +737,7 @@ static int build_accel_on_stream(bpt_context* c) {
     if (!c->mesh_built) {
         BPT_CUDA_TRY(c, bvh8_alloc(c->blas, c->ntris));
         c->blas.optimal_collapse = c->optimal_collapse;
+        c->blas.sah_max_leaves = c->sah_max_leaves;
         bvh8_launch_tri_bounds(c->blas, c->d_verts, c->d_idx, c->stream);
         BPT_CUDA_TRY(c, bvh8_build(c->blas, c->stream));
         if (c->blas.num_leaf_slots != c->ntris)
@@ -753,6 +760,7 @@ static int build_accel_on_stream(bpt_context* c) {
         // K8: the same builder over the instances' world boxes (main.cpp:514-538), then one node array [mesh | instances]
         BPT_CUDA_TRY(c, bvh8_alloc(c->tlas, c->ninst));
         c->tlas.optimal_collapse = c->optimal_collapse;
+        c->tlas.sah_max_leaves = c->sah_max_leaves;
         bvh8_launch_instance_bounds(c->tlas, c->d_xforms, c->blas.scene_lo, c->blas.scene_hi, c->stream);
         BPT_CUDA_TRY(c, bvh8_build(c->tlas, c->stream));
         if (c->tlas.num_leaf_slots != c->ninst)
@@ -1135,6 +1143,16 @@ int bpt_download_morton(bpt_context* c, uint64_t* keys, uint32_t n) {
     cudaSetDevice(c->device);
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     BPT_CUDA_TRY(c, cudaMemcpy(keys, c->blas.keys, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return BPT_OK;
+}
+
+int bpt_download_leaf_order(bpt_context* c, uint32_t* prims, uint32_t n) {
+    if (!c || !prims) return BPT_E_INVALID;
+    if (!c->built) return bpt_fail(c, BPT_E_STATE, "no acceleration structure built");
+    if (n != c->ntris) return bpt_fail(c, BPT_E_INVALID, "n must equal the triangle count %u", c->ntris);
+    cudaSetDevice(c->device);
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    BPT_CUDA_TRY(c, cudaMemcpy(prims, c->blas.leaf_prim, (size_t)n * 4, cudaMemcpyDeviceToHost));
     return BPT_OK;
 }
 

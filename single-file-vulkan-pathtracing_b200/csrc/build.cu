@@ -237,7 +237,7 @@ __device__ __forceinline__ void dp_internal(float* __restrict__ cost, uint8_t* _
 }
 
 // K5: leaves copy their primitive box, then climb; the second arrival at a node merges (boxes and collapse costs).
-__global__ void k_lbvh_refit(const uint64_t* __restrict__ keys, uint32_t n, const float4* __restrict__ plo,
+__global__ void k_lbvh_refit(const uint32_t* __restrict__ leaf_prim, uint32_t n, const float4* __restrict__ plo,
                              const float4* __restrict__ phi, const uint32_t* __restrict__ left,
                              const uint32_t* __restrict__ right, const uint32_t* __restrict__ parent,
                              const uint32_t* __restrict__ first, const uint32_t* __restrict__ last,
@@ -245,7 +245,7 @@ __global__ void k_lbvh_refit(const uint64_t* __restrict__ keys, uint32_t n, cons
                              float* __restrict__ dp_cost, uint8_t* __restrict__ dp_dec) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    uint32_t prim = (uint32_t)(keys[k] & 0xffffffffu);
+    uint32_t prim = leaf_prim[k];
     uint32_t node = n - 1 + k;
     float4 lo = plo[prim], hi = phi[prim];
     nlo[node] = lo;
@@ -270,7 +270,7 @@ __global__ void k_lbvh_refit(const uint64_t* __restrict__ keys, uint32_t n, cons
 // ---------------------------------------------------------------- K6: collapse to BVH8
 struct CollapseArgs {
     uint32_t n;  // primitives
-    const uint64_t* keys;
+    const uint32_t* leaf_prim;  // leaf position -> primitive
     const uint32_t *left, *right, *first, *last;
     const float4 *nlo, *nhi;
     Node8* recs;              // the record array; this kernel writes the node records
@@ -466,7 +466,7 @@ __global__ void k_bvh8_collapse(CollapseArgs a) {
             valid |= k << (2 * s);
             uint32_t f = node_first(a, cand[c]);
             for (uint32_t j = 0; j < k; ++j)
-                a.rec_prim[tri_base + leaf_off + j] = (uint32_t)(a.keys[f + j] & 0xffffffffu);
+                a.rec_prim[tri_base + leaf_off + j] = a.leaf_prim[f + j];
             leaf_off += k;
         }
     }
@@ -551,7 +551,7 @@ cudaError_t dalloc(T** p, size_t count) {
 void bvh8_free(Bvh8& b) {
     cudaFree(b.plo); cudaFree(b.phi); cudaFree(b.keys); cudaFree(b.keys_tmp); cudaFree(b.left); cudaFree(b.right);
     cudaFree(b.parent); cudaFree(b.first); cudaFree(b.last); cudaFree(b.arrive); cudaFree(b.nlo); cudaFree(b.nhi);
-    cudaFree(b.dp_cost); cudaFree(b.dp_dec);
+    cudaFree(b.dp_cost); cudaFree(b.dp_dec); cudaFree(b.leaf_prim);
     cudaFree(b.recs); cudaFree(b.wide_src); cudaFree(b.rec_prim); cudaFree(b.list[0]); cudaFree(b.list[1]);
     cudaFree(b.counters); cudaFree(b.bounds); cudaFree(b.sort_tmp);
     b = Bvh8{};
@@ -559,8 +559,12 @@ void bvh8_free(Bvh8& b) {
 
 cudaError_t bvh8_alloc(Bvh8& b, uint32_t n) {
     if (b.n == n && b.recs) return cudaSuccess;  // rebuild over the same primitive count: keep the buffers
+    const bool keep_collapse = b.optimal_collapse;
+    const uint32_t keep_sah = b.sah_max_leaves;
     bvh8_free(b);
     b.n = n;
+    b.optimal_collapse = keep_collapse;
+    b.sah_max_leaves = keep_sah;
     cudaError_t e;
 #define A(x) if ((e = (x)) != cudaSuccess) return e
     A(dalloc(&b.plo, n)); A(dalloc(&b.phi, n));
@@ -569,6 +573,7 @@ cudaError_t bvh8_alloc(Bvh8& b, uint32_t n) {
     A(dalloc(&b.parent, 2 * (size_t)n)); A(dalloc(&b.arrive, n));
     A(dalloc(&b.nlo, 2 * (size_t)n)); A(dalloc(&b.nhi, 2 * (size_t)n));
     A(dalloc(&b.dp_cost, 14 * (size_t)n)); A(dalloc(&b.dp_dec, 16 * (size_t)n));
+    A(dalloc(&b.leaf_prim, n));
     // every wide node expands at least one binary internal node, so n nodes always suffice; + n triangle records
     b.nodes_cap = n < 8 ? 8 : n;
     b.recs_cap = b.nodes_cap + n;
@@ -605,7 +610,13 @@ cudaError_t bvh8_build(Bvh8& b, cudaStream_t st) {
     if (sorted != b.keys) { uint64_t* t = b.keys; b.keys = b.keys_tmp; b.keys_tmp = t; }
     if ((e = cudaMemsetAsync(b.arrive, 0, sizeof(uint32_t) * n, st)) != cudaSuccess) return e;
     if (n > 1) k_lbvh_hierarchy<<<grid_for(n - 1), kBlock, 0, st>>>(b.keys, n, b.left, b.right, b.parent, b.first, b.last);
-    k_lbvh_refit<<<grid_for(n), kBlock, 0, st>>>(b.keys, n, b.plo, b.phi, b.left, b.right, b.parent, b.first, b.last, b.arrive,
+    sah_launch_leaf_order(b.keys, n, b.leaf_prim, st);
+    // quality stage: SAH rebuild of the subtrees with at most sah_max_leaves leaves (scratch: the level list and a spare
+    // counter, both unused until the collapse)
+    if (b.sah_max_leaves >= 3)
+        sah_launch_rebuild(n, b.sah_max_leaves, b.plo, b.phi, b.leaf_prim, b.left, b.right, b.parent, b.first, b.last,
+                           b.list[0], b.counters + 4, st);
+    k_lbvh_refit<<<grid_for(n), kBlock, 0, st>>>(b.leaf_prim, n, b.plo, b.phi, b.left, b.right, b.parent, b.first, b.last, b.arrive,
                                                  b.nlo, b.nhi, b.dp_cost, b.dp_dec);
 
     uint32_t hb[6];
@@ -631,7 +642,7 @@ cudaError_t bvh8_build(Bvh8& b, cudaStream_t st) {
     }
 
     CollapseArgs a;
-    a.n = n; a.keys = b.keys; a.left = b.left; a.right = b.right; a.first = b.first; a.last = b.last;
+    a.n = n; a.leaf_prim = b.leaf_prim; a.left = b.left; a.right = b.right; a.first = b.first; a.last = b.last;
     a.nlo = b.nlo; a.nhi = b.nhi; a.recs = b.recs; a.wide_src = b.wide_src; a.rec_prim = b.rec_prim;
     a.counters = b.counters;
     a.dp_dec = b.optimal_collapse ? b.dp_dec : nullptr;

@@ -15,6 +15,9 @@ struct Bvh8 {
     float* dp_cost = nullptr;               // optimal-collapse costs c(node, 1..7)
     uint8_t* dp_dec = nullptr;              // and choices, 8 bytes per binary node (build.cu)
     bool optimal_collapse = true;           // BPT_OPT_BVH_OPTIMAL_COLLAPSE
+    uint32_t* leaf_prim = nullptr;          // leaf position -> primitive: the sorted order, permuted inside the subtrees
+                                            // the SAH stage rebuilds (sah.cu)
+    uint32_t sah_max_leaves = 32;           // BPT_OPT_BVH_SAH_SUBTREE: 0 = plain LBVH
     // BVH8 (K6): one array of 64-byte records, nodes and triangle (instance) records interleaved
     Node8* recs = nullptr;
     uint32_t nodes_cap = 0, recs_cap = 0;
@@ -44,6 +47,12 @@ void bvh8_launch_woop(const Bvh8& b, const float* verts, const uint32_t* idx, cu
 // record array [mesh | instances] (child pointers of the instance-level nodes rebased by rec_off)
 void bvh8_launch_instance_records(const Bvh8& tlas, const float* inv_xforms, cudaStream_t st);
 void bvh8_launch_append_recs(const Bvh8& tlas, uint32_t rec_off, Node8* dst, cudaStream_t st);
+
+// sah.cu — SAH rebuild of the small subtrees of the LBVH (between K4 and K5)
+void sah_launch_leaf_order(const uint64_t* keys, uint32_t n, uint32_t* leaf_prim, cudaStream_t st);
+void sah_launch_rebuild(uint32_t n, uint32_t max_leaves, const float4* plo, const float4* phi, uint32_t* leaf_prim,
+                        uint32_t* left, uint32_t* right, uint32_t* parent, uint32_t* first, uint32_t* last, uint32_t* roots,
+                        uint32_t* nroots, cudaStream_t st);
 
 // radix_sort.cu — stable LSD radix sort of 64-bit keys on bits [begin_bit, end_bit).
 // Returns the buffer (keys or tmp) that holds the sorted result.

@@ -103,8 +103,11 @@ def check_build_invariants(pt, verts, idx):
                     stack.append(c)
         assert np.all(seen == 1)
         leaf_boxes = aabbs[n - 1:]
-        np.testing.assert_array_equal(leaf_boxes[:, :3], lo[prim_sorted])
-        np.testing.assert_array_equal(leaf_boxes[:, 3:], hi[prim_sorted])
+        # leaf order = the sorted order, permuted only inside the small subtrees the SAH stage rebuilt
+        order = pt.download_leaf_order()
+        assert np.array_equal(np.sort(order), np.arange(n, dtype=np.uint32))
+        np.testing.assert_array_equal(leaf_boxes[:, :3], lo[order])
+        np.testing.assert_array_equal(leaf_boxes[:, 3:], hi[order])
         np.testing.assert_array_equal(aabbs[0, :3], slo)
         np.testing.assert_array_equal(aabbs[0, 3:], shi)
     # K6: BVH8 — one array of 64-byte records; every triangle in exactly one triangle record; quantised child boxes
@@ -871,3 +874,41 @@ def test_device_side_scene_front_end(cornell, pt_cornell):
             pt.upload_obj_arrays(pos, corner, badm, mats)               # a face without a material (main.cpp:49-51)
         with pytest.raises(bpt.BptError):
             pt.trace(bpt.default_params(8, 8, 1, 1))                    # a failed upload leaves no scene behind
+
+
+def test_sah_subtree_stage(soup20k):
+    """the build's quality stage (BPT_OPT_BVH_SAH_SUBTREE, sah.cu) rebuilds every LBVH subtree of at
+    most 32 triangles with the surface-area heuristic. It may only permute leaves inside such a subtree (a window of
+    at most 32 positions of the Morton order), every structural invariant of the hierarchy and of the BVH8 still holds,
+    the closest hits are the same, and the traversal visits fewer nodes."""
+    verts, idx, faces, scene = soup20k
+    rays = random_rays(100_000, 31)
+    stats = {}
+    hits = {}
+    for size in (0, 32, 8):
+        with bpt.PathTracer(0) as pt:
+            pt.set_option(bpt.OPT_BVH_SAH_SUBTREE, size)
+            pt.upload_mesh(verts, idx, faces)
+            pt.build_accel()
+            check_build_invariants(pt, verts, idx)
+            keys = pt.download_morton()
+            sorted_prims = (keys & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+            order = pt.download_leaf_order()
+            if size == 0:
+                assert np.array_equal(order, sorted_prims)
+            else:
+                pos_sorted = np.empty(len(order), np.int64); pos_sorted[sorted_prims] = np.arange(len(order))
+                moved = np.abs(pos_sorted[order] - np.arange(len(order)))
+                assert moved.max() < size and (moved > 0).mean() > 0.3
+            pt.set_option(bpt.OPT_COUNT_TRAVERSAL, 1)
+            pt.reset_stats()
+            hits[size] = pt.trace_rays(rays)
+            st = pt.stats()
+            stats[size] = (st.nodes_visited / len(rays), st.tris_tested / len(rays))
+            with pytest.raises(bpt.BptError):
+                pt.set_option(bpt.OPT_BVH_SAH_SUBTREE, 64)
+    ref = scene.intersect(rays, 64)
+    for size in hits:
+        compare_hits(hits[size], ref, None, max_mismatch=5e-4)
+    print("nodes, triangles per ray by SAH subtree size:", stats)
+    assert stats[32][0] < stats[0][0] and stats[32][0] + stats[32][1] < stats[0][0] + stats[0][1]

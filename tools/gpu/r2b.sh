@@ -4,7 +4,7 @@
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 O=gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -s -p no:cacheprovider -k "shade_step or crop or text or lanes or async or host_app or roulette or next_event or front_end" > $O/r2b_pytest.txt 2>&1
+timeout 1500 python -m pytest tests -m gpu -q -s -p no:cacheprovider -k "shade_step or crop or text or lanes or async or host_app or roulette or next_event or front_end or sah or build_invariants or soup_build" > $O/r2b_pytest.txt 2>&1
 echo "pytest exit $?" >> $O/r2b_pytest.txt
 {
 for blk in 1024 256; do for lanes in 1 2; do
