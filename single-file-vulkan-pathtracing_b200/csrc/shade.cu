@@ -137,7 +137,103 @@ __global__ void k_refine_hits(SceneView s, const float4* __restrict__ rays, uint
 }
 
 // path_color[path id] collects `color` of one sample (raygen.rgen:76); k_gather_pass folds the samples of a pass into
-// the frame sum in sample order, so the result does not depend on how many samples a pass carries.
+// the frame sum in sample order, so the result does not depend on how many samples a pass carries. One path is owned
+// by one thread at a time, so the add needs no return value: a vector reduction (RED.ADD.F32x4) that the thread does
+// not wait for, instead of a load - add - store chain at the end of the dependent chain hit -> record -> shade.
+__device__ __forceinline__ void add_color(float4* path_color, uint32_t pix, V3 c) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(path_color + pix), "f"(c.x), "f"(c.y), "f"(c.z), "f"(0.0f)
+                 : "memory");
+}
+
+// What every shade kernel hands to shade_one for a path: its hit, state, path id, ray and the (object-space) shading
+// record of the primitive it hit.
+struct ShadeOut { float4 ro, rd, st; };
+// closesthit.rchit:50-65 / miss.rmiss:8-12 / raygen.rgen:76-83 for one path. Returns true when the path continues
+// (o holds its next ray and state).
+__device__ __forceinline__ bool shade_one(const FrameParams& p, const SceneView& s, uint32_t depth, uint4 h, float4 st, uint32_t pix,
+                                          float4 ro, float4 rd, float4 ra, float4 rb, float4 rc, float4 rdd, float4* path_color,
+                                          float* pdf_prev, float light_area, ShadeOut& o) {
+    V3 w{st.x, st.y, st.z};
+    uint32_t seed = __float_as_uint(st.w);
+    if (h.w == BPT_MISS) {
+        // miss.rmiss:10-11 then raygen.rgen:76 and the break at :81
+        add_color(path_color, pix, w * V3{p.sky[0], p.sky[1], p.sky[2]});
+        return false;
+    }
+    const float* m = s.xforms ? s.xforms + 12 * (size_t)(h.w / s.ntris) : nullptr;
+    const V3 v0 = xform(m, V3{ra.x, ra.y, ra.z}), v1 = xform(m, V3{ra.w, rb.x, rb.y}), v2 = xform(m, V3{rb.z, rb.w, rc.x});
+    const V3 kd{rc.y, rc.z, rc.w}, ke{rdd.x, rdd.y, rdd.z};
+    // the barycentrics that shading consumes are derived from the original vertices, so the hit position
+    // carries no traversal-format error (the traversal kernel only names the closest triangle)
+    float u, v, t = __uint_as_float(h.x);
+    barycentrics(V3{ro.x, ro.y, ro.z}, V3{rd.x, rd.y, rd.z}, v0, v1, v2, u, v, t);
+    const float b0 = 1.0f - u - v;                           // closesthit.rchit:56
+    const V3 pos = v0 * b0 + v1 * u + v2 * v;                // :57
+    const V3 nrm = -normalize(cross(v1 - v0, v2 - v0));      // :58, :43-48
+    if (ke.x != 0.0f || ke.y != 0.0f || ke.z != 0.0f) {      // raygen.rgen:76 (adding 0 is exact)
+        V3 c = w * ke;
+        if (p.nee && depth > 0u) {
+            // next-event estimation: the previous vertex sampled this emitter by area as well; balance heuristic
+            // between the pdf the bounce direction was drawn with and the area sampler's pdf for this point
+            const float cy = fabsf(dot(V3{rd.x, rd.y, rd.z}, nrm));
+            const float pl = cy > 0.0f && light_area > 0.0f ? t * t / (cy * light_area) : 0.0f;
+            const float pp = pdf_prev[pix];
+            c = c * (pp / (pp + pl));
+        }
+        add_color(path_color, pix, c);
+    }
+    if (depth + 1u >= p.max_depth) return false;             // the next segment would not be traced
+    const V3 brdf = kd / kPi;                                // closesthit.rchit:61
+    const float r1 = bpt_rand(seed);
+    const float r2 = bpt_rand(seed);                         // raygen.rgen:78
+    V3 T, B;                                                 // :14-21
+    if (fabsf(nrm.x) > fabsf(nrm.y)) T = V3{nrm.z, 0.0f, -nrm.x} / sqrtf(nrm.x * nrm.x + nrm.z * nrm.z);
+    else T = V3{0.0f, -nrm.z, nrm.y} / sqrtf(nrm.y * nrm.y + nrm.z * nrm.z);
+    B = cross(nrm, T);
+    V3 l;
+    if (p.sampler == BPT_SAMPLER_COSINE) {
+        const float sr = sqrtf(r1);
+        l = V3{cosf(kTwoPi * r2) * sr, sinf(kTwoPi * r2) * sr, sqrtf(1.0f - r1)};
+    } else {                                                 // :23-30 uniform hemisphere
+        const float sr = sqrtf(1.0f - r1 * r1);
+        l = V3{cosf(kTwoPi * r2) * sr, sinf(kTwoPi * r2) * sr, r1};
+    }
+    const V3 d = l.x * T + l.y * B + l.z * nrm;              // :38
+    if (p.nee) pdf_prev[pix] = p.sampler == BPT_SAMPLER_COSINE ? dot(d, nrm) / kPi : kPdf;
+    if (p.sampler == BPT_SAMPLER_COSINE) w = w * (brdf * kPi);
+    else w = w * (brdf * dot(d, nrm) / kPdf);                // :79-80
+    if (p.rr_start_depth && depth + 1u >= p.rr_start_depth) {   // Russian roulette (bpt.h), not the reference
+        const float q = fminf(1.0f, fmaxf(w.x, fmaxf(w.y, w.z)));
+        const float r3 = bpt_rand(seed);
+        if (!(r3 < q)) return false;
+        w = w / q;
+    }
+    o.ro = make_float4(pos.x, pos.y, pos.z, p.tmin);
+    o.rd = make_float4(d.x, d.y, d.z, p.tmax);
+    o.st = make_float4(w.x, w.y, w.z, __uint_as_float(seed));
+    return true;
+}
+
+// warp-ballot compaction of the surviving paths into the next queue: one atomic per warp
+__device__ __forceinline__ void compact_out(bool alive, const ShadeOut& o, uint32_t pix, PathQueue out, uint32_t* count_next,
+                                            unsigned lane) {
+    const unsigned live = __ballot_sync(FULL, alive);
+    if (!live) return;
+    uint32_t base = 0;
+    if (lane == (unsigned)(__ffs(live) - 1)) base = atomicAdd(count_next, (uint32_t)__popc(live));
+    base = __shfl_sync(FULL, base, __ffs(live) - 1);
+    if (alive) {
+        const uint32_t j = base + __popc(live & ((1u << lane) - 1u));
+        out.rays[2 * (size_t)j] = o.ro;
+        out.rays[2 * (size_t)j + 1] = o.rd;
+        out.state[j] = o.st;
+        out.pixel[j] = pix;
+    }
+}
+
+// Plain instance: one 256-path tile at a time per block, everything loaded where it is used. A dependent chain
+// tile counter -> hit -> shading record -> stores with nothing else in flight (measured 46 % of the HBM peak);
+// kept as the reference point of the ring instance below (BPT_OPT_SHADE_RING = 0).
 __global__ void __launch_bounds__(kBlock, 4) k_shade(FrameParams p, SceneView s, uint32_t depth, PathQueue in, const uint4* __restrict__ hits,
                         PathQueue out, uint32_t* counts, uint32_t* tile_ctr, float4* path_color, float* pdf_prev,
                         float light_area) {
@@ -149,104 +245,135 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(FrameParams p, SceneView s,
     const unsigned lane = threadIdx.x & 31u;
     __shared__ uint32_t s_tile;
     for (;;) {
-    if (threadIdx.x == 0) s_tile = atomicAdd(tile_ctr, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    __syncthreads();
-    if ((uint64_t)tile * blockDim.x >= n) break;
-    const uint32_t i = tile * blockDim.x + threadIdx.x;
-    bool alive = false;
-    float4 nro, nrd, nst;
-    uint32_t pix = 0;
-    if (i < n) {
-        const uint4 h = hits[i];
-        const float4 st = in.state[i];
-        pix = in.pixel[i];
-        V3 w{st.x, st.y, st.z};
-        uint32_t seed = __float_as_uint(st.w);
-        if (h.w == BPT_MISS) {
-            // miss.rmiss:10-11 then raygen.rgen:76 and the break at :81
-            const V3 c = w * V3{p.sky[0], p.sky[1], p.sky[2]};
-            float4 acc = path_color[pix];
-            acc.x += c.x; acc.y += c.y; acc.z += c.z;
-            path_color[pix] = acc;
-        } else {
-            const uint32_t inst = s.xforms ? h.w / s.ntris : 0u;
-            const uint32_t prim = s.xforms ? h.w - inst * s.ntris : h.w;
-            const float* m = s.xforms ? s.xforms + 12 * (size_t)inst : nullptr;
-            const ShadeRec sr = load_rec(s, prim, m);
-            const V3 v0 = sr.v0, v1 = sr.v1, v2 = sr.v2;
-            // the barycentrics that shading consumes are derived from the original vertices, so the hit position
-            // carries no traversal-format error (the traversal kernel only names the closest triangle)
-            const float4 ro = in.rays[2 * (size_t)i], rd = in.rays[2 * (size_t)i + 1];
-            float u, v, t = __uint_as_float(h.x);
-            barycentrics(V3{ro.x, ro.y, ro.z}, V3{rd.x, rd.y, rd.z}, v0, v1, v2, u, v, t);
-            const float b0 = 1.0f - u - v;                           // closesthit.rchit:56
-            const V3 pos = v0 * b0 + v1 * u + v2 * v;                // :57
-            const V3 nrm = -normalize(cross(v1 - v0, v2 - v0));      // :58, :43-48
-            const V3 kd = sr.kd, ke = sr.ke;
-            if (ke.x != 0.0f || ke.y != 0.0f || ke.z != 0.0f) {      // raygen.rgen:76 (adding 0 is exact)
-                V3 c = w * ke;
-                if (p.nee && depth > 0u) {
-                    // next-event estimation: the previous vertex sampled this emitter by area as well; balance heuristic
-                    // between the pdf the bounce direction was drawn with and the area sampler's pdf for this point
-                    const float cy = fabsf(dot(V3{rd.x, rd.y, rd.z}, nrm));
-                    const float pl = cy > 0.0f && light_area > 0.0f ? t * t / (cy * light_area) : 0.0f;
-                    const float pp = pdf_prev[pix];
-                    c = c * (pp / (pp + pl));
-                }
-                float4 acc = path_color[pix];
-                acc.x += c.x; acc.y += c.y; acc.z += c.z;
-                path_color[pix] = acc;
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_ctr, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        __syncthreads();
+        if ((uint64_t)tile * blockDim.x >= n) break;
+        const uint32_t i = tile * blockDim.x + threadIdx.x;
+        bool alive = false;
+        ShadeOut o;
+        uint32_t pix = 0;
+        if (i < n) {
+            const uint4 h = hits[i];
+            const float4 st = in.state[i];
+            pix = in.pixel[i];
+            float4 ro = make_float4(0.f, 0.f, 0.f, 0.f), rd = ro, ra = ro, rb = ro, rc = ro, rdd = ro;
+            if (h.w != BPT_MISS) {
+                const float4* r = s.srec + 4 * (size_t)(s.xforms ? h.w % s.ntris : h.w);
+                ra = __ldg(r); rb = __ldg(r + 1); rc = __ldg(r + 2); rdd = __ldg(r + 3);
+                ro = in.rays[2 * (size_t)i]; rd = in.rays[2 * (size_t)i + 1];
             }
-            if (depth + 1u < p.max_depth) {                          // the next segment will be traced
-                const V3 brdf = kd / kPi;                            // closesthit.rchit:61
-                const float r1 = bpt_rand(seed);
-                const float r2 = bpt_rand(seed);                     // raygen.rgen:78
-                V3 T, B;                                             // :14-21
-                if (fabsf(nrm.x) > fabsf(nrm.y)) T = V3{nrm.z, 0.0f, -nrm.x} / sqrtf(nrm.x * nrm.x + nrm.z * nrm.z);
-                else T = V3{0.0f, -nrm.z, nrm.y} / sqrtf(nrm.y * nrm.y + nrm.z * nrm.z);
-                B = cross(nrm, T);
-                V3 l;
-                if (p.sampler == BPT_SAMPLER_COSINE) {
-                    const float sr = sqrtf(r1);
-                    l = V3{cosf(kTwoPi * r2) * sr, sinf(kTwoPi * r2) * sr, sqrtf(1.0f - r1)};
-                } else {                                             // :23-30 uniform hemisphere
-                    const float sr = sqrtf(1.0f - r1 * r1);
-                    l = V3{cosf(kTwoPi * r2) * sr, sinf(kTwoPi * r2) * sr, r1};
-                }
-                const V3 d = l.x * T + l.y * B + l.z * nrm;          // :38
-                if (p.nee) pdf_prev[pix] = p.sampler == BPT_SAMPLER_COSINE ? dot(d, nrm) / kPi : kPdf;
-                if (p.sampler == BPT_SAMPLER_COSINE) w = w * (brdf * kPi);
-                else w = w * (brdf * dot(d, nrm) / kPdf);            // :79-80
-                alive = true;
-                if (p.rr_start_depth && depth + 1u >= p.rr_start_depth) {   // Russian roulette (bpt.h), not the reference
-                    const float q = fminf(1.0f, fmaxf(w.x, fmaxf(w.y, w.z)));
-                    const float r3 = bpt_rand(seed);
-                    if (!(r3 < q)) alive = false;
-                    else w = w / q;
-                }
-                nro = make_float4(pos.x, pos.y, pos.z, p.tmin);
-                nrd = make_float4(d.x, d.y, d.z, p.tmax);
-                nst = make_float4(w.x, w.y, w.z, __uint_as_float(seed));
+            alive = shade_one(p, s, depth, h, st, pix, ro, rd, ra, rb, rc, rdd, path_color, pdf_prev, light_area, o);
+        }
+        compact_out(alive, o, pix, out, &counts[depth + 1], lane);
+    }
+}
+
+// ---------------------------------------------------------------- K11, ring instance
+// The same work with every memory round trip of a path in flight while other paths are shaded. Each WARP streams
+// 32-path sub-tiles through a three-stage ring in shared memory filled by cp.async (LDGSTS: no registers are held while
+// the data is on its way): stage A copies hit, state and path id of sub-tile k+2; stage B, once the hit of sub-tile k+1
+// has landed, copies its ray and the shading record the hit names (the 64-byte gather); stage C shades sub-tile k out
+// of shared memory. A thread only ever reads the slots it copied itself, so cp.async.wait_group orders everything and
+// the kernel has no barrier. Sub-tiles come in chunks of 256 consecutive paths per atomic on the tile counter (the
+// next chunk is fetched a chunk ahead), which keeps the compacted output close to queue order (ray coherence of the
+// next traversal launch). 132 bytes per path and stage: 128-thread blocks x 3 stages = 50 KB, four blocks per SM.
+constexpr int kRingBlock = 128, kRingStages = 3, kRingChunk = 256;
+constexpr int kRingWarpBytes = kRingStages * (8 * 512 + 128);        // per stage: 8 float4 arrays + the path ids
+constexpr int kRingSmem = (kRingBlock / 32) * kRingWarpBytes;
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(kRingBlock, 4) k_shade_ring(FrameParams p, SceneView s, uint32_t depth, PathQueue in,
+                                                              const uint4* __restrict__ hits, PathQueue out, uint32_t* counts,
+                                                              uint32_t* tile_ctr, float4* path_color, float* pdf_prev,
+                                                              float light_area) {
+    extern __shared__ __align__(16) unsigned char ring_raw[];
+    const uint32_t n = counts[depth];
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned char* wbase = ring_raw + (threadIdx.x >> 5) * kRingWarpBytes;
+    // slot of this lane: array a (0..7: hit, state, ray o, ray d, record 0..3) of stage g
+    auto slot = [&](int g, int a) { return reinterpret_cast<float4*>(wbase + g * (8 * 512 + 128) + a * 512) + lane; };
+    auto pix_slot = [&](int g) { return reinterpret_cast<uint32_t*>(wbase + g * (8 * 512 + 128) + 8 * 512) + lane; };
+    const uint32_t nchunks = (n + kRingChunk - 1) / kRingChunk;
+
+    // the warp's stream of sub-tiles
+    uint32_t chunk = 0, next_chunk = 0, sub = kRingChunk / 32;
+    if (lane == 0) { chunk = atomicAdd(tile_ctr, 1u); next_chunk = atomicAdd(tile_ctr, 1u); }
+    chunk = __shfl_sync(FULL, chunk, 0);
+    sub = 0;
+    auto next_subtile = [&]() -> uint32_t {   // first path of the next sub-tile, or 0xffffffff when the queue is exhausted
+        if (sub == kRingChunk / 32) {
+            chunk = __shfl_sync(FULL, next_chunk, 0);
+            if (lane == 0 && chunk < nchunks) next_chunk = atomicAdd(tile_ctr, 1u);
+            sub = 0;
+        }
+        if (chunk >= nchunks) return 0xffffffffu;
+        const uint32_t base = chunk * kRingChunk + sub * 32u;
+        ++sub;
+        return base < n ? base : 0xffffffffu;
+    };
+    auto issue_a = [&](uint32_t t, int g) {   // hit, state, path id of sub-tile t into stage g
+        const uint32_t i = t + lane;
+        if (t != 0xffffffffu && i < n) {
+            cp_async16((uint32_t)__cvta_generic_to_shared(slot(g, 0)), hits + i);
+            cp_async16((uint32_t)__cvta_generic_to_shared(slot(g, 1)), in.state + i);
+            cp_async4((uint32_t)__cvta_generic_to_shared(pix_slot(g)), in.pixel + i);
+        }
+        cp_commit();
+    };
+    auto issue_b = [&](uint32_t t, int g) {   // ray and shading record of sub-tile t (its hit has landed) into stage g
+        const uint32_t i = t + lane;
+        if (t != 0xffffffffu && i < n) {
+            const uint32_t prim = reinterpret_cast<const uint4*>(slot(g, 0))->w;
+            if (prim != BPT_MISS) {
+                cp_async16((uint32_t)__cvta_generic_to_shared(slot(g, 2)), in.rays + 2 * (size_t)i);
+                cp_async16((uint32_t)__cvta_generic_to_shared(slot(g, 3)), in.rays + 2 * (size_t)i + 1);
+                const float4* r = s.srec + 4 * (size_t)(s.xforms ? prim % s.ntris : prim);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) cp_async16((uint32_t)__cvta_generic_to_shared(slot(g, 4 + q)), r + q);
             }
         }
-    }
-    // warp-ballot compaction of the surviving paths into the next queue
-    const unsigned live = __ballot_sync(FULL, alive);
-    if (live) {
-        uint32_t base = 0;
-        if (lane == (unsigned)(__ffs(live) - 1)) base = atomicAdd(&counts[depth + 1], (uint32_t)__popc(live));
-        base = __shfl_sync(FULL, base, __ffs(live) - 1);
-        if (alive) {
-            const uint32_t j = base + __popc(live & ((1u << lane) - 1u));
-            out.rays[2 * (size_t)j] = nro;
-            out.rays[2 * (size_t)j + 1] = nrd;
-            out.state[j] = nst;
-            out.pixel[j] = pix;
+        cp_commit();
+    };
+
+    uint32_t t0 = next_subtile();
+    if (t0 == 0xffffffffu) return;
+    issue_a(t0, 0);
+    uint32_t t1 = next_subtile();
+    issue_a(t1, 1);
+    cp_wait<1>();          // A(t0) has landed
+    issue_b(t0, 0);
+    int g0 = 0;            // stage of the sub-tile being shaded
+    for (;;) {
+        const int g1 = g0 == 2 ? 0 : g0 + 1, g2 = g1 == 2 ? 0 : g1 + 1;
+        const uint32_t t2 = next_subtile();
+        issue_a(t2, g2);   // pending, oldest first: A(t1) B(t0) A(t2)
+        cp_wait<2>();      // A(t1) has landed
+        issue_b(t1, g1);   // pending: B(t0) A(t2) B(t1)
+        cp_wait<2>();      // B(t0) has landed
+        const uint32_t i = t0 + lane;
+        bool alive = false;
+        ShadeOut o;
+        uint32_t pix = 0;
+        if (i < n) {
+            const uint4 h = *reinterpret_cast<const uint4*>(slot(g0, 0));
+            pix = *pix_slot(g0);
+            alive = shade_one(p, s, depth, h, *slot(g0, 1), pix, *slot(g0, 2), *slot(g0, 3), *slot(g0, 4), *slot(g0, 5), *slot(g0, 6),
+                              *slot(g0, 7), path_color, pdf_prev, light_area, o);
         }
+        compact_out(alive, o, pix, out, &counts[depth + 1], lane);
+        if (t1 == 0xffffffffu) break;   // the stream is exhausted: every later sub-tile is too
+        t0 = t1; t1 = t2; g0 = g1;
     }
-    }
+    cp_wait<0>();
 }
 
 // ---------------------------------------------------------------- next-event estimation (bpt.h; not the reference)
@@ -461,10 +588,20 @@ void launch_gather_pass(uint32_t npix, uint32_t ns, float4* path_color, float4* 
 }
 void launch_shade(const FrameParams& p, const SceneView& s, const NeeView& nv, uint32_t depth, PathQueue in, const uint4* hits,
                   PathQueue out, uint32_t* counts, uint32_t* fetch, float4* path_color, uint32_t max_paths, unsigned num_sms,
-                  cudaStream_t st) {
+                  bool ring, cudaStream_t st) {
     const unsigned full = grid_for(max_paths);
+    if (ring) {
+        // persistent warps: four 128-thread blocks per SM, fewer when the queue cannot hold a chunk per warp
+        const unsigned want = (unsigned)(((uint64_t)max_paths + kRingChunk - 1) / kRingChunk + 3u) / 4u;
+        k_shade_ring<<<std::min(std::max(want, 1u), num_sms * 4u), kRingBlock, kRingSmem, st>>>(
+            p, s, depth, in, hits, out, counts, fetch + kCounterStride + depth, path_color, nv.pdf_prev, nv.light_area);
+        return;
+    }
     k_shade<<<std::min(full, num_sms * 16u), kBlock, 0, st>>>(p, s, depth, in, hits, out, counts, fetch + kCounterStride + depth,
                                                             path_color, nv.pdf_prev, nv.light_area);
+}
+cudaError_t shade_configure() {
+    return cudaFuncSetAttribute(k_shade_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmem);
 }
 void launch_nee(const FrameParams& p, const SceneView& s, const NeeView& nv, uint32_t depth, PathQueue in, const uint4* hits,
                 const uint32_t* counts, float4* shadow_rays, float4* shadow_contrib, unsigned long long* ray_stat,
