@@ -391,7 +391,7 @@ def run_ours(args):
     for o in args.opt:
         k, v = o.split("=")
         pt.set_option(int(k), int(v))
-    lanes = 2
+    lanes = 1
     for o in args.opt:
         if o.split("=")[0] == str(bpt.OPT_STREAMS):
             lanes = int(o.split("=")[1])

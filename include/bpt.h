@@ -135,9 +135,10 @@ typedef struct bpt_accel_info {
 #define BPT_OPT_COUNT_TRAVERSAL  2 /* 1: use the instrumented traversal kernel (nodes/tris)  */
 #define BPT_OPT_SMEM_TOP_NODES   3 /* stage the whole BVH in shared memory (TMA) when it has at most
                                       this many nodes and fits (0 = never stage)             */
-#define BPT_OPT_STREAMS          4 /* sample lanes per pass (1..4, default 2): the samples of a pass are split into this many
-                                      independent wavefronts on their own CUDA streams, so the tail of one lane's persistent
-                                      traversal launch is filled by the other lanes' kernels; results do not depend on it */
+#define BPT_OPT_STREAMS          4 /* sample lanes per pass (1..4, default 1): the samples of a pass are split into this many
+                                      independent wavefronts on their own CUDA streams, so that the tail of one lane's persistent
+                                      traversal launch can be filled by the other lanes' kernels; results do not depend on it.
+                                      Measured on B200: no gain, every kernel fills the whole machine */
 #define BPT_OPT_TRACE_BLOCK      5 /* threads per traversal CTA: 1024 (one persistent CTA per SM) or 256 (four per SM, scenes in
                                       global memory only): smaller CTAs hand their SM share back earlier in a launch's tail */
 #define BPT_OPT_USE_GRAPH        6 /* 1: capture a frame's launch list as a CUDA graph and replay it while only the

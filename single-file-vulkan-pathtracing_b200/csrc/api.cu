@@ -75,7 +75,7 @@ struct bpt_context {
     size_t cap_nee = 0;
     uint32_t* counters = nullptr;            // per lane: counts[], fetch[], shade tile counters[] (kMaxDepth+1 each; shade.cuh)
     // sample lanes (BPT_OPT_STREAMS): lane 0 runs on `stream`, lane l > 0 on lane_stream[l-1], forked and joined with events
-    int num_lanes = 2;
+    int num_lanes = 1;
     cudaStream_t lane_stream[kMaxLanes - 1] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes - 1] = {nullptr, nullptr, nullptr};
     // present path: asynchronous read-back on its own stream (bpt_read_image_async)

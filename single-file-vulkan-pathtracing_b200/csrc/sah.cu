@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_sah_rebuild(uint32_t n,
             const float cen[3] = {bx.lx + bx.hx, bx.ly + bx.hy, bx.lz + bx.hz};
 #pragma unroll
             for (int axis = 0; axis < 3; ++axis) {
-                const float key = cen[axis];
+                const float key = cen[axis] == cen[axis] ? cen[axis] : 0.0f;  // a NaN would break the total order of the ranks
                 int rank = 0;
                 for (int j = s; j < e; ++j) {
                     const float kj = __shfl_sync(FULL, key, j);

@@ -741,7 +741,7 @@ def test_sample_lanes_do_not_change_the_image(pt_cornell):
     pt_cornell.clear_image()
     assert np.array_equal(pt_cornell.render(bpt.default_params(160, 96, 7, 6), frames=2), imgs[0])
     pt_cornell.set_option(bpt.OPT_USE_GRAPH, 0)
-    pt_cornell.set_option(bpt.OPT_STREAMS, 2)
+    pt_cornell.set_option(bpt.OPT_STREAMS, 1)
     with pytest.raises(bpt.BptError):
         pt_cornell.set_option(bpt.OPT_STREAMS, 5)
     pt_cornell.clear_image()
