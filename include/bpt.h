@@ -139,8 +139,6 @@ typedef struct bpt_accel_info {
                                       independent wavefronts on their own CUDA streams, so that the tail of one lane's persistent
                                       traversal launch can be filled by the other lanes' kernels; results do not depend on it.
                                       Measured on B200: no gain, every kernel fills the whole machine */
-#define BPT_OPT_TRACE_BLOCK      5 /* threads per traversal CTA: 1024 (one persistent CTA per SM) or 256 (four per SM, scenes in
-                                      global memory only): smaller CTAs hand their SM share back earlier in a launch's tail */
 #define BPT_OPT_USE_GRAPH        6 /* 1: capture a frame's launch list as a CUDA graph and replay it while only the
                                       frame index changes (pays off for launch-bound, small frames)             */
 #define BPT_OPT_PASS_PATHS       10 /* target paths per sample pass: a pass carries min(spp, this / tile pixels)

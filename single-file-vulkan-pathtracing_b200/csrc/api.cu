@@ -89,7 +89,6 @@ struct bpt_context {
     bool profile = false, count = false;
     int64_t opt_stage_max_nodes = 1 << 20;  // BPT_OPT_SMEM_TOP_NODES: 0 disables shared-memory staging
     int refill_below = 30, steps_per_refill = 2, staged_tris_per_step = 2;
-    int trace_block = kTraceBlock;  // BPT_OPT_TRACE_BLOCK
     bool shade_ring = true;         // BPT_OPT_SHADE_RING
     // BPT_OPT_USE_GRAPH: the launch list of a frame captured once as a CUDA graph and replayed while nothing but the
     // frame index changes (the kernels then read the frame index from d_frame)
@@ -357,7 +356,7 @@ void launch_trace(bpt_context* c, const TraceArgs& a, cudaStream_t st) {
         e0 = get_event(c); e1 = get_event(c);
         cudaEventRecord(e0, st);
     }
-    trace_launch(a, (unsigned)c->num_sms, c->trace_block, c->staged, c->two_level, c->count, st);
+    trace_launch(a, (unsigned)c->num_sms, c->staged, c->two_level, c->count, st);
     if (c->profile) {
         cudaEventRecord(e1, st);
         c->trace_events.emplace_back(e0, e1);
@@ -584,10 +583,6 @@ int bpt_set_option(bpt_context* c, int option, int64_t value) {
         case BPT_OPT_TRACE_STAGED_TRIS_PER_STEP:
             if (value < 1 || value > 16) return bpt_fail(c, BPT_E_INVALID, "triangle tests per step must be in [1,16]");
             c->staged_tris_per_step = (int)value;
-            return BPT_OK;
-        case BPT_OPT_TRACE_BLOCK:
-            if (value != kTraceBlock && value != kTraceBlockSmall) return bpt_fail(c, BPT_E_INVALID, "traversal CTA size must be %d or %d", kTraceBlock, kTraceBlockSmall);
-            c->trace_block = (int)value;
             return BPT_OK;
         case BPT_OPT_SHADE_RING: c->shade_ring = value != 0; return BPT_OK;
         case BPT_OPT_STREAMS:

@@ -53,6 +53,10 @@ constexpr int kLocalStack = kTraceLocalStack;
 #ifndef BPT_NODE_STEPS
 #define BPT_NODE_STEPS 1
 #endif
+// 1: barycentrics only behind the distance test (the round-1 kernel; kept for the A/B in DESIGN.md)
+#ifndef BPT_TRI_LAZY_UV
+#define BPT_TRI_LAZY_UV 0
+#endif
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---------------------------------------------------------------- TMA / mbarrier (PTX)
@@ -454,7 +458,14 @@ __global__ void __launch_bounds__(BLOCK, kTraceBlock / BLOCK) k_trace(TraceArgs 
                 float rdz;  // MUFU.RCP alone: a denormal dz (ray in the triangle's plane) gives inf / NaN, which fails the range test
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rdz) : "f"(dz));
                 const float t = -oz * rdz;
-                if (t >= r.tmin && t <= r.tbest) {
+#if BPT_TRI_LAZY_UV
+                if (t >= r.tmin && t <= r.tbest)
+#endif
+                {
+                    // u and v are evaluated for every tested triangle, not only behind the distance test: ptxas sinks the
+                    // load of the record's first half into that branch otherwise, and the warp pays a third exposed
+                    // memory round trip per iteration (10 % of all stall samples, profiles/r2b_*) for 1 lane in 6 it
+                    // spares the arithmetic
                     const float rux = __uint_as_float(w0.lo.x), ruy = __uint_as_float(w0.lo.y), ruz = __uint_as_float(w0.lo.z);
                     const float rvx = __uint_as_float(w0.hi.x), rvy = __uint_as_float(w0.hi.y), rvz = __uint_as_float(w0.hi.z);
                     const float ou = __uint_as_float(w0.lo.w) + r.ox * rux + r.oy * ruy + r.oz * ruz;
@@ -465,7 +476,7 @@ __global__ void __launch_bounds__(BLOCK, kTraceBlock / BLOCK) k_trace(TraceArgs 
                     const float v = ov + t * dv;
                     // equal distance (exact duplicate triangles): lowest primitive id wins
                     const uint32_t prim = inst_base + w1.hi.x;
-                    if (u >= 0.f && v >= 0.f && u + v <= 1.f && (t < r.tbest || prim < r.hprim)) {
+                    if (t >= r.tmin && t <= r.tbest && u >= 0.f && v >= 0.f && u + v <= 1.f && (t < r.tbest || prim < r.hprim)) {
                         r.tbest = t;
                         r.hprim = prim;
                     }
@@ -510,23 +521,17 @@ cudaError_t trace_configure() {
     CFG(kTraceBlock, false, false, false) CFG(kTraceBlock, false, false, true) CFG(kTraceBlock, true, false, false)
     CFG(kTraceBlock, true, false, true) CFG(kTraceBlock, false, true, false) CFG(kTraceBlock, false, true, true)
     CFG(kTraceBlock, true, true, false) CFG(kTraceBlock, true, true, true)
-    CFG(kTraceBlockSmall, false, false, false) CFG(kTraceBlockSmall, false, false, true)
-    CFG(kTraceBlockSmall, false, true, false) CFG(kTraceBlockSmall, false, true, true)
 #undef CFG
     return cudaSuccess;
 }
 
-void trace_launch(const TraceArgs& a, unsigned num_sms, int block, bool staged, bool two_level, bool count, cudaStream_t st) {
-    if (staged) block = kTraceBlock;  // the staged instance keeps one copy of the records per SM
-    const size_t smem = trace_smem_bytes(a.staged_recs, block);
-    const unsigned grid = num_sms * (unsigned)(kTraceBlock / block);
+void trace_launch(const TraceArgs& a, unsigned num_sms, bool staged, bool two_level, bool count, cudaStream_t st) {
+    const size_t smem = trace_smem_bytes(a.staged_recs, kTraceBlock);
+    const unsigned grid = num_sms;
 #define GO(B, S, L, C) k_trace<B, kTraceSmemStack, S, L, C><<<grid, B, smem, st>>>(a)
     if (staged) {
         if (two_level) { if (count) GO(kTraceBlock, true, true, true); else GO(kTraceBlock, true, true, false); }
         else { if (count) GO(kTraceBlock, true, false, true); else GO(kTraceBlock, true, false, false); }
-    } else if (block == kTraceBlockSmall) {
-        if (two_level) { if (count) GO(kTraceBlockSmall, false, true, true); else GO(kTraceBlockSmall, false, true, false); }
-        else { if (count) GO(kTraceBlockSmall, false, false, true); else GO(kTraceBlockSmall, false, false, false); }
     } else {
         if (two_level) { if (count) GO(kTraceBlock, false, true, true); else GO(kTraceBlock, false, true, false); }
         else { if (count) GO(kTraceBlock, false, false, true); else GO(kTraceBlock, false, false, false); }

@@ -2,8 +2,7 @@
 #pragma once
 #include "common.cuh"
 
-constexpr int kTraceBlock = 1024;      // threads per SM: one persistent CTA of 32 warps, or 4 CTAs of 8 warps (kTraceBlockSmall)
-constexpr int kTraceBlockSmall = 256;
+constexpr int kTraceBlock = 1024;      // one persistent CTA of 32 warps per SM (four CTAs of 8 warps measured -2.4 %)
 constexpr int kTraceSmemStack = 8;     // per-lane stack entries held in shared memory
 constexpr int kTraceMaxSmem = 227 * 1024;
 __host__ __device__ constexpr int trace_smem_fixed(int block) { return 16 + 2048 + block * 48; }  // mbarrier + octant permutation table + per-warp ray pools
@@ -35,7 +34,6 @@ struct TraceArgs {
     int count_rays;                // 1: add the launch's ray count to stat[RAYS] (0: shadow-ray launches, counted by k_nee)
 };
 
-// block: kTraceBlock (one CTA per SM) or kTraceBlockSmall (four per SM; global-memory instance only)
 size_t trace_smem_bytes(uint32_t staged_recs, int block = kTraceBlock);
 cudaError_t trace_configure();
-void trace_launch(const TraceArgs& a, unsigned num_sms, int block, bool staged, bool two_level, bool count, cudaStream_t st);
+void trace_launch(const TraceArgs& a, unsigned num_sms, bool staged, bool two_level, bool count, cudaStream_t st);

@@ -56,7 +56,7 @@ def test_cfg4_soup10m_4096_crop_image_parity(pt_soup10m, oracle_soup10m):
     err, bad, rg, ro = crop_parity(pt_soup10m, oracle_soup10m, 4096, 4096, (2046, 2050), 4)
     print(f"cfg4 crop: rel-L2 {err:.3e}, pixels differing {bad:.3e}, rays {rg} vs {ro}")
     assert abs(rg - ro) <= 2e-4 * ro
-    assert bad <= 2e-3 and err <= 2e-2
+    assert bad <= 2e-3 and err <= 5e-3      # measured: 1.0e-3 of the pixels differ, rel-L2 2.5e-3 at 4 spp
 
 
 def test_soup10m_closest_hits_match_the_oracle(pt_soup10m, oracle_soup10m):
@@ -155,12 +155,13 @@ def test_cfg3_soup1m_1080p_crop_image_parity():
         err, bad, rg, ro = crop_parity(pt, scene, 1920, 1080, (536, 544), 8)
     print(f"cfg3 crop: rel-L2 {err:.3e}, pixels differing {bad:.3e}, rays {rg} vs {ro}")
     assert abs(rg - ro) <= 2e-4 * ro
-    assert bad <= 2e-3 and err <= 2e-2
+    assert bad <= 2.5e-3 and err <= 5e-3    # measured: 1.2e-3 of the pixels differ, rel-L2 1.6e-3 at 8 spp
 
 
 def test_cfg5_cornell1000_2048_crop_image_parity(cornell):
     """BASELINE config 5 at its stated size — 1000 instances (10 x 10 x 10, pitch 2.5), 2048 x 2048, depth 8, camera at
-    z = 55 as bench.py frames it — rows 1020..1027 of the full launch, 32 spp (one frame of the text's constant)."""
+    z = 55 as bench.py frames it — rows 952..959 of the full launch (they cross a layer of boxes; the centre rows look
+    through the gap between two layers), 32 spp (one frame of the text's constant)."""
     n = 10
     c = 0.5 * (n - 1) * 2.5
     g = np.stack(np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij"), -1).reshape(-1, 3)
@@ -174,7 +175,8 @@ def test_cfg5_cornell1000_2048_crop_image_parity(cornell):
         pt.upload_mesh(*cornell)
         pt.set_instances(xf)
         pt.build_accel()
-        err, bad, rg, ro = crop_parity(pt, scene, 2048, 2048, (1020, 1028), 32, **cam)
+        err, bad, rg, ro = crop_parity(pt, scene, 2048, 2048, (952, 960), 32, **cam)
     print(f"cfg5 crop: rel-L2 {err:.3e}, pixels differing {bad:.3e}, rays {rg} vs {ro}")
+    assert ro > 1.5 * 2048 * 8 * 32          # the rows see the boxes, not only the sky
     assert abs(rg - ro) <= 2e-4 * ro
     assert err <= 1e-3
