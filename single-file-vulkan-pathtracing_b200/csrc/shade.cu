@@ -138,11 +138,13 @@ __global__ void k_refine_hits(SceneView s, const float4* __restrict__ rays, uint
 
 // path_color[path id] collects `color` of one sample (raygen.rgen:76); k_gather_pass folds the samples of a pass into
 // the frame sum in sample order, so the result does not depend on how many samples a pass carries. One path is owned
-// by one thread at a time, so the add needs no return value: a vector reduction (RED.ADD.F32x4) that the thread does
-// not wait for, instead of a load - add - store chain at the end of the dependent chain hit -> record -> shade.
-__device__ __forceinline__ void add_color(float4* path_color, uint32_t pix, V3 c) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(path_color + pix), "f"(c.x), "f"(c.y), "f"(c.z), "f"(0.0f)
-                 : "memory");
+// by one thread at a time: a plain load - add - store. (A vector reduction, RED.ADD.F32x4, would spare the thread the
+// wait for the load, but the L2 atomic units sustain only ~7 G of them per second: measured +20 ms per 440 M-ray frame,
+// Cornell box 12.1 -> 7.9 Gray/s.) `have`: the current value when the caller already fetched it (ring instance).
+__device__ __forceinline__ void add_color(float4* path_color, uint32_t pix, V3 c, const float4* have) {
+    float4 acc = have ? *have : path_color[pix];
+    acc.x += c.x; acc.y += c.y; acc.z += c.z;
+    path_color[pix] = acc;
 }
 
 // What every shade kernel hands to shade_one for a path: its hit, state, path id, ray and the (object-space) shading
@@ -152,12 +154,12 @@ struct ShadeOut { float4 ro, rd, st; };
 // (o holds its next ray and state).
 __device__ __forceinline__ bool shade_one(const FrameParams& p, const SceneView& s, uint32_t depth, uint4 h, float4 st, uint32_t pix,
                                           float4 ro, float4 rd, float4 ra, float4 rb, float4 rc, float4 rdd, float4* path_color,
-                                          float* pdf_prev, float light_area, ShadeOut& o) {
+                                          const float4* miss_color, float* pdf_prev, float light_area, ShadeOut& o) {
     V3 w{st.x, st.y, st.z};
     uint32_t seed = __float_as_uint(st.w);
     if (h.w == BPT_MISS) {
         // miss.rmiss:10-11 then raygen.rgen:76 and the break at :81
-        add_color(path_color, pix, w * V3{p.sky[0], p.sky[1], p.sky[2]});
+        add_color(path_color, pix, w * V3{p.sky[0], p.sky[1], p.sky[2]}, miss_color);
         return false;
     }
     const float* m = s.xforms ? s.xforms + 12 * (size_t)(h.w / s.ntris) : nullptr;
@@ -180,7 +182,7 @@ __device__ __forceinline__ bool shade_one(const FrameParams& p, const SceneView&
             const float pp = pdf_prev[pix];
             c = c * (pp / (pp + pl));
         }
-        add_color(path_color, pix, c);
+        add_color(path_color, pix, c, nullptr);
     }
     if (depth + 1u >= p.max_depth) return false;             // the next segment would not be traced
     const V3 brdf = kd / kPi;                                // closesthit.rchit:61
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(FrameParams p, SceneView s,
                 ra = __ldg(r); rb = __ldg(r + 1); rc = __ldg(r + 2); rdd = __ldg(r + 3);
                 ro = in.rays[2 * (size_t)i]; rd = in.rays[2 * (size_t)i + 1];
             }
-            alive = shade_one(p, s, depth, h, st, pix, ro, rd, ra, rb, rc, rdd, path_color, pdf_prev, light_area, o);
+            alive = shade_one(p, s, depth, h, st, pix, ro, rd, ra, rb, rc, rdd, path_color, nullptr, pdf_prev, light_area, o);
         }
         compact_out(alive, o, pix, out, &counts[depth + 1], lane);
     }
@@ -274,7 +276,8 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(FrameParams p, SceneView s,
 // The same work with every memory round trip of a path in flight while other paths are shaded. Each WARP streams
 // 32-path sub-tiles through a three-stage ring in shared memory filled by cp.async (LDGSTS: no registers are held while
 // the data is on its way): stage A copies hit, state and path id of sub-tile k+2; stage B, once the hit of sub-tile k+1
-// has landed, copies its ray and the shading record the hit names (the 64-byte gather); stage C shades sub-tile k out
+// has landed, copies its ray and the shading record the hit names (the 64-byte gather) — or, for a path that missed, the
+// colour it has collected so far, which the sky is about to be added to; stage C shades sub-tile k out
 // of shared memory. A thread only ever reads the slots it copied itself, so cp.async.wait_group orders everything and
 // the kernel has no barrier. Sub-tiles come in chunks of 256 consecutive paths per atomic on the tile counter (the
 // next chunk is fetched a chunk ahead), which keeps the compacted output close to queue order (ray coherence of the
@@ -333,7 +336,11 @@ __global__ void __launch_bounds__(kRingBlock, 4) k_shade_ring(FrameParams p, Sce
         const uint32_t i = t + lane;
         if (t != 0xffffffffu && i < n) {
             const uint32_t prim = reinterpret_cast<const uint4*>(slot(g, 0))->w;
-            if (prim != BPT_MISS) {
+            if (prim == BPT_MISS) {
+                // a path that missed ends here and adds the sky to its colour: fetch the colour so far into the slot its
+                // ray would have used
+                cp_async16((uint32_t)__cvta_generic_to_shared(slot(g, 2)), path_color + *pix_slot(g));
+            } else {
                 cp_async16((uint32_t)__cvta_generic_to_shared(slot(g, 2)), in.rays + 2 * (size_t)i);
                 cp_async16((uint32_t)__cvta_generic_to_shared(slot(g, 3)), in.rays + 2 * (size_t)i + 1);
                 const float4* r = s.srec + 4 * (size_t)(s.xforms ? prim % s.ntris : prim);
@@ -342,6 +349,26 @@ __global__ void __launch_bounds__(kRingBlock, 4) k_shade_ring(FrameParams p, Sce
             }
         }
         cp_commit();
+    };
+
+    // Compaction is pipelined as well: the atomic that reserves a sub-tile's slots in the next queue is issued when the
+    // sub-tile has been shaded, its result is read (and the survivors are stored) only after the NEXT sub-tile has
+    // been shaded — a warp that waits for the atomic's round trip after every 32 paths is what bounded the first
+    // version of this kernel (69 % of its stall samples).
+    bool r_alive = false;
+    ShadeOut r_o;
+    uint32_t r_pix = 0, r_base = 0;
+    unsigned r_live = 0;
+    auto retire = [&]() {   // store the survivors of the previously shaded sub-tile
+        if (!r_live) return;
+        const uint32_t base = __shfl_sync(FULL, r_base, __ffs(r_live) - 1);
+        if (r_alive) {
+            const uint32_t j = base + __popc(r_live & ((1u << lane) - 1u));
+            out.rays[2 * (size_t)j] = r_o.ro;
+            out.rays[2 * (size_t)j + 1] = r_o.rd;
+            out.state[j] = r_o.st;
+            out.pixel[j] = r_pix;
+        }
     };
 
     uint32_t t0 = next_subtile();
@@ -367,12 +394,16 @@ __global__ void __launch_bounds__(kRingBlock, 4) k_shade_ring(FrameParams p, Sce
             const uint4 h = *reinterpret_cast<const uint4*>(slot(g0, 0));
             pix = *pix_slot(g0);
             alive = shade_one(p, s, depth, h, *slot(g0, 1), pix, *slot(g0, 2), *slot(g0, 3), *slot(g0, 4), *slot(g0, 5), *slot(g0, 6),
-                              *slot(g0, 7), path_color, pdf_prev, light_area, o);
+                              *slot(g0, 7), path_color, slot(g0, 2), pdf_prev, light_area, o);
         }
-        compact_out(alive, o, pix, out, &counts[depth + 1], lane);
+        retire();
+        r_live = __ballot_sync(FULL, alive);
+        if (r_live && lane == (unsigned)(__ffs(r_live) - 1)) r_base = atomicAdd(&counts[depth + 1], (uint32_t)__popc(r_live));
+        r_alive = alive; r_o = o; r_pix = pix;
         if (t1 == 0xffffffffu) break;   // the stream is exhausted: every later sub-tile is too
         t0 = t1; t1 = t2; g0 = g1;
     }
+    retire();
     cp_wait<0>();
 }
 
