@@ -148,8 +148,6 @@ typedef struct bpt_accel_info {
 #define BPT_OPT_BVH_SAH_SUBTREE  12 /* quality stage of the build (stands in for ePreferFastTrace, main.cpp:419): every subtree of
                                        the binary LBVH with at most this many triangles (3..32; default 32; 0 = plain LBVH) is
                                        rebuilt with the full-sweep surface-area heuristic before the collapse to 8-wide nodes */
-#define BPT_OPT_SHADE_RING      13 /* 1 (default): the shade kernel streams its paths through a cp.async ring in shared memory
-                                       (every memory round trip of a path in flight while others are shaded); 0: plain tile loop */
 #define BPT_OPT_TRACE_REFILL_BELOW 8     /* traversal: refill a warp when fewer lanes than this are live */
 #define BPT_OPT_TRACE_STEPS_PER_REFILL 9 /* traversal: loop iterations between two refill votes           */
 #define BPT_OPT_TRACE_STAGED_TRIS_PER_STEP 11 /* traversal of a shared-memory-staged scene: triangle tests per lane

@@ -89,7 +89,6 @@ struct bpt_context {
     bool profile = false, count = false;
     int64_t opt_stage_max_nodes = 1 << 20;  // BPT_OPT_SMEM_TOP_NODES: 0 disables shared-memory staging
     int refill_below = 30, steps_per_refill = 2, staged_tris_per_step = 2;
-    bool shade_ring = true;         // BPT_OPT_SHADE_RING
     // BPT_OPT_USE_GRAPH: the launch list of a frame captured once as a CUDA graph and replayed while nothing but the
     // frame index changes (the kernels then read the frame index from d_frame)
     bool use_graph = false;
@@ -423,7 +422,7 @@ void enqueue_frame(bpt_context* c, const FrameParams& f, uint32_t npix, uint32_t
                     c->stats.kernel_launches += 2;
                 }
                 launch_shade(f, sv, nv, d, ln.q[cur], ln.hits, ln.q[cur ^ 1], ln.counts, ln.fetch, c->path_color, ln.paths,
-                             (unsigned)c->num_sms, c->shade_ring, ln.st);
+                             (unsigned)c->num_sms, ln.st);
                 c->stats.kernel_launches++;
             }
         for (uint32_t l = 1; l < L; ++l) {
@@ -523,7 +522,7 @@ int bpt_create(int device, void* stream, bpt_context** out) {
         (e = cudaMalloc(&c->counters, kMaxLanes * kLaneCounters * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&c->d_stats, BPT_STAT_COUNT * sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaMemsetAsync(c->d_stats, 0, BPT_STAT_COUNT * sizeof(unsigned long long), c->stream)) != cudaSuccess ||
-        (e = trace_configure()) != cudaSuccess || (e = shade_configure()) != cudaSuccess) {
+        (e = trace_configure()) != cudaSuccess) {
         int rc = bpt_fail(nullptr, BPT_E_CUDA, "context setup: %s", cudaGetErrorString(e));
         bpt_destroy(c);
         return rc;
@@ -584,7 +583,6 @@ int bpt_set_option(bpt_context* c, int option, int64_t value) {
             if (value < 1 || value > 16) return bpt_fail(c, BPT_E_INVALID, "triangle tests per step must be in [1,16]");
             c->staged_tris_per_step = (int)value;
             return BPT_OK;
-        case BPT_OPT_SHADE_RING: c->shade_ring = value != 0; return BPT_OK;
         case BPT_OPT_STREAMS:
             if (value < 1 || value > kMaxLanes) return bpt_fail(c, BPT_E_INVALID, "sample lanes must be in [1,%d]", kMaxLanes);
             c->num_lanes = (int)value;
@@ -1083,7 +1081,7 @@ int bpt_shade_step(bpt_context* c, const bpt_params* p, uint32_t n, const float*
     BPT_CUDA_TRY(c, cudaMemcpyAsync(counts, init, 8, cudaMemcpyHostToDevice, c->stream));          // counts[0] = n, counts[1] = 0
     BPT_CUDA_TRY(c, cudaMemcpyAsync(fetch + kCounterStride, init + 1, 4, cudaMemcpyHostToDevice, c->stream));  // tile counter of bounce 0
     launch_shade(f, SceneView{c->d_srec, c->d_xforms, c->ntris}, NeeView{nullptr, nullptr, 0u, 0.f, nullptr}, 0u, c->q[0], c->hits,
-                 c->q[1], counts, fetch, c->path_color, n, (unsigned)c->num_sms, c->shade_ring, c->stream);
+                 c->q[1], counts, fetch, c->path_color, n, (unsigned)c->num_sms, c->stream);
     uint32_t m = 0;
     std::vector<float4> col(n), orays(2 * (size_t)n), ost(n);
     BPT_CUDA_TRY(c, cudaMemcpyAsync(&m, counts + 1, 4, cudaMemcpyDeviceToHost, c->stream));

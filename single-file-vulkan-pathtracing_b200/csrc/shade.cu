@@ -140,9 +140,9 @@ __global__ void k_refine_hits(SceneView s, const float4* __restrict__ rays, uint
 // the frame sum in sample order, so the result does not depend on how many samples a pass carries. One path is owned
 // by one thread at a time: a plain load - add - store. (A vector reduction, RED.ADD.F32x4, would spare the thread the
 // wait for the load, but the L2 atomic units sustain only ~7 G of them per second: measured +20 ms per 440 M-ray frame,
-// Cornell box 12.1 -> 7.9 Gray/s.) `have`: the current value when the caller already fetched it (ring instance).
-__device__ __forceinline__ void add_color(float4* path_color, uint32_t pix, V3 c, const float4* have) {
-    float4 acc = have ? *have : path_color[pix];
+// Cornell box 12.1 -> 7.9 Gray/s.)
+__device__ __forceinline__ void add_color(float4* path_color, uint32_t pix, V3 c) {
+    float4 acc = path_color[pix];
     acc.x += c.x; acc.y += c.y; acc.z += c.z;
     path_color[pix] = acc;
 }
@@ -154,12 +154,12 @@ struct ShadeOut { float4 ro, rd, st; };
 // (o holds its next ray and state).
 __device__ __forceinline__ bool shade_one(const FrameParams& p, const SceneView& s, uint32_t depth, uint4 h, float4 st, uint32_t pix,
                                           float4 ro, float4 rd, float4 ra, float4 rb, float4 rc, float4 rdd, float4* path_color,
-                                          const float4* miss_color, float* pdf_prev, float light_area, ShadeOut& o) {
+                                          float* pdf_prev, float light_area, ShadeOut& o) {
     V3 w{st.x, st.y, st.z};
     uint32_t seed = __float_as_uint(st.w);
     if (h.w == BPT_MISS) {
         // miss.rmiss:10-11 then raygen.rgen:76 and the break at :81
-        add_color(path_color, pix, w * V3{p.sky[0], p.sky[1], p.sky[2]}, miss_color);
+        add_color(path_color, pix, w * V3{p.sky[0], p.sky[1], p.sky[2]});
         return false;
     }
     const float* m = s.xforms ? s.xforms + 12 * (size_t)(h.w / s.ntris) : nullptr;
@@ -182,7 +182,7 @@ __device__ __forceinline__ bool shade_one(const FrameParams& p, const SceneView&
             const float pp = pdf_prev[pix];
             c = c * (pp / (pp + pl));
         }
-        add_color(path_color, pix, c, nullptr);
+        add_color(path_color, pix, c);
     }
     if (depth + 1u >= p.max_depth) return false;             // the next segment would not be traced
     const V3 brdf = kd / kPi;                                // closesthit.rchit:61
@@ -233,9 +233,14 @@ __device__ __forceinline__ void compact_out(bool alive, const ShadeOut& o, uint3
     }
 }
 
-// Plain instance: one 256-path tile at a time per block, everything loaded where it is used. A dependent chain
-// tile counter -> hit -> shading record -> stores with nothing else in flight (measured 46 % of the HBM peak);
-// kept as the reference point of the ring instance below (BPT_OPT_SHADE_RING = 0).
+// One 256-path tile at a time per block, everything loaded where it is used: a dependent chain tile counter -> hit ->
+// shading record -> stores, hidden by 32 resident warps per SM. ncu (profiles/r2b_k_shade_plain_ncu_soup10m.txt):
+// 14.4 GB of DRAM traffic in 3.26 ms = 4.4 TB/s = 67 % of the measured copy bandwidth (54 % of ncu's theoretical peak),
+// issue slots 44 % busy (IEEE division / square root sequences). A cp.async ring instance (three stages per warp, every
+// load of a path in flight while others are shaded, no barriers) was built and measured in round 2: with the 50 KB of
+// shared memory per 128-thread block it runs 16 warps per SM instead of 32, which the arithmetic of a shade step
+// needs more than the loads need the ring: 3.56 ms per launch on the soup, and 4 x slower on the Cornell box
+// (profiles/r2d_*); removed again.
 __global__ void __launch_bounds__(kBlock, 4) k_shade(FrameParams p, SceneView s, uint32_t depth, PathQueue in, const uint4* __restrict__ hits,
                         PathQueue out, uint32_t* counts, uint32_t* tile_ctr, float4* path_color, float* pdf_prev,
                         float light_area) {
@@ -266,145 +271,10 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(FrameParams p, SceneView s,
                 ra = __ldg(r); rb = __ldg(r + 1); rc = __ldg(r + 2); rdd = __ldg(r + 3);
                 ro = in.rays[2 * (size_t)i]; rd = in.rays[2 * (size_t)i + 1];
             }
-            alive = shade_one(p, s, depth, h, st, pix, ro, rd, ra, rb, rc, rdd, path_color, nullptr, pdf_prev, light_area, o);
+            alive = shade_one(p, s, depth, h, st, pix, ro, rd, ra, rb, rc, rdd, path_color, pdf_prev, light_area, o);
         }
         compact_out(alive, o, pix, out, &counts[depth + 1], lane);
     }
-}
-
-// ---------------------------------------------------------------- K11, ring instance
-// The same work with every memory round trip of a path in flight while other paths are shaded. Each WARP streams
-// 32-path sub-tiles through a three-stage ring in shared memory filled by cp.async (LDGSTS: no registers are held while
-// the data is on its way): stage A copies hit, state and path id of sub-tile k+2; stage B, once the hit of sub-tile k+1
-// has landed, copies its ray and the shading record the hit names (the 64-byte gather) — or, for a path that missed, the
-// colour it has collected so far, which the sky is about to be added to; stage C shades sub-tile k out
-// of shared memory. A thread only ever reads the slots it copied itself, so cp.async.wait_group orders everything and
-// the kernel has no barrier. Sub-tiles come in chunks of 256 consecutive paths per atomic on the tile counter (the
-// next chunk is fetched a chunk ahead), which keeps the compacted output close to queue order (ray coherence of the
-// next traversal launch). 132 bytes per path and stage: 128-thread blocks x 3 stages = 50 KB, four blocks per SM.
-constexpr int kRingBlock = 128, kRingStages = 3, kRingChunk = 256;
-constexpr int kRingWarpBytes = kRingStages * (8 * 512 + 128);        // per stage: 8 float4 arrays + the path ids
-constexpr int kRingSmem = (kRingBlock / 32) * kRingWarpBytes;
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__global__ void __launch_bounds__(kRingBlock, 4) k_shade_ring(FrameParams p, SceneView s, uint32_t depth, PathQueue in,
-                                                              const uint4* __restrict__ hits, PathQueue out, uint32_t* counts,
-                                                              uint32_t* tile_ctr, float4* path_color, float* pdf_prev,
-                                                              float light_area) {
-    extern __shared__ __align__(16) unsigned char ring_raw[];
-    const uint32_t n = counts[depth];
-    const unsigned lane = threadIdx.x & 31u;
-    unsigned char* wbase = ring_raw + (threadIdx.x >> 5) * kRingWarpBytes;
-    // slot of this lane: array a (0..7: hit, state, ray o, ray d, record 0..3) of stage g
-    auto slot = [&](int g, int a) { return reinterpret_cast<float4*>(wbase + g * (8 * 512 + 128) + a * 512) + lane; };
-    auto pix_slot = [&](int g) { return reinterpret_cast<uint32_t*>(wbase + g * (8 * 512 + 128) + 8 * 512) + lane; };
-    const uint32_t nchunks = (n + kRingChunk - 1) / kRingChunk;
-
-    // the warp's stream of sub-tiles
-    uint32_t chunk = 0, next_chunk = 0, sub = kRingChunk / 32;
-    if (lane == 0) { chunk = atomicAdd(tile_ctr, 1u); next_chunk = atomicAdd(tile_ctr, 1u); }
-    chunk = __shfl_sync(FULL, chunk, 0);
-    sub = 0;
-    auto next_subtile = [&]() -> uint32_t {   // first path of the next sub-tile, or 0xffffffff when the queue is exhausted
-        if (sub == kRingChunk / 32) {
-            chunk = __shfl_sync(FULL, next_chunk, 0);
-            if (lane == 0 && chunk < nchunks) next_chunk = atomicAdd(tile_ctr, 1u);
-            sub = 0;
-        }
-        if (chunk >= nchunks) return 0xffffffffu;
-        const uint32_t base = chunk * kRingChunk + sub * 32u;
-        ++sub;
-        return base < n ? base : 0xffffffffu;
-    };
-    auto issue_a = [&](uint32_t t, int g) {   // hit, state, path id of sub-tile t into stage g
-        const uint32_t i = t + lane;
-        if (t != 0xffffffffu && i < n) {
-            cp_async16((uint32_t)__cvta_generic_to_shared(slot(g, 0)), hits + i);
-            cp_async16((uint32_t)__cvta_generic_to_shared(slot(g, 1)), in.state + i);
-            cp_async4((uint32_t)__cvta_generic_to_shared(pix_slot(g)), in.pixel + i);
-        }
-        cp_commit();
-    };
-    auto issue_b = [&](uint32_t t, int g) {   // ray and shading record of sub-tile t (its hit has landed) into stage g
-        const uint32_t i = t + lane;
-        if (t != 0xffffffffu && i < n) {
-            const uint32_t prim = reinterpret_cast<const uint4*>(slot(g, 0))->w;
-            if (prim == BPT_MISS) {
-                // a path that missed ends here and adds the sky to its colour: fetch the colour so far into the slot its
-                // ray would have used
-                cp_async16((uint32_t)__cvta_generic_to_shared(slot(g, 2)), path_color + *pix_slot(g));
-            } else {
-                cp_async16((uint32_t)__cvta_generic_to_shared(slot(g, 2)), in.rays + 2 * (size_t)i);
-                cp_async16((uint32_t)__cvta_generic_to_shared(slot(g, 3)), in.rays + 2 * (size_t)i + 1);
-                const float4* r = s.srec + 4 * (size_t)(s.xforms ? prim % s.ntris : prim);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) cp_async16((uint32_t)__cvta_generic_to_shared(slot(g, 4 + q)), r + q);
-            }
-        }
-        cp_commit();
-    };
-
-    // Compaction is pipelined as well: the atomic that reserves a sub-tile's slots in the next queue is issued when the
-    // sub-tile has been shaded, its result is read (and the survivors are stored) only after the NEXT sub-tile has
-    // been shaded — a warp that waits for the atomic's round trip after every 32 paths is what bounded the first
-    // version of this kernel (69 % of its stall samples).
-    bool r_alive = false;
-    ShadeOut r_o;
-    uint32_t r_pix = 0, r_base = 0;
-    unsigned r_live = 0;
-    auto retire = [&]() {   // store the survivors of the previously shaded sub-tile
-        if (!r_live) return;
-        const uint32_t base = __shfl_sync(FULL, r_base, __ffs(r_live) - 1);
-        if (r_alive) {
-            const uint32_t j = base + __popc(r_live & ((1u << lane) - 1u));
-            out.rays[2 * (size_t)j] = r_o.ro;
-            out.rays[2 * (size_t)j + 1] = r_o.rd;
-            out.state[j] = r_o.st;
-            out.pixel[j] = r_pix;
-        }
-    };
-
-    uint32_t t0 = next_subtile();
-    if (t0 == 0xffffffffu) return;
-    issue_a(t0, 0);
-    uint32_t t1 = next_subtile();
-    issue_a(t1, 1);
-    cp_wait<1>();          // A(t0) has landed
-    issue_b(t0, 0);
-    int g0 = 0;            // stage of the sub-tile being shaded
-    for (;;) {
-        const int g1 = g0 == 2 ? 0 : g0 + 1, g2 = g1 == 2 ? 0 : g1 + 1;
-        const uint32_t t2 = next_subtile();
-        issue_a(t2, g2);   // pending, oldest first: A(t1) B(t0) A(t2)
-        cp_wait<2>();      // A(t1) has landed
-        issue_b(t1, g1);   // pending: B(t0) A(t2) B(t1)
-        cp_wait<2>();      // B(t0) has landed
-        const uint32_t i = t0 + lane;
-        bool alive = false;
-        ShadeOut o;
-        uint32_t pix = 0;
-        if (i < n) {
-            const uint4 h = *reinterpret_cast<const uint4*>(slot(g0, 0));
-            pix = *pix_slot(g0);
-            alive = shade_one(p, s, depth, h, *slot(g0, 1), pix, *slot(g0, 2), *slot(g0, 3), *slot(g0, 4), *slot(g0, 5), *slot(g0, 6),
-                              *slot(g0, 7), path_color, slot(g0, 2), pdf_prev, light_area, o);
-        }
-        retire();
-        r_live = __ballot_sync(FULL, alive);
-        if (r_live && lane == (unsigned)(__ffs(r_live) - 1)) r_base = atomicAdd(&counts[depth + 1], (uint32_t)__popc(r_live));
-        r_alive = alive; r_o = o; r_pix = pix;
-        if (t1 == 0xffffffffu) break;   // the stream is exhausted: every later sub-tile is too
-        t0 = t1; t1 = t2; g0 = g1;
-    }
-    retire();
-    cp_wait<0>();
 }
 
 // ---------------------------------------------------------------- next-event estimation (bpt.h; not the reference)
@@ -619,21 +489,12 @@ void launch_gather_pass(uint32_t npix, uint32_t ns, float4* path_color, float4* 
 }
 void launch_shade(const FrameParams& p, const SceneView& s, const NeeView& nv, uint32_t depth, PathQueue in, const uint4* hits,
                   PathQueue out, uint32_t* counts, uint32_t* fetch, float4* path_color, uint32_t max_paths, unsigned num_sms,
-                  bool ring, cudaStream_t st) {
+                  cudaStream_t st) {
     const unsigned full = grid_for(max_paths);
-    if (ring) {
-        // persistent warps: four 128-thread blocks per SM, fewer when the queue cannot hold a chunk per warp
-        const unsigned want = (unsigned)(((uint64_t)max_paths + kRingChunk - 1) / kRingChunk + 3u) / 4u;
-        k_shade_ring<<<std::min(std::max(want, 1u), num_sms * 4u), kRingBlock, kRingSmem, st>>>(
-            p, s, depth, in, hits, out, counts, fetch + kCounterStride + depth, path_color, nv.pdf_prev, nv.light_area);
-        return;
-    }
     k_shade<<<std::min(full, num_sms * 16u), kBlock, 0, st>>>(p, s, depth, in, hits, out, counts, fetch + kCounterStride + depth,
                                                             path_color, nv.pdf_prev, nv.light_area);
 }
-cudaError_t shade_configure() {
-    return cudaFuncSetAttribute(k_shade_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmem);
-}
+
 void launch_nee(const FrameParams& p, const SceneView& s, const NeeView& nv, uint32_t depth, PathQueue in, const uint4* hits,
                 const uint32_t* counts, float4* shadow_rays, float4* shadow_contrib, unsigned long long* ray_stat,
                 uint32_t max_paths, unsigned num_sms, cudaStream_t st) {

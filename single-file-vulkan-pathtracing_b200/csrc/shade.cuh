@@ -72,9 +72,7 @@ void launch_gather_pass(uint32_t npix, uint32_t ns, float4* path_color, float4* 
 // and counted in counts[depth+1]. path_color: per-path radiance of the pass (indexed by path id).
 void launch_shade(const FrameParams& p, const SceneView& s, const NeeView& nv, uint32_t depth, PathQueue in, const uint4* hits,
                   PathQueue out, uint32_t* counts, uint32_t* fetch, float4* path_color, uint32_t max_paths, unsigned num_sms,
-                  bool ring, cudaStream_t st);  // ring: the cp.async ring instance of the kernel (default), else the plain tile loop
-// once per process: opt the ring instance of the shade kernel into its shared-memory size
-cudaError_t shade_configure();
+                  cudaStream_t st);
 // Next-event estimation, run between the traversal and the shade of bounce `depth`: for every path of `in` that hit
 // something, one shadow ray towards an area-sampled point of the emissive triangles (shadow_rays 2 x float4 per path;
 // tmax < 0 marks "no connection") and the radiance it carries if nothing is in the way (shadow_contrib); consumes three

@@ -912,31 +912,3 @@ def test_sah_subtree_stage(soup20k):
         compare_hits(hits[size], ref, None, max_mismatch=5e-4)
     print("nodes, triangles per ray by SAH subtree size:", stats)
     assert stats[32][0] < stats[0][0] and stats[32][0] + stats[32][1] < stats[0][0] + stats[0][1]
-
-
-def test_shade_ring_instance_is_bit_identical(pt_cornell, pt_instanced, soup20k):
-    """BPT_OPT_SHADE_RING: the cp.async ring instance of the shade kernel (default) and the plain tile loop produce the
-    same images bit for bit — every path's arithmetic is the same function, only the order in which paths are shaded
-    and compacted differs — on the Cornell box (incl. queue lengths that are not multiples of 32 or 256), an instanced
-    scene and a soup, with the non-reference estimators too."""
-    def both(pt, p, frames=2):
-        out = []
-        for ring in (1, 0):
-            pt.set_option(bpt.OPT_SHADE_RING, ring)
-            pt.clear_image(); pt.reset_stats()
-            out.append((pt.render(p, frames=frames).copy(), pt.stats().rays_traced))
-        pt.set_option(bpt.OPT_SHADE_RING, 1)
-        pt.clear_image()
-        assert out[0][1] == out[1][1]
-        assert np.array_equal(out[0][0], out[1][0])
-    for (w, h, spp, depth) in ((200, 120, 4, 8), (33, 7, 3, 5), (1, 1, 1, 2), (256, 256, 1, 2)):
-        both(pt_cornell, bpt.default_params(w, h, spp, depth))
-    both(pt_cornell, bpt.default_params(96, 96, 4, 8, nee=1, rr_start_depth=3, sampler=bpt.SAMPLER_COSINE))
-    both(pt_cornell, bpt.default_params(96, 96, 4, 6, accum_mode=bpt.ACCUM_RGBA8))
-    pt, xf, scene = pt_instanced
-    both(pt, bpt.default_params(128, 128, 2, 6, cam_origin=(0.0, -1.0, 14.0), cam_target=(0.0, -1.0, 11.0)))
-    verts, idx, faces, _ = soup20k
-    with bpt.PathTracer(0) as ps:
-        ps.upload_mesh(verts, idx, faces)
-        ps.build_accel()
-        both(ps, bpt.default_params(160, 100, 4, 8))
