@@ -53,11 +53,6 @@ constexpr int kLocalStack = kTraceLocalStack;
 #ifndef BPT_NODE_STEPS
 #define BPT_NODE_STEPS 1
 #endif
-// 1 (default): the record of a lane's next pending triangle is prefetched into L1 as soon as it is known — one loop
-// iteration (a node fetch and its slab tests) before it is tested
-#ifndef BPT_TRI_PREFETCH
-#define BPT_TRI_PREFETCH 1
-#endif
 // 1: barycentrics only behind the distance test (the round-1 kernel; kept for the A/B in DESIGN.md)
 #ifndef BPT_TRI_LAZY_UV
 #define BPT_TRI_LAZY_UV 0
@@ -247,7 +242,6 @@ __global__ void __launch_bounds__(BLOCK, kTraceBlock / BLOCK) k_trace(TraceArgs 
     uint2 G = make_uint2(0u, 0u);  // node group: x = first internal child, y = hits by priority << 24 | internal mask
     uint2 T = make_uint2(0u, 0u);  // triangle group: x = node the triangles belong to, y = hit bits (valid layout)
     uint32_t Tb = 0u, Tv = 0u;     // tri_base and valid word of node T.x
-    uint32_t tc = 0u;              // record of the next triangle of group T (meaningful while T.y != 0)
     uint32_t octsel = 0u;          // byte-permute selector that picks byte `oct` of a slut row into byte 3
     uint32_t inst_base = 0u;       // TWO_LEVEL: instance * mesh triangles while inside an instance
     int sp = 0;
@@ -262,18 +256,6 @@ __global__ void __launch_bounds__(BLOCK, kTraceBlock / BLOCK) k_trace(TraceArgs 
         ++sp;                                                                                     \
     }
 #define BPT_LEADER() ((__activemask() & lt) == 0u)
-    // The next triangle of group T: the highest pending slot s, its last untested triangle k; the record sits behind the
-    // node's internal children and the triangles of the lower leaf slots. Called whenever T changes; the record is
-    // prefetched so that it is in L1 when the triangle step gets to it an iteration later.
-#define BPT_PEEK_TRI()                                                                                        \
-    {                                                                                                         \
-        const uint32_t sh_ = (31u - __clz(T.y)) & ~1u;                                                        \
-        const uint32_t below_ = Tv & ~(0xffffffffu << sh_);                                                   \
-        tc = Tb + __popc(Tv & 0xff0000u) + __popc(below_ & 0x5555u) + 2u * __popc(below_ & 0xaaaau) +         \
-             ((T.y >> sh_) & 3u) - 1u;                                                                        \
-        if (!STAGED && BPT_TRI_PREFETCH)                                                                      \
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const unsigned char*>(a.recs) + (size_t)tc * BPT_REC_BYTES)); \
-    }
 
     for (;;) {
         unsigned actmask = __ballot_sync(FULL, active);
@@ -369,7 +351,6 @@ __global__ void __launch_bounds__(BLOCK, kTraceBlock / BLOCK) k_trace(TraceArgs 
                         const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(a.recs) + (size_t)e.x * BPT_REC_BYTES + 8));
                         Tv = h.x; Tb = h.y;
                     }
-                    BPT_PEEK_TRI()
                 }
             }
             // ---------------- node step
@@ -423,7 +404,6 @@ __global__ void __launch_bounds__(BLOCK, kTraceBlock / BLOCK) k_trace(TraceArgs 
                     T.x = node;
                     T.y = hit & 0xffffu;  // per hit leaf slot: how many of its triangles are still to be tested
                     Tb = v0.lo.w; Tv = valid;
-                    BPT_PEEK_TRI()
                 }
             }
 #if BPT_NODE_STEPS > 1
@@ -435,8 +415,13 @@ __global__ void __launch_bounds__(BLOCK, kTraceBlock / BLOCK) k_trace(TraceArgs 
             for (int q = 0; q < tris_per_step; ++q)  // global instance: exactly one
             if (T.y) {
                 if (COUNT) { if (BPT_LEADER()) ++cnt_wtri; ++cnt_tris; }
-                const uint32_t tri = tc;
-                T.y -= 1u << ((31u - __clz(T.y)) & ~1u);   // the triangle BPT_PEEK_TRI named is consumed
+                // highest pending slot s, its last untested triangle k; the record sits behind the node's internal
+                // children and the triangles of the lower leaf slots
+                const uint32_t sh = (31u - __clz(T.y)) & ~1u;            // 2 * s
+                const uint32_t k = ((T.y >> sh) & 3u) - 1u;
+                T.y -= 1u << sh;
+                const uint32_t below = Tv & ~(0xffffffffu << sh);        // counts of the slots below s
+                const uint32_t tri = Tb + __popc(Tv & 0xff0000u) + __popc(below & 0x5555u) + 2u * __popc(below & 0xaaaau) + k;
                 U8 w0, w1;  // w0: ru rv   w1: rw | prim - - -
                 if (STAGED) {
                     const uint32_t tp = srecs_a + tri * BPT_REC_BYTES;
@@ -497,7 +482,6 @@ __global__ void __launch_bounds__(BLOCK, kTraceBlock / BLOCK) k_trace(TraceArgs 
                     }
                 }
                 }
-                if (T.y) BPT_PEEK_TRI()  // the group's next triangle: named and prefetched an iteration ahead
             }
             // ---------------- terminate
             __syncwarp();
@@ -510,7 +494,6 @@ __global__ void __launch_bounds__(BLOCK, kTraceBlock / BLOCK) k_trace(TraceArgs 
     }
 #undef BPT_PUSH
 #undef BPT_LEADER
-#undef BPT_PEEK_TRI
     if (COUNT) {
         unsigned long long c[6] = {cnt_nodes, cnt_tris, cnt_witer, cnt_wnode, cnt_wtri, cnt_liter};
 #pragma unroll
