@@ -50,6 +50,12 @@ namespace {
 constexpr int kLocalStack = kTraceLocalStack;
 // (pop + node step) rounds per loop iteration: one triangle step, terminate test and loop overhead per BPT_NODE_STEPS
 // node steps (compile-time: even a trip-count-1 loop changes the register allocation of the kernel)
+// Experiment knob (compile time): the instance that reads its records from global memory runs BPT_TRACE_CTAS_G CTAs of
+// BPT_TRACE_BLOCK_G threads per SM instead of one CTA of 1024 (e.g. 2 x 576 = 36 warps at 56 registers per thread)
+#ifndef BPT_TRACE_BLOCK_G
+#define BPT_TRACE_BLOCK_G kTraceBlock
+#define BPT_TRACE_CTAS_G 1
+#endif
 #ifndef BPT_NODE_STEPS
 #define BPT_NODE_STEPS 1
 #endif
@@ -190,7 +196,7 @@ __device__ __forceinline__ uint32_t test_quad(uint32_t xn, uint32_t yn, uint32_t
 // state plus a sentinel, moves the ray into object space (d is NOT renormalised, so t is the same in both spaces) and
 // descends from the mesh root (node 0); popping the sentinel reloads the world-space ray.
 template <int BLOCK, int SSTACK, bool STAGED, bool TWO_LEVEL, bool COUNT>
-__global__ void __launch_bounds__(BLOCK, kTraceBlock / BLOCK) k_trace(TraceArgs a) {
+__global__ void __launch_bounds__(BLOCK, BLOCK == kTraceBlock ? 1 : BPT_TRACE_CTAS_G) k_trace(TraceArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     uint2* slut = reinterpret_cast<uint2*>(smem_raw + 16);  // byte o of slut[b]: bit p = bit (p ^ o) of b
@@ -516,25 +522,26 @@ cudaError_t trace_configure() {
     cudaError_t e;
 #define CFG(B, S, L, C)                                                                               \
     if ((e = cudaFuncSetAttribute(k_trace<B, kTraceSmemStack, S, L, C>,                                \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kTraceMaxSmem / (kTraceBlock / B))) != cudaSuccess) \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, B == kTraceBlock ? kTraceMaxSmem : kTraceMaxSmem / BPT_TRACE_CTAS_G)) != cudaSuccess) \
         return e;
-    CFG(kTraceBlock, false, false, false) CFG(kTraceBlock, false, false, true) CFG(kTraceBlock, true, false, false)
-    CFG(kTraceBlock, true, false, true) CFG(kTraceBlock, false, true, false) CFG(kTraceBlock, false, true, true)
+    CFG(BPT_TRACE_BLOCK_G, false, false, false) CFG(BPT_TRACE_BLOCK_G, false, false, true) CFG(kTraceBlock, true, false, false)
+    CFG(kTraceBlock, true, false, true) CFG(BPT_TRACE_BLOCK_G, false, true, false) CFG(BPT_TRACE_BLOCK_G, false, true, true)
     CFG(kTraceBlock, true, true, false) CFG(kTraceBlock, true, true, true)
 #undef CFG
     return cudaSuccess;
 }
 
 void trace_launch(const TraceArgs& a, unsigned num_sms, bool staged, bool two_level, bool count, cudaStream_t st) {
-    const size_t smem = trace_smem_bytes(a.staged_recs, kTraceBlock);
-    const unsigned grid = num_sms;
+    const int block = staged ? kTraceBlock : BPT_TRACE_BLOCK_G;
+    const size_t smem = trace_smem_bytes(a.staged_recs, block);
+    const unsigned grid = staged ? num_sms : num_sms * (unsigned)BPT_TRACE_CTAS_G;
 #define GO(B, S, L, C) k_trace<B, kTraceSmemStack, S, L, C><<<grid, B, smem, st>>>(a)
     if (staged) {
         if (two_level) { if (count) GO(kTraceBlock, true, true, true); else GO(kTraceBlock, true, true, false); }
         else { if (count) GO(kTraceBlock, true, false, true); else GO(kTraceBlock, true, false, false); }
     } else {
-        if (two_level) { if (count) GO(kTraceBlock, false, true, true); else GO(kTraceBlock, false, true, false); }
-        else { if (count) GO(kTraceBlock, false, false, true); else GO(kTraceBlock, false, false, false); }
+        if (two_level) { if (count) GO(BPT_TRACE_BLOCK_G, false, true, true); else GO(BPT_TRACE_BLOCK_G, false, true, false); }
+        else { if (count) GO(BPT_TRACE_BLOCK_G, false, false, true); else GO(BPT_TRACE_BLOCK_G, false, false, false); }
     }
 #undef GO
 }
