@@ -475,6 +475,12 @@ __global__ void k_obj_arrays(const float* __restrict__ positions, uint32_t nposi
     }
 }
 
+__global__ void k_check_indices(const uint32_t* __restrict__ idx, uint32_t n, uint32_t nverts, uint32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || idx[i] < nverts) return;
+    if (atomicAdd(&out[0], 1u) == 0u) out[1] = i;  // any out-of-range position serves the message
+}
+
 inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
 }  // namespace
@@ -522,6 +528,9 @@ void launch_obj_arrays(const float* positions, uint32_t npositions, const int32_
                        float* faces, uint32_t* bad, cudaStream_t st) {
     k_obj_arrays<<<grid_for(ncorners), kBlock, 0, st>>>(positions, npositions, corner_vertex, ncorners, face_material, materials,
                                                         nmaterials, verts, idx, faces, bad);
+}
+void launch_check_indices(const uint32_t* idx, uint32_t n, uint32_t nverts, uint32_t* out, cudaStream_t st) {
+    k_check_indices<<<grid_for(n), kBlock, 0, st>>>(idx, n, nverts, out);
 }
 void launch_soup(uint32_t ntris, uint32_t seed, float scale, float* verts, uint32_t* idx, float* faces, cudaStream_t st) {
     k_soup<<<grid_for(ntris), kBlock, 0, st>>>(ntris, seed, scale, verts, idx, faces);

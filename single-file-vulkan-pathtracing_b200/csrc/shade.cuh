@@ -90,6 +90,8 @@ void launch_accumulate(const FrameParams& p, const int32_t* frame_dev, float4* f
 void launch_obj_arrays(const float* positions, uint32_t npositions, const int32_t* corner_vertex, uint32_t ncorners,
                        const int32_t* face_material, const float* materials, uint32_t nmaterials, float* verts, uint32_t* idx,
                        float* faces, uint32_t* bad, cudaStream_t st);
+// out[0] = number of indices >= nverts, out[1] = position of the first one (out zeroed by the caller)
+void launch_check_indices(const uint32_t* idx, uint32_t n, uint32_t nverts, uint32_t* out, cudaStream_t st);
 void launch_soup(uint32_t ntris, uint32_t seed, float scale, float* verts, uint32_t* idx, float* faces, cudaStream_t st);
 void launch_image_to_bgra8(const float4* image, uint8_t* bgra, size_t npix, cudaStream_t st);
 // rank-major (interleaved tiling) image buffer -> row-major image
