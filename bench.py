@@ -528,8 +528,21 @@ def run_ours(args):
                 "timing": f"{KT} frames with one sample lane, CUDA events around every launch on its stream",
                 "trace_share_of_step": st.trace_kernel_ms / max(single_lane_ms, 1e-9),
                 "ms_per_step_single_lane": single_lane_ms / KT}
+    # every rank's own device-to-device copy bandwidth (1 GiB, best of 5), next to its frame times: a rank whose HBM-bound
+    # kernels (shade, generate, gather) run slower than its peers' shows here whether its memory is slower as well
+    a = torch.empty(1 << 28, dtype=torch.float32, device=f"cuda:{d.local_rank}")
+    b = torch.empty_like(a)
+    best = 0.0
+    with torch.cuda.stream(stream):
+        for _ in range(6):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream); b.copy_(a); c1.record(stream)
+            torch.cuda.synchronize()
+            best = max(best, 2.0 * a.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9)
+    del a, b
     ranks = {"frames_ms": rank_frames_ms, "timed_region_ms": rank_region_ms,
-             "frames_ms_min": min(rank_frames_ms), "frames_ms_max": max(rank_frames_ms)}
+             "frames_ms_min": min(rank_frames_ms), "frames_ms_max": max(rank_frames_ms),
+             "hbm_copy_gbs": d.gather_floats(best)}
 
     # ---- end to end through the public API with host buffers
     e2e = None

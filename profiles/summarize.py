@@ -3,7 +3,7 @@
 
     python profiles/summarize.py launches gpurun_out/launches.csv            > profiles/<tag>_launches.txt
     python profiles/summarize.py kernel   gpurun_out/prof_trace.ncu-rep      > profiles/<tag>_k_trace_ncu.txt
-    python profiles/summarize.py traffic  gpurun_out/prof_trace.ncu-rep WORKLOAD N_GPUS   (updates profiles/k_trace_traffic.json)
+    python profiles/summarize.py traffic  gpurun_out/prof_trace.ncu-rep WORKLOAD N_GPUS [OUT.json]  (updates profiles/k_trace_traffic.json)
     python profiles/summarize.py sass     single-file-vulkan-pathtracing_b200/lib/libbpt.so > profiles/k_trace.sass
 
 `traffic` averages, over ALL captured k_trace launches (capture every bounce of a frame: `-k regex:k_trace -s <first
@@ -68,7 +68,7 @@ def _num(x):
         return float("nan")
 
 
-def traffic(path, workload, n_gpus):
+def traffic(path, workload, n_gpus, out=None):
     here = os.path.dirname(os.path.abspath(__file__))
     sys.path.insert(0, os.path.dirname(here))
     import bench
@@ -95,7 +95,7 @@ def traffic(path, workload, n_gpus):
              "l2_hit_rate": wavg("lts__t_sector_hit_rate.pct"),
              "dram_pct_of_peak_ncu": wavg("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
              "per_launch": [{"ms": 1e3 * t, "dram_bytes": b} for t, b in zip(dur, dram)]}
-    out = os.path.join(here, "k_trace_traffic.json")
+    out = out or os.path.join(here, "k_trace_traffic.json")
     try:
         entries = json.load(open(out))
     except (OSError, ValueError):
