@@ -180,15 +180,16 @@ def tile_kwargs(height, nranks, rank):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons of the job's GPUs, sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
+    def __init__(self, indices):
         self.lines = []
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(i) for i in indices), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
@@ -200,28 +201,39 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm, smax, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for (t, line) in self.lines:
+    @classmethod
+    def summarise(cls, lines, t0, t1):
+        """(whole-job summary for the `clocks` key, per-GPU median SM clock and peak power)"""
+        per = {}
+        sm, smax, power, reasons = [], [], [], set()
+        for (t, line) in lines:
             if t < t0 or t > t1:
                 continue
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+                gpu, c, cmax, w = int(f[0]), float(f[1]), float(f[2]), float(f[3])
             except ValueError:
                 continue
-            for name, v in zip(names, f[3:7]):
+            sm.append(c); smax.append(cmax); power.append(w)
+            g = per.setdefault(gpu, {"sm": [], "w": []})
+            g["sm"].append(c); g["w"].append(w)
+            for name, v in zip(cls.NAMES, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        clocks = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                  "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        per_gpu = {str(g): {"sm_mhz": float(np.median(v["sm"])), "sm_mhz_min": min(v["sm"]), "power_w_max": max(v["w"])}
+                   for g, v in sorted(per.items())}
+        return clocks, per_gpu
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}, {}
+        time.sleep(0.25)
+        self.proc.terminate()
+        return self.summarise(self.lines, t0, t1)
 
 
 # ------------------------------------------------------------------------------------------ CPU legs (oracle)
@@ -427,7 +439,7 @@ def run_ours(args):
         pt.allgather_image(W, H)
     pt.sync()
     pt.reset_stats()
-    clocks = ClockSampler(d.local_rank) if d.rank == 0 else None
+    clocks = ClockSampler(range(d.world)) if d.rank == 0 else None   # one node: the job's GPUs are 0..world-1
     time.sleep(0.3 if clocks else 0.0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     d.barrier(); torch.cuda.synchronize()
@@ -450,7 +462,7 @@ def run_ours(args):
     if os.environ.get("BPT_BENCH_DEBUG"):
         print(f"[rank {d.rank}] timed region {ms_own:.2f} ms, frames {st.frame_ms:.2f} ms, rays {st.rays_traced}",
               file=sys.stderr, flush=True)
-    clk = clocks.stop(t0, t1) if clocks else None
+    clk, clk_per_gpu = clocks.stop(t0, t1) if clocks else (None, None)
     rays = d.sum(st.rays_traced)
     paths = d.sum(st.paths)
     value = rays / (ms * 1e-3) / 1e6
@@ -542,7 +554,7 @@ def run_ours(args):
     del a, b
     ranks = {"frames_ms": rank_frames_ms, "timed_region_ms": rank_region_ms,
              "frames_ms_min": min(rank_frames_ms), "frames_ms_max": max(rank_frames_ms),
-             "hbm_copy_gbs": d.gather_floats(best)}
+             "hbm_copy_gbs": d.gather_floats(best), "gpu_clocks": clk_per_gpu}
 
     # ---- end to end through the public API with host buffers
     e2e = None
