@@ -262,8 +262,8 @@ def oracle_scene(w):
     return O, O.Scene(verts, idx, faces, xforms=instance_grid(w["instances"]) if w.get("instances") else None)
 
 
-def cpu_sample_params(O, w, frame):
-    rows = min(CPU_SAMPLE_ROWS, w["height"])
+def cpu_sample_params(O, w, frame, rows_target=None):
+    rows = min(rows_target or CPU_SAMPLE_ROWS, w["height"])
     while w["height"] % rows:
         rows -= 1
     # `rows` single rows spread uniformly over the image: the interleaved tiling with 1-row blocks, rank 0
@@ -271,7 +271,7 @@ def cpu_sample_params(O, w, frame):
                             tile_nranks=w["height"] // rows, tile_rank=0, **camera_kwargs(w)), rows
 
 
-def cpu_baseline(w, steps=1, warmup=0):
+def cpu_baseline(w, steps=1, warmup=0, rows_target=None):
     """The reference's algorithm on all host cores over a bounded sample: CPU_SAMPLE_ROWS rows x full width x
     CPU_SAMPLE_SPP spp per step. kind "reference": the reference's OWN shader text compiled as C++
     (oracle/_ref/libref_shade.so, built from /root/reference/shaders where they lie) does everything the reference's
@@ -284,7 +284,7 @@ def cpu_baseline(w, steps=1, warmup=0):
     use_text = O.ref_shade_available() and not w.get("instances") and "cam_origin" not in w
     rays_total, secs = 0, 0.0
     for s in range(warmup + steps):
-        p, rows = cpu_sample_params(O, w, s)
+        p, rows = cpu_sample_params(O, w, s, rows_target)
         t0 = time.perf_counter()
         if use_text:
             _, rays = O.ref_shade_render(scene.verts, scene.indices, scene.faces, w["width"], w["height"], 1, CPU_SAMPLE_SPP,
@@ -311,7 +311,10 @@ def run_reference(args):
     if rank != 0:
         return
     w = workload_of(args)
-    base, rays, secs = cpu_baseline(w, steps=args.steps, warmup=args.warmup)
+    # the per-step sample shrinks with the number of steps so that the whole run stays within about a minute of CPU time
+    n = args.steps + args.warmup
+    rows_target = CPU_SAMPLE_ROWS if n <= 6 else max(8, CPU_SAMPLE_ROWS * 6 // n)
+    base, rays, secs = cpu_baseline(w, steps=args.steps, warmup=args.warmup, rows_target=rows_target)
     val = base["value"]
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -565,6 +568,7 @@ def run_ours(args):
         hv, hi, hf = [p.numpy() for p in pin]
         himg = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
         himg_np = himg.numpy()
+        himg2 = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()   # the presenter's second frame buffer
         pt.reset_stats()
         d.barrier(); torch.cuda.synchronize()
         tw0 = time.perf_counter()
@@ -576,7 +580,6 @@ def run_ours(args):
             pt.set_instances(instance_grid(w["instances"]))
         pt.build_accel()
         if dbg: print(f"[rank {d.rank}] +build {1e3 * (time.perf_counter() - tw0):.1f} ms", file=sys.stderr, flush=True)
-        himg2 = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
         host_frames = [himg_np, himg2.numpy()]
         for s in range(K):
             pt.trace(params(s))

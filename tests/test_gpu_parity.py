@@ -912,3 +912,41 @@ def test_sah_subtree_stage(soup20k):
         compare_hits(hits[size], ref, None, max_mismatch=5e-4)
     print("nodes, triangles per ray by SAH subtree size:", stats)
     assert stats[32][0] < stats[0][0] and stats[32][0] + stats[32][1] < stats[0][0] + stats[0][1]
+
+
+def test_hostile_meshes_do_not_break_the_build(cornell):
+    """Inputs the reference would hand to the driver without a check: triangles with NaN / infinite vertices, all
+    triangles identical, all triangles degenerate. The build (Morton keys, SAH ranks, collapse) must terminate with a
+    structure that still answers rays for the sane triangles, and must never hang or fault."""
+    verts, idx, faces = cornell
+    rays = random_rays(20_000, 41)
+    v = verts.copy()
+    v[3 * 5:3 * 5 + 3] = np.nan                      # triangle 5: NaN
+    v[3 * 9] = np.inf                                # triangle 9: one infinite vertex
+    with bpt.PathTracer(0) as pt:
+        pt.upload_mesh(v, idx, faces)
+        pt.build_accel()
+        h = pt.trace_rays(rays)
+        sane = O.Scene(np.delete(v.reshape(-1, 3, 3), [5, 9], axis=0).reshape(-1, 3), np.arange(3 * 34, dtype=np.uint32),
+                       np.delete(faces, [5, 9], axis=0))
+        ref = sane.intersect(rays, 64, brute=True)
+        hit = ref["prim"] != O.MISS
+        # every ray the sane triangles stop is stopped at the same distance (the broken ones can only add or hide nothing finite)
+        close = np.abs(h["t"][hit] - ref["t"][hit]) <= 2e-4 * (1 + ref["t"][hit])
+        assert close.mean() > 0.98
+        img = pt.render(bpt.default_params(32, 32, 2, 4))
+        assert img.shape == (32, 32, 4)
+    n = 40
+    same = np.tile(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), (n, 1))
+    f = np.tile(np.array([0.5, 0.5, 0.5, 0, 0, 0], np.float32), (n, 1))
+    for vv in (same, np.zeros_like(same)):           # 40 identical triangles; 40 degenerate ones
+        with bpt.PathTracer(0) as pt:
+            pt.upload_mesh(vv, np.arange(3 * n, dtype=np.uint32), f)
+            pt.build_accel()
+            check_build_invariants(pt, vv, np.arange(3 * n, dtype=np.uint32))
+            r = np.array([[0.2, 0.2, 1, 1e-3, 0, 0, -1, 1e4]], np.float32)
+            hh = pt.trace_rays(r)
+            if vv is same:
+                assert hh["prim"][0] == 0 and abs(hh["t"][0] - 1.0) < 1e-5   # exact duplicates: the lowest id wins
+            else:
+                assert hh["prim"][0] == O.MISS
