@@ -63,20 +63,29 @@ __device__ __forceinline__ void warp_reduce_bounds(float lo[3], float hi[3], uin
     }
 }
 
-// K1 (triangles): AABB of triangle i from the indexed vertex buffer (closesthit.rchit:52-54 layout).
+// K1 (triangles): AABB of triangle i from the indexed vertex buffer (closesthit.rchit:52-54 layout). A triangle with a
+// NaN or infinite vertex is INACTIVE, as in the Vulkan acceleration-structure build the reference calls (a NaN in the
+// first vertex component marks an inactive triangle there): it gets the empty box (lo = +max, hi = -max), which leaves
+// the scene bounds and every enclosing node box alone, quantises to an empty slab in the BVH8 and is never hit.
 __global__ void k_tri_bounds(const float* __restrict__ verts, const uint32_t* __restrict__ idx, uint32_t n,
                              float4* __restrict__ plo, float4* __restrict__ phi, uint32_t* bounds) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     if (i < n) {
+        bool finite = true;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float* v = verts + 3 * (size_t)idx[3 * (size_t)i + c];
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
+                finite = finite && isfinite(v[a]);
                 lo[a] = fminf(lo[a], v[a]);
                 hi[a] = fmaxf(hi[a], v[a]);
             }
+        }
+        if (!finite) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { lo[a] = FLT_MAX; hi[a] = -FLT_MAX; }
         }
         plo[i] = make_float4(lo[0], lo[1], lo[2], 0.f);
         phi[i] = make_float4(hi[0], hi[1], hi[2], 0.f);
@@ -182,7 +191,8 @@ __global__ void k_lbvh_hierarchy(const uint64_t* __restrict__ keys, uint32_t n, 
 // ray, 2 -> 29.3 + 5.5 and +2.4 % Mray/s, 1 -> 29.9 + 4.7 and the same speed with 17 % more nodes.
 constexpr uint32_t kMaxLeafTris = 2u;
 __device__ __forceinline__ float half_area(float4 lo, float4 hi) {
-    float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    // the empty box of an inactive primitive (hi < lo) has no area
+    float dx = fmaxf(hi.x - lo.x, 0.f), dy = fmaxf(hi.y - lo.y, 0.f), dz = fmaxf(hi.z - lo.z, 0.f);
     return dx * dy + dy * dz + dz * dx;
 }
 

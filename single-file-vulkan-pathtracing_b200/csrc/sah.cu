@@ -32,7 +32,7 @@ __device__ __forceinline__ Box box_merge(const Box& a, const Box& b) {
     return {fminf(a.lx, b.lx), fminf(a.ly, b.ly), fminf(a.lz, b.lz), fmaxf(a.hx, b.hx), fmaxf(a.hy, b.hy), fmaxf(a.hz, b.hz)};
 }
 __device__ __forceinline__ float box_half_area(const Box& b) {
-    const float dx = b.hx - b.lx, dy = b.hy - b.ly, dz = b.hz - b.lz;
+    const float dx = fmaxf(b.hx - b.lx, 0.f), dy = fmaxf(b.hy - b.ly, 0.f), dz = fmaxf(b.hz - b.lz, 0.f);  // empty box: no area
     return dx * dy + dy * dz + dz * dx;
 }
 

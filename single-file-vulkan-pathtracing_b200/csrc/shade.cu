@@ -151,7 +151,10 @@ __device__ __forceinline__ void add_color(float4* path_color, uint32_t pix, V3 c
 // record of the primitive it hit.
 struct ShadeOut { float4 ro, rd, st; };
 // closesthit.rchit:50-65 / miss.rmiss:8-12 / raygen.rgen:76-83 for one path. Returns true when the path continues
-// (o holds its next ray and state).
+// (o holds its next ray and state). EXTRA: the instance that also knows the estimators the reference does not have
+// (next-event estimation, Russian roulette); the reference's estimator runs the instance without that code (the extra
+// branches and registers cost the Cornell box 6 % of its step).
+template <bool EXTRA>
 __device__ __forceinline__ bool shade_one(const FrameParams& p, const SceneView& s, uint32_t depth, uint4 h, float4 st, uint32_t pix,
                                           float4 ro, float4 rd, float4 ra, float4 rb, float4 rc, float4 rdd, float4* path_color,
                                           float* pdf_prev, float light_area, ShadeOut& o) {
@@ -174,7 +177,7 @@ __device__ __forceinline__ bool shade_one(const FrameParams& p, const SceneView&
     const V3 nrm = -normalize(cross(v1 - v0, v2 - v0));      // :58, :43-48
     if (ke.x != 0.0f || ke.y != 0.0f || ke.z != 0.0f) {      // raygen.rgen:76 (adding 0 is exact)
         V3 c = w * ke;
-        if (p.nee && depth > 0u) {
+        if (EXTRA && p.nee && depth > 0u) {
             // next-event estimation: the previous vertex sampled this emitter by area as well; balance heuristic
             // between the pdf the bounce direction was drawn with and the area sampler's pdf for this point
             const float cy = fabsf(dot(V3{rd.x, rd.y, rd.z}, nrm));
@@ -201,10 +204,10 @@ __device__ __forceinline__ bool shade_one(const FrameParams& p, const SceneView&
         l = V3{cosf(kTwoPi * r2) * sr, sinf(kTwoPi * r2) * sr, r1};
     }
     const V3 d = l.x * T + l.y * B + l.z * nrm;              // :38
-    if (p.nee) pdf_prev[pix] = p.sampler == BPT_SAMPLER_COSINE ? dot(d, nrm) / kPi : kPdf;
+    if (EXTRA && p.nee) pdf_prev[pix] = p.sampler == BPT_SAMPLER_COSINE ? dot(d, nrm) / kPi : kPdf;
     if (p.sampler == BPT_SAMPLER_COSINE) w = w * (brdf * kPi);
     else w = w * (brdf * dot(d, nrm) / kPdf);                // :79-80
-    if (p.rr_start_depth && depth + 1u >= p.rr_start_depth) {   // Russian roulette (bpt.h), not the reference
+    if (EXTRA && p.rr_start_depth && depth + 1u >= p.rr_start_depth) {   // Russian roulette (bpt.h), not the reference
         const float q = fminf(1.0f, fmaxf(w.x, fmaxf(w.y, w.z)));
         const float r3 = bpt_rand(seed);
         if (!(r3 < q)) return false;
@@ -241,6 +244,7 @@ __device__ __forceinline__ void compact_out(bool alive, const ShadeOut& o, uint3
 // shared memory per 128-thread block it runs 16 warps per SM instead of 32, which the arithmetic of a shade step
 // needs more than the loads need the ring: 3.56 ms per launch on the soup, and 4 x slower on the Cornell box
 // (profiles/r2d_*); removed again.
+template <bool EXTRA>
 __global__ void __launch_bounds__(kBlock, 4) k_shade(FrameParams p, SceneView s, uint32_t depth, PathQueue in, const uint4* __restrict__ hits,
                         PathQueue out, uint32_t* counts, uint32_t* tile_ctr, float4* path_color, float* pdf_prev,
                         float light_area) {
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(FrameParams p, SceneView s,
                 ra = __ldg(r); rb = __ldg(r + 1); rc = __ldg(r + 2); rdd = __ldg(r + 3);
                 ro = in.rays[2 * (size_t)i]; rd = in.rays[2 * (size_t)i + 1];
             }
-            alive = shade_one(p, s, depth, h, st, pix, ro, rd, ra, rb, rc, rdd, path_color, pdf_prev, light_area, o);
+            alive = shade_one<EXTRA>(p, s, depth, h, st, pix, ro, rd, ra, rb, rc, rdd, path_color, pdf_prev, light_area, o);
         }
         compact_out(alive, o, pix, out, &counts[depth + 1], lane);
     }
@@ -497,8 +501,12 @@ void launch_shade(const FrameParams& p, const SceneView& s, const NeeView& nv, u
                   PathQueue out, uint32_t* counts, uint32_t* fetch, float4* path_color, uint32_t max_paths, unsigned num_sms,
                   cudaStream_t st) {
     const unsigned full = grid_for(max_paths);
-    k_shade<<<std::min(full, num_sms * 16u), kBlock, 0, st>>>(p, s, depth, in, hits, out, counts, fetch + kCounterStride + depth,
-                                                            path_color, nv.pdf_prev, nv.light_area);
+    if (p.nee || p.rr_start_depth)
+        k_shade<true><<<std::min(full, num_sms * 16u), kBlock, 0, st>>>(p, s, depth, in, hits, out, counts, fetch + kCounterStride + depth,
+                                                                      path_color, nv.pdf_prev, nv.light_area);
+    else
+        k_shade<false><<<std::min(full, num_sms * 16u), kBlock, 0, st>>>(p, s, depth, in, hits, out, counts, fetch + kCounterStride + depth,
+                                                                       path_color, nv.pdf_prev, nv.light_area);
 }
 
 void launch_nee(const FrameParams& p, const SceneView& s, const NeeView& nv, uint32_t depth, PathQueue in, const uint4* hits,

@@ -14,7 +14,8 @@
 //   * rays are 2 x float4, hits 1 x uint4 -> all queue traffic is 128-bit
 //   * traversal order: octant-permuted slot priority (Ylitie et al. 2017)
 //
-// What bounds it (profiles/). The kernel moves almost no DRAM bytes (L2 hit rate 83-90 %). With
+// What bounds it (profiles/). The kernel moves few DRAM bytes (3-12 % of peak from bounce 0 to 7, L2
+// hit rate 89-61 %): instruction issue binds it (74-65 % of the slots busy, ALU pipe 72-62 %). With
 // 80- and 96-byte nodes it was bound by the SM's L1 data pipe: every lane walks its own node, nothing coalesces, and
 // every 32-byte sector a lane receives costs one cycle of that pipe (82-87 % busy; a 4th sector per node visit cost
 // 23 %). With 64-byte records the bound is instruction issue (70-73 %) and the ALU pipe (PRMT/LOP3/FMNMX/SEL: half
@@ -39,6 +40,9 @@
 //     36 triangles under 6 nodes a lane has more triangles than nodes to work through; +16 % on the Cornell box)
 //   * the whole warp runs every phase of the loop behind a __syncwarp(): without it the lanes that popped and the
 //     lanes that did not reach the node step as two groups and the node step runs twice per iteration at 12/32 lanes
+//   * both halves of a triangle record are consumed in one basic block (distance and barycentrics evaluated together):
+//     with the barycentrics behind the distance test ptxas sinks the first half's load into that branch and every
+//     iteration pays a third exposed memory round trip (10 % of all stall samples; +5 % when removed)
 //   * small scenes (Cornell box, or 1000 instances of it: every record fits) run the STAGED instance: the record
 //     array is copied into shared memory once per CTA by TMA bulk copies (cp.async.bulk + mbarrier complete_tx) and
 //     never touched in global memory again; big scenes run the global instance (staging only the top of the tree was
