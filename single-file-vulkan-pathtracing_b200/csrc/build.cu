@@ -225,7 +225,8 @@ __device__ __forceinline__ void dp_internal(float* __restrict__ cost, uint8_t* _
         for (int k = 1; k < j; ++k) {
             if (k > 7 || j - k > 7) continue;
             const float c = cl[k - 1] + cr[j - k - 1];
-            if (c < best) { best = c; bk = k; }
+            // equal costs (coincident primitives): the more balanced split, or the collapse degenerates into a chain
+            if (c < best || (c == best && abs(2 * k - j) < abs(2 * bk - j))) { best = c; bk = k; }
         }
         cd[j] = best; kb[j] = (uint8_t)bk;
     }
@@ -642,11 +643,17 @@ cudaError_t bvh8_build(Bvh8& b, cudaStream_t st) {
     }
     diag = sqrtf(diag);
 
-    // scene grid of the node origins: BPT_GRID_BITS per axis over the padded scene box
+    // scene grid of the node origins: BPT_GRID_BITS per axis over the padded scene box. A node origin sits one
+    // quantisation margin (2^-7 of the node's step, and a node has ONE step for its three axes: at most 1/127 of the
+    // scene's LARGEST extent) below its box, so the grid reaches that far below the scene on every axis — also on an
+    // axis along which the scene is flat (a single quad), where the margin is far larger than the extent itself.
     const float pad = 9.5367431640625e-07f * fmaxf(diag, mag);  // 2^-20 of the scene scale
+    float smax = 0.f;
+    for (int a = 0; a < 3; ++a) smax = fmaxf(smax, b.scene_hi[a] - b.scene_lo[a]);
     for (int a = 0; a < 3; ++a) {
-        const float ext = (b.scene_hi[a] - b.scene_lo[a]) + 4.f * pad + 1e-30f;
-        b.grid_lo[a] = b.scene_lo[a] - 2.f * pad - ext * 0.001f;
+        const float below = 2.f * pad + ((b.scene_hi[a] - b.scene_lo[a]) + smax) * 0.001f;
+        const float ext = (b.scene_hi[a] - b.scene_lo[a]) + 2.f * pad + below + 1e-30f;
+        b.grid_lo[a] = b.scene_lo[a] - below;
         b.grid_step[a] = ext * 1.002f / (float)(1 << BPT_GRID_BITS);
         b.grid_bias[a] = b.grid_lo[a] - 8388608.0f * b.grid_step[a];
     }

@@ -115,14 +115,16 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_sah_rebuild(uint32_t n,
                 float cost = 3.0e38f;
                 if (in && lane < e - 1)
                     cost = box_half_area(pre) * (float)(lane - s + 1) + box_half_area(suf1) * (float)(e - 1 - lane);
-                // warp minimum, lowest position on ties
+                // warp minimum; on ties (coincident primitives) the split closest to the middle, then the lowest position
                 float c = cost;
                 int pos = lane;
+                const int mid2 = s + e - 2;  // twice the middle split position
 #pragma unroll
                 for (int d = 16; d; d >>= 1) {
                     const float oc = __shfl_xor_sync(FULL, c, d);
                     const int op = __shfl_xor_sync(FULL, pos, d);
-                    if (oc < c || (oc == c && op < pos)) { c = oc; pos = op; }
+                    const int ob = abs(2 * op - mid2), mb = abs(2 * pos - mid2);
+                    if (oc < c || (oc == c && (ob < mb || (ob == mb && op < pos)))) { c = oc; pos = op; }
                 }
                 if (c < best_cost) { best_cost = c; best_pos = pos; rank_keep = rank; }
             }
