@@ -54,7 +54,7 @@ extern "C" {
  *   nee = 1 : next-event estimation. At every hit whose next segment would be traced, one point on the emissive
  *       triangles (Ke != 0; chosen with probability proportional to area, uniform on the triangle: three rand(seed)
  *       before the two of the bounce) is connected by a shadow ray; Ke of a triangle hit by a BOUNCE ray is then not
- *       added again (camera rays still add it). Single-level scenes only. */
+ *       added again (camera rays still add it). Instanced scenes: every instance of an emissive triangle is a light. */
 
 typedef struct bpt_context bpt_context; /* opaque; owns all device memory */
 

@@ -206,23 +206,34 @@ int build_light_table(bpt_context* c) {
     BPT_CUDA_TRY(c, cudaMemcpy(verts.data(), c->d_verts, verts.size() * 4, cudaMemcpyDeviceToHost));
     BPT_CUDA_TRY(c, cudaMemcpy(idx.data(), c->d_idx, idx.size() * 4, cudaMemcpyDeviceToHost));
     BPT_CUDA_TRY(c, cudaMemcpy(faces.data(), c->d_faces, faces.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<float> xf;
+    if (c->d_xforms) {
+        xf.resize(12 * (size_t)c->ninst);
+        BPT_CUDA_TRY(c, cudaMemcpy(xf.data(), c->d_xforms, xf.size() * 4, cudaMemcpyDeviceToHost));
+    }
     std::vector<uint32_t> prims;
     std::vector<double> cum;
     double total = 0.0;
-    for (uint32_t t = 0; t < c->ntris; ++t) {
-        const float* f = &faces[6 * (size_t)t];
-        if (f[3] == 0.0f && f[4] == 0.0f && f[5] == 0.0f) continue;
-        const float* a = &verts[3 * (size_t)idx[3 * (size_t)t]];
-        const float* b = &verts[3 * (size_t)idx[3 * (size_t)t + 1]];
-        const float* d = &verts[3 * (size_t)idx[3 * (size_t)t + 2]];
-        const double e1[3] = {(double)b[0] - a[0], (double)b[1] - a[1], (double)b[2] - a[2]};
-        const double e2[3] = {(double)d[0] - a[0], (double)d[1] - a[1], (double)d[2] - a[2]};
-        const double x[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
-        const double area = 0.5 * std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-        if (!(area > 0.0)) continue;
-        total += area;
-        prims.push_back(t);
-        cum.push_back(total);
+    const uint32_t ninst = c->d_xforms ? c->ninst : 1u;
+    for (uint32_t inst = 0; inst < ninst; ++inst) {
+        const float* m = c->d_xforms ? &xf[12 * (size_t)inst] : nullptr;
+        for (uint32_t t = 0; t < c->ntris; ++t) {
+            const float* f = &faces[6 * (size_t)t];
+            if (f[3] == 0.0f && f[4] == 0.0f && f[5] == 0.0f) continue;
+            float w[3][3];  // world-space vertices as shading sees them: float, x' = m0*x + m1*y + m2*z + m3, left to right
+            for (int k = 0; k < 3; ++k) {
+                const float* v = &verts[3 * (size_t)idx[3 * (size_t)t + k]];
+                for (int r = 0; r < 3; ++r) w[k][r] = m ? m[4 * r] * v[0] + m[4 * r + 1] * v[1] + m[4 * r + 2] * v[2] + m[4 * r + 3] : v[r];
+            }
+            const double e1[3] = {(double)w[1][0] - w[0][0], (double)w[1][1] - w[0][1], (double)w[1][2] - w[0][2]};
+            const double e2[3] = {(double)w[2][0] - w[0][0], (double)w[2][1] - w[0][1], (double)w[2][2] - w[0][2]};
+            const double x[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+            const double area = 0.5 * std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+            if (!(area > 0.0)) continue;
+            total += area;
+            prims.push_back(inst * c->ntris + t);
+            cum.push_back(total);
+        }
     }
     std::vector<float> cdf(cum.size());
     for (size_t i = 0; i < cum.size(); ++i) cdf[i] = (float)(cum[i] / total);
@@ -717,6 +728,7 @@ int bpt_set_instances(bpt_context* c, const float* xforms3x4, uint32_t n) {
     cudaFree(c->d_xforms); cudaFree(c->d_xforms_inv);
     c->d_xforms = nullptr; c->d_xforms_inv = nullptr;
     c->built = false;
+    c->lights_built = false;
     BPT_CUDA_TRY(c, cudaMalloc(&c->d_xforms, 48 * (size_t)n));
     BPT_CUDA_TRY(c, cudaMalloc(&c->d_xforms_inv, 48 * (size_t)n));
     BPT_CUDA_TRY(c, cudaMemcpyAsync(c->d_xforms, xforms3x4, 48 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
@@ -831,7 +843,6 @@ int bpt_trace(bpt_context* c, const bpt_params* p) {
     if ((rc = ensure_frame_sum(c, npix)) != BPT_OK) return rc;
     if ((rc = ensure_image(c, f.width, f.height)) != BPT_OK) return rc;
     if (f.nee) {
-        if (c->two_level) return bpt_fail(c, BPT_E_INVALID, "next-event estimation supports single-level scenes only");
         if ((rc = build_light_table(c)) != BPT_OK) return rc;
         if ((rc = ensure_nee(c)) != BPT_OK) return rc;
     }

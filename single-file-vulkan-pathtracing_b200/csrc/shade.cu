@@ -298,7 +298,8 @@ __global__ void __launch_bounds__(kBlock) k_nee(FrameParams p, SceneView s, NeeV
             const float4 st = in.state[i];
             uint32_t seed = __float_as_uint(st.w);
             const V3 w{st.x, st.y, st.z};
-            const ShadeRec sr = load_rec(s, h.w, nullptr);
+            // instanced scenes: world primitive id = instance * ntris + triangle, vertices through the instance matrix
+            const ShadeRec sr = load_rec(s, s.xforms ? h.w % s.ntris : h.w, s.xforms ? s.xforms + 12 * (size_t)(h.w / s.ntris) : nullptr);
             const float4 ro = in.rays[2 * (size_t)i], rd = in.rays[2 * (size_t)i + 1];
             float u, v, t = __uint_as_float(h.x);
             barycentrics(V3{ro.x, ro.y, ro.z}, V3{rd.x, rd.y, rd.z}, sr.v0, sr.v1, sr.v2, u, v, t);
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(kBlock) k_nee(FrameParams p, SceneView s, NeeV
                 if (__ldg(nv.light_cdf + mid) > rs) hi = mid; else lo = mid + 1u;
             }
             const uint32_t lp = __ldg(nv.light_prims + lo);
-            const ShadeRec lr = load_rec(s, lp, nullptr);
+            const ShadeRec lr = load_rec(s, s.xforms ? lp % s.ntris : lp, s.xforms ? s.xforms + 12 * (size_t)(lp / s.ntris) : nullptr);
             const float su = sqrtf(ra);
             const float bu = su * (1.0f - rb), bv = su * rb, lb0 = 1.0f - bu - bv;
             const V3 y = lr.v0 * lb0 + lr.v1 * bu + lr.v2 * bv;

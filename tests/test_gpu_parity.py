@@ -827,9 +827,17 @@ def test_next_event_estimation(pt_cornell, cornell_oracle, soup20k):
         img = pt.render(bpt.default_params(96, 96, 4, 6, nee=1))
         ref, _ = scene.render(O.default_params(96, 96, 4, 6, nee=1), 32)
         assert O.rel_l2(img, ref) <= 2e-3
-        pt.set_instances(np.eye(3, 4, dtype=np.float32).reshape(1, 12)); pt.build_accel()
-        with pytest.raises(bpt.BptError):
-            pt.trace(bpt.default_params(8, 8, 1, 2, nee=1))          # single-level scenes only
+    # instanced scene: 27 rotated / scaled / translated boxes, 54 lights
+    xf = instance_grid()
+    cam = dict(cam_origin=(0.0, -1.0, 14.0), cam_target=(0.0, -1.0, 11.0))
+    with bpt.PathTracer(0) as pt:
+        pt.upload_mesh(*[cornell_oracle.verts, cornell_oracle.indices, cornell_oracle.faces])
+        pt.set_instances(xf)
+        pt.build_accel()
+        img = pt.render(bpt.default_params(128, 128, 4, 6, nee=1, **cam))
+    ref, _ = O.Scene(cornell_oracle.verts, cornell_oracle.indices, cornell_oracle.faces, xforms=xf).render(
+        O.default_params(128, 128, 4, 6, nee=1, **cam), 32)
+    assert O.rel_l2(img, ref) <= 2e-3
     dark = dict(sky=(0.0, 0.0, 0.0))
     def blocks(frames, f0, **kw):
         pt_cornell.clear_image()
@@ -951,3 +959,44 @@ def test_hostile_meshes_do_not_break_the_build(cornell):
                 assert hh["prim"][0] == 0 and abs(hh["t"][0] - 1.0) < 1e-5   # exact duplicates: the lowest id wins
             else:
                 assert hh["prim"][0] == O.MISS
+
+
+def test_flat_and_rescaled_scenes(cornell):
+    """Scenes whose extent is degenerate along an axis (a single quad: the scene grid and every node are flat there) and
+    the Cornell box at 1000x and 1/1000 of its size: closest hits against the oracle's brute force."""
+    quad = np.array([[-1, 0, -1], [1, 0, -1], [1, 0, 1], [-1, 0, -1], [1, 0, 1], [-1, 0, 1]], np.float32)
+    f = np.tile(np.array([0.5, 0.5, 0.5, 0, 0, 0], np.float32), (2, 1))
+    rng = np.random.default_rng(51)
+    n = 50_000
+    o = np.stack([rng.uniform(-1.5, 1.5, n), rng.uniform(0.2, 2.0, n) * rng.choice([-1, 1], n), rng.uniform(-1.5, 1.5, n)], 1)
+    tgt = np.stack([rng.uniform(-1.2, 1.2, n), np.zeros(n), rng.uniform(-1.2, 1.2, n)], 1)
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, np.full((n, 1), 1e-3), d, np.full((n, 1), 1e4)], 1).astype(np.float32)
+    for axis in range(3):                              # the quad flat in y, then the same quad flat in z and in x
+        perm = np.roll(np.arange(3), axis)
+        v = quad[:, perm]
+        r = rays.copy(); r[:, 0:3] = rays[:, 0:3][:, perm]; r[:, 4:7] = rays[:, 4:7][:, perm]
+        with bpt.PathTracer(0) as pt:
+            pt.upload_mesh(v, np.arange(6, dtype=np.uint32), f)
+            pt.build_accel()
+            check_build_invariants(pt, v, np.arange(6, dtype=np.uint32))
+            gpu = pt.trace_rays(r)
+        ref = O.Scene(v, np.arange(6, dtype=np.uint32), f).intersect(r, 64, brute=True)
+        assert (ref["prim"] != O.MISS).mean() > 0.6
+        compare_hits(gpu, ref, None, max_mismatch=5e-4)
+    verts, idx, faces = cornell
+    for scale in (1000.0, 0.001):
+        v = (verts * np.float32(scale)).astype(np.float32)
+        r = random_rays(50_000, 52)
+        r[:, 0:3] *= scale
+        r[:, 3] = 1e-3 * scale; r[:, 7] = 1e4 * scale
+        with bpt.PathTracer(0) as pt:
+            pt.upload_mesh(v, idx, faces)
+            pt.build_accel()
+            gpu = pt.trace_rays(r)
+        ref = O.Scene(v, idx, faces).intersect(r, 64, brute=True)
+        same = gpu["prim"] == ref["prim"]
+        assert 1.0 - same.mean() <= 5e-4, scale
+        hit = same & (ref["prim"] != O.MISS)
+        np.testing.assert_allclose(gpu["t"][hit], ref["t"][hit], rtol=3e-4)
