@@ -49,7 +49,10 @@ def launches(path):
 
 
 def kernel(path):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """path: a .ncu-rep, or the `ncu -i rep --page raw --csv` export of one (reports of many launches are too large to
+    bring back from the box; their CSV export is not)."""
+    raw = open(path).read() if path.endswith(".csv") else \
+        subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     print(f"# ncu --set full --clock-control none: {path} ({len(data)} launches)")
