@@ -313,7 +313,7 @@ def run_reference(args):
     w = workload_of(args)
     # the per-step sample shrinks with the number of steps so that the whole run stays within about a minute of CPU time
     n = args.steps + args.warmup
-    rows_target = CPU_SAMPLE_ROWS if n <= 6 else max(8, CPU_SAMPLE_ROWS * 6 // n)
+    rows_target = CPU_SAMPLE_ROWS if n <= 6 else max(64, CPU_SAMPLE_ROWS * 6 // n)   # >= 4 rows per thread on a 16-core host
     base, rays, secs = cpu_baseline(w, steps=args.steps, warmup=args.warmup, rows_target=rows_target)
     val = base["value"]
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
