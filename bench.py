@@ -500,16 +500,27 @@ def run_ours(args):
     # Requested bytes (SURVEY 8d "modelled"): 32 B ray + 16 B hit + one 64 B record per node visited and per triangle
     # tested. Almost all of them are served by L1/L2 (ncu: L2 hit rate 83-90 %), so this is NOT DRAM traffic and is
     # reported under its own name only.
-    requested_per_ray = 48.0 + 64.0 * nodes_per_ray + 64.0 * tris_per_ray
     launches = max(st.trace_launches, 1)
+    # Which frame loop ran: the fused path kernel (BPT_OPT_FUSED_PATHS, default) launches the traversal kernel once per
+    # sample pass, the wavefront once per bounce of every pass.
+    fused = w["depth"] > 1 and launches / KT < w["depth"]
+    ray_record_bytes = 0.0 if fused else 48.0
+    requested_per_ray = ray_record_bytes + 64.0 * nodes_per_ray + 64.0 * tris_per_ray
     avg_launch_ms = st.trace_kernel_ms / launches
     kernel_s = max(st.trace_kernel_ms * 1e-3, 1e-12)
     rays_per_launch = st.rays_traced / launches
-    # Algorithmic DRAM bytes of one launch (the floor): every ray record read and every hit record written once
-    # (48 B per ray), and every acceleration-structure record the launch touches fetched from DRAM once — at most the
-    # whole record array, at most one record per visit.
+    # Algorithmic DRAM bytes of one launch (the floor): every acceleration-structure record the launch touches fetched
+    # from DRAM once — at most the whole record array, at most one record per visit — plus, for the wavefront's traversal
+    # launches, every ray record read and every hit record written once (48 B per ray); for the fused path kernel, which
+    # has no ray or hit records in HBM, the 64-byte shading record of every hit (at most the whole array, at most one per
+    # ray) and the 16-byte colour of every path written once.
     bvh_bytes = float(info.bytes_nodes + info.bytes_tris)
-    algo_per_launch = 48.0 * rays_per_launch + min(bvh_bytes, 64.0 * (nodes_per_ray + tris_per_ray) * rays_per_launch)
+    algo_per_launch = min(bvh_bytes, 64.0 * (nodes_per_ray + tris_per_ray) * rays_per_launch)
+    if fused:
+        paths_per_launch = float(w["spp"]) * W * (H // d.world) * KT / launches
+        algo_per_launch += min(64.0 * max(info.num_tris, 1), 64.0 * rays_per_launch) + 16.0 * paths_per_launch
+    else:
+        algo_per_launch += 48.0 * rays_per_launch
     achieved = algo_per_launch / max(avg_launch_ms * 1e-3, 1e-12) / 1e9
     peak, peak_src = 6650.0, "fallback"
     try:
@@ -519,14 +530,16 @@ def run_ours(args):
         pass
     cap = ncu_capture(w["name"], d.world)
     traffic = cap["dram_bytes_per_launch"] if cap else None
-    roofline = {"kernel": "k_trace (persistent BVH8 traversal)",
+    roofline = {"kernel": ("k_trace<FUSED> (persistent path kernel: primary rays, BVH8 traversal, shade and bounce of a sample pass)"
+                           if fused else "k_trace (persistent BVH8 traversal)"),
+                "frame_loop": "fused path kernel, one launch per sample pass" if fused else "wavefront, one launch per bounce",
                 # what binds the kernel by ncu (profiles/*_k_trace_ncu_*.txt): instruction issue and the ALU pipe; DRAM
                 # throughput is a few per cent of peak. `achieved`/`frac` are the kernel's algorithmic DRAM bytes per
                 # launch over its measured duration against the measured HBM peak: far below 1 because the kernel is
                 # not an HBM-bound kernel on this machine (the hot top of the BVH lives in the 126 MB L2).
                 "bound": "issue", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo_per_launch, "compulsory_bytes_per_ray": 48.0,
+                "algorithmic_bytes_per_launch": algo_per_launch, "compulsory_bytes_per_ray": ray_record_bytes,
                 "hbm_frac_ncu": (traffic / max(avg_launch_ms * 1e-3, 1e-12) / 1e9 / peak) if traffic else None,
                 "issue_frac": cap.get("issue_active_frac") if cap else None,
                 "alu_pipe_frac": cap.get("alu_pipe_frac") if cap else None,
@@ -623,7 +636,8 @@ def run_ours(args):
                           "sample_lanes": lanes,
                           "tiling": (f"{tile['tile_block']}-row blocks round-robin over {d.world} GPUs + 1 NCCL all-gather"
                                      if tile else "single tile"),
-                          "l2": "working set per step (path queues + BVH) is far larger than the 126 MB L2; no flush needed",
+                          "frame_loop": roofline["frame_loop"],
+                          "l2": "working set per step (BVH + shading records + per-path colours, in the wavefront also the path queues) is far larger than the 126 MB L2; no flush needed",
                           "bvh8_nodes": info.num_nodes8, "bvh_bytes": int(info.bytes_nodes + info.bytes_tris),
                           **({"options": args.opt} if args.opt else {})},
                "samples_per_s": paths / (ms * 1e-3), "rays": int(rays), "paths": int(paths), "build_ms": build_ms,

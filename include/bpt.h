@@ -141,6 +141,14 @@ typedef struct bpt_accel_info {
                                       Measured on B200: no gain, every kernel fills the whole machine */
 #define BPT_OPT_USE_GRAPH        6 /* 1: capture a frame's launch list as a CUDA graph and replay it while only the
                                       frame index changes (pays off for launch-bound, small frames)             */
+#define BPT_OPT_FUSED_PATHS      13 /* 1: bpt_trace runs ONE path kernel per sample pass — primary rays, traversal, closest-hit /
+                                     miss and the bounce all inside the SMs, path state in shared memory — instead of the
+                                     per-bounce wavefront (generate, then traverse + shade per bounce through ray / hit queues
+                                     in HBM). Same paths, same arithmetic: the image is bit-identical. Default 0: on B200 it
+                                     is 10-20 % faster for frames of up to ~2 M paths (1024 x 1024 at 1 spp) and 6-10 % slower
+                                     for the big ones. The wavefront always runs the estimators the reference does not have
+                                     (nee, rr_start_depth), the sample lanes (BPT_OPT_STREAMS > 1) and staged scenes too big to
+                                     leave room for the path slots */
 #define BPT_OPT_PASS_PATHS       10 /* target paths per sample pass: a pass carries min(spp, this / tile pixels)
                                       samples of every tile pixel (default 2^27); results do not depend on it */
 #define BPT_OPT_BVH_OPTIMAL_COLLAPSE 7 /* 1 (default): SAH-optimal binary -> 8-wide collapse (Ylitie et al. 2017, dynamic

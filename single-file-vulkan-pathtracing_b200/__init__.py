@@ -27,6 +27,7 @@ OPT_PROFILE, OPT_COUNT_TRAVERSAL, OPT_SMEM_TOP_NODES, OPT_STREAMS = 1, 2, 3, 4
 OPT_TRACE_REFILL_BELOW, OPT_TRACE_STEPS_PER_REFILL, OPT_PASS_PATHS, OPT_TRACE_STAGED_TRIS_PER_STEP = 8, 9, 10, 11
 OPT_USE_GRAPH = 6
 OPT_BVH_SAH_SUBTREE = 12
+OPT_FUSED_PATHS = 13
 OPT_TRACE_BLOCK = 5
 OPT_BVH_OPTIMAL_COLLAPSE = 7
 NCCL_UNIQUE_ID_BYTES = 128

@@ -50,6 +50,7 @@ struct bpt_context {
     bool built = false, built_nodes_ok = false;
     bool mesh_built = false;  // the mesh-level BVH8, triangle and shading records match the uploaded mesh
     bool staged = false;  // the traversal kernel instance that holds the whole BVH in shared memory is in use
+    bool fused_fits = false;  // the fused path kernel's shared memory (path slots + stack + staged records) fits an SM
 
     // wavefront buffers
     size_t cap_paths = 0;
@@ -100,6 +101,7 @@ struct bpt_context {
     bool optimal_collapse = true;  // BPT_OPT_BVH_OPTIMAL_COLLAPSE
     uint32_t sah_max_leaves = 32;  // BPT_OPT_BVH_SAH_SUBTREE
     int64_t pass_paths = 1ll << 27;  // BPT_OPT_PASS_PATHS: target number of paths per sample pass
+    bool fused = false;  // BPT_OPT_FUSED_PATHS: one path kernel per sample pass instead of the per-bounce wavefront
 
     // statistics
     bpt_stats stats{};
@@ -342,7 +344,7 @@ int row_major_image(bpt_context* c, const float4** out) {
 }
 
 TraceArgs make_trace_args(bpt_context* c, const float4* rays, uint4* hits, const uint32_t* count, uint32_t* fetch) {
-    TraceArgs a;
+    TraceArgs a{};
     a.rays = rays; a.hits = hits; a.count_ptr = count; a.fetch_ctr = fetch;
     a.recs = c->two_level ? c->d_recs_all : c->blas.recs;
     a.staged_recs = c->staged ? c->blas.num_recs + (c->two_level ? c->tlas.num_recs : 0u) : 0u;
@@ -360,13 +362,13 @@ TraceArgs make_trace_args(bpt_context* c, const float4* rays, uint4* hits, const
     return a;
 }
 
-void launch_trace(bpt_context* c, const TraceArgs& a, cudaStream_t st) {
+void launch_trace(bpt_context* c, const TraceArgs& a, cudaStream_t st, bool fused = false) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->profile) {
         e0 = get_event(c); e1 = get_event(c);
         cudaEventRecord(e0, st);
     }
-    trace_launch(a, (unsigned)c->num_sms, c->staged, c->two_level, c->count, st);
+    trace_launch(a, (unsigned)c->num_sms, c->staged, c->two_level, c->count, fused, st);
     if (c->profile) {
         cudaEventRecord(e1, st);
         c->trace_events.emplace_back(e0, e1);
@@ -386,7 +388,33 @@ void enqueue_frame(bpt_context* c, const FrameParams& f, uint32_t npix, uint32_t
     SceneView sv{c->d_srec, c->d_xforms, c->ntris};
     const bool nee = f.nee && c->nlights > 0;
     const NeeView nv{c->d_light_prims, c->d_light_cdf, c->nlights, c->light_area, f.nee ? c->pdf_prev : nullptr};
-    for (uint32_t s0 = 0; s0 < f.spp_per_frame; s0 += ns) {
+    // The fused path kernel (trace.cu, FUSED; opt-in, BPT_OPT_FUSED_PATHS): one launch per sample pass generates, traces
+    // and shades every path of the pass inside the SMs; it runs the reference's estimator (and the cosine sampler), the
+    // other estimators and the sample lanes stay with the wavefront below. Same paths, same arithmetic, same per-path
+    // colours: the image is bit-identical (tests). Measured: 10-20 % faster on frames of up to
+    // ~2 M paths (fewer launches and tails), 6-10 % slower on the big ones — the traversal is issue-bound, and the
+    // ~1000 instructions of a shade step, which the wavefront's HBM-bound shade kernel hides under its memory traffic,
+    // queue up behind it in the same warps.
+    const bool fused = c->fused && c->fused_fits && !f.nee && !f.rr_start_depth && c->num_lanes == 1;
+    for (uint32_t s0 = 0; fused && s0 < f.spp_per_frame; s0 += ns) {
+        const uint32_t n = std::min(ns, f.spp_per_frame - s0);
+        uint32_t* path_ctr = c->counters + (kMaxDepth + 1);  // fetch[0] of lane 0
+        cudaMemsetAsync(path_ctr, 0, sizeof(uint32_t), c->stream);
+        TraceArgs a = make_trace_args(c, nullptr, nullptr, nullptr, nullptr);
+        a.f.p = f;
+        a.f.s = sv;
+        a.f.path_color = c->path_color;
+        a.f.path_ctr = path_ctr;
+        a.f.frame_dev = frame_dev;
+        a.f.s0 = s0;
+        a.f.npaths = npix * n;
+        a.f.npix = npix;
+        a.f.path_base = 0u;
+        launch_trace(c, a, c->stream, true);
+        launch_gather_pass(npix, n, c->path_color, c->frame_sum, c->stream);
+        c->stats.kernel_launches++;
+    }
+    for (uint32_t s0 = 0; !fused && s0 < f.spp_per_frame; s0 += ns) {
         const uint32_t n = std::min(ns, f.spp_per_frame - s0);
         const uint32_t L = std::min<uint32_t>((uint32_t)c->num_lanes, n);
         if (L > 1) {
@@ -454,6 +482,8 @@ void plan_staging(bpt_context* c) {
     const uint64_t recs = (uint64_t)c->blas.num_recs + (c->two_level ? c->tlas.num_recs : 0u);
     c->staged = c->built_nodes_ok && nodes <= (uint64_t)c->opt_stage_max_nodes &&
                 trace_smem_bytes((uint32_t)recs) <= (size_t)kTraceMaxSmem;
+    // the fused path kernel keeps 64 path slots per warp next to the stack: a staged scene must leave room for them
+    c->fused_fits = trace_smem_bytes(c->staged ? (uint32_t)recs : 0u, kTraceBlock, true) <= (size_t)kTraceMaxSmem;
 }
 
 // inverse of a row-major 3x4 affine transform, in double; false if singular
@@ -603,6 +633,7 @@ int bpt_set_option(bpt_context* c, int option, int64_t value) {
             c->pass_paths = value;
             return BPT_OK;
         case BPT_OPT_USE_GRAPH: c->use_graph = value != 0; return BPT_OK;
+        case BPT_OPT_FUSED_PATHS: c->fused = value != 0; return BPT_OK;
         case BPT_OPT_BVH_OPTIMAL_COLLAPSE:  // takes effect at the next build of a changed mesh
             c->optimal_collapse = value != 0;
             c->mesh_built = false;

@@ -47,6 +47,7 @@
 //     array is copied into shared memory once per CTA by TMA bulk copies (cp.async.bulk + mbarrier complete_tx) and
 //     never touched in global memory again; big scenes run the global instance (staging only the top of the tree was
 //     measured at +-1 %: the shared/global dual path costs the issue slots the saved round trips buy)
+#include "shade_one.cuh"
 #include "trace.cuh"
 
 namespace {
@@ -119,6 +120,17 @@ __device__ __forceinline__ void sts128f(uint32_t addr, float4 v) {
 __device__ __forceinline__ float4 as_float4(uint4 q) {
     return make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
 }
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -151,6 +163,15 @@ constexpr float kByteBias = 32768.0f;
 __device__ __forceinline__ float safe_rcp(float d) {
     const float eps = 1e-30f;
     return __fdividef(1.0f, fabsf(d) > eps ? d : copysignf(eps, d));
+}
+
+// This file is compiled with --fmad=false (the fused instance shades paths with the shader's IEEE operation order,
+// shade_one.cuh), so the traversal arithmetic names its fused multiply-adds itself.
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+    return fmaf(az, bz, fmaf(ax, bx, ay * by));
+}
+__device__ __forceinline__ float dot3p(float ax, float ay, float az, float bx, float by, float bz, float c) {
+    return fmaf(az, bz, fmaf(ay, by, fmaf(ax, bx, c)));
 }
 
 struct RayState {
@@ -195,21 +216,110 @@ __device__ __forceinline__ uint32_t test_quad(uint32_t xn, uint32_t yn, uint32_t
     return hit;
 }
 
+// ---------------------------------------------------------------- fused path kernel: the shade batch
+// Slot layout (64 bytes, shared memory): +0 {o.xyz, path id}  +16 {d.xyz, seed}  +32 {1/d.xyz, octant | depth << 8}
+// +48 {throughput rgb, -}; a finished ray overwrites +32, +36 with {t, primitive}. A slot that has never held a path
+// carries kNewPath as its primitive.
+constexpr uint32_t kNewPath = 0xfffffffeu;
+constexpr uint32_t kFusedReady = 64u, kFusedCtl = 128u, kFusedSlot0 = 192u;  // offsets inside a warp's block
+
+// Shades up to 32 finished rays of the calling warp (the tail of its done list), one per lane, at full SIMD width:
+// closest-hit / miss + path update exactly as the wavefront shade kernel does (shade_one), then every path that ended
+// is replaced by the next primary ray of the pass (one atomic per batch) while there are any. Slots that hold a ray
+// again go onto the ready list. Not inlined: the traversal loop keeps its register allocation, and what lives across
+// the call is saved around it once per ~30 loop iterations.
+// Returns (entries left on the done list) | (entries on the ready list) << 8.
+__device__ __noinline__ uint32_t fused_shade_batch(const FusedArgs* f, uint32_t wf_a, uint32_t n_done) {
+    using namespace bpt_shade;
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    const uint32_t cnt = min(32u, n_done), first = n_done - cnt;
+    uint32_t slot = 0u, sa = 0u, pix = 0u, depth = 0u;
+    bool alive = false, need_new = false;
+    ShadeOut o;
+    o.ro = o.rd = o.st = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < cnt) {
+        slot = lds8(wf_a + first + lane);
+        sa = wf_a + kFusedSlot0 + slot * 64u;
+        const uint4 q2 = lds128(sa + 32u);
+        const uint32_t prim = q2.y;
+        depth = q2.w >> 8;
+        if (prim == kNewPath) need_new = true;
+        else {
+            const uint4 q0 = lds128(sa), q1 = lds128(sa + 16u), q3 = lds128(sa + 48u);
+            pix = q0.w;
+            const float4 ro = make_float4(__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z), f->p.tmin);
+            const float4 rd = make_float4(__uint_as_float(q1.x), __uint_as_float(q1.y), __uint_as_float(q1.z), f->p.tmax);
+            const float4 st = make_float4(__uint_as_float(q3.x), __uint_as_float(q3.y), __uint_as_float(q3.z), __uint_as_float(q1.w));
+            float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra, rc = ra, rdd = ra;
+            if (prim != BPT_MISS) {
+                const float4* rp = f->s.srec + 4 * (size_t)(f->s.xforms ? prim % f->s.ntris : prim);
+                ra = __ldg(rp); rb = __ldg(rp + 1); rc = __ldg(rp + 2); rdd = __ldg(rp + 3);
+            }
+            alive = shade_one<false>(f->p, f->s, depth, make_uint4(q2.x, 0u, 0u, prim), st, pix, ro, rd, ra, rb, rc, rdd,
+                                     f->path_color, nullptr, 0.f, o);
+            if (alive) ++depth; else need_new = true;
+        }
+    }
+    const unsigned nm = __ballot_sync(FULL, need_new);
+    if (nm) {
+        // the counter may run past npaths while a pass drains: it is 32 bits, a pass has < 2^31 paths
+        const int leader = __ffs(nm) - 1;
+        uint32_t base = 0u;
+        if ((int)lane == leader) base = atomicAdd(f->path_ctr, (uint32_t)__popc(nm));
+        base = __shfl_sync(FULL, base, leader);
+        if (need_new) {
+            const uint32_t i = base + __popc(nm & lt);
+            if (i < f->npaths) {
+                uint32_t seed;
+                gen_primary(f->p, f->s0, f->npix, i, o.ro, o.rd, seed);
+                o.st = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
+                pix = f->path_base + i;
+                depth = 0u;
+                alive = true;
+            }
+        }
+    }
+    const unsigned am = __ballot_sync(FULL, alive);
+    if (alive) {
+        const uint32_t oct = (o.rd.x >= 0.f ? 4u : 0u) | (o.rd.y >= 0.f ? 2u : 0u) | (o.rd.z >= 0.f ? 1u : 0u);
+        sts128(sa, make_uint4(__float_as_uint(o.ro.x), __float_as_uint(o.ro.y), __float_as_uint(o.ro.z), pix));
+        sts128(sa + 16u, make_uint4(__float_as_uint(o.rd.x), __float_as_uint(o.rd.y), __float_as_uint(o.rd.z), __float_as_uint(o.st.w)));
+        sts128(sa + 32u, make_uint4(__float_as_uint(safe_rcp(o.rd.x)), __float_as_uint(safe_rcp(o.rd.y)),
+                                    __float_as_uint(safe_rcp(o.rd.z)), oct | (depth << 8)));
+        sts128(sa + 48u, make_uint4(__float_as_uint(o.st.x), __float_as_uint(o.st.y), __float_as_uint(o.st.z), 0u));
+        sts8(wf_a + kFusedReady + __popc(am & lt), slot);
+    }
+    if (lane == 0u) {  // rays handed to the traversal: the warp's share of bpt_stats.rays
+        const uint2 c = lds64(wf_a + kFusedCtl);
+        const unsigned long long n = (((unsigned long long)c.y << 32) | c.x) + (unsigned long long)__popc(am);
+        sts64(wf_a + kFusedCtl, make_uint2((uint32_t)n, (uint32_t)(n >> 32)));
+    }
+    __syncwarp();
+    return (n_done - cnt) | ((uint32_t)__popc(am) << 8);
+}
+
 // TWO_LEVEL (instanced scenes, main.cpp:515-538): nodes = [mesh BVH8 | instance BVH8], records = [triangles | instances];
 // an instance record holds the rows of the inverse 3x4 transform. Hitting one pushes what is left of the instance-level
 // state plus a sentinel, moves the ray into object space (d is NOT renormalised, so t is the same in both spaces) and
 // descends from the mesh root (node 0); popping the sentinel reloads the world-space ray.
-template <int BLOCK, int SSTACK, bool STAGED, bool TWO_LEVEL, bool COUNT>
+//
+// FUSED (the path kernel): no ray queue at all. A warp owns kFusedSlots path slots in shared memory; a lane whose ray is
+// done leaves {t, primitive} in its slot and takes a slot from the warp's ready list, and when that list is empty the
+// warp shades its finished rays 32 at a time (fused_shade_batch), which refills it — with bounce rays and, for every
+// path that ended, the next primary ray of the pass. Ray and hit records, path state and the queue compaction of the
+// wavefront never touch HBM, and a sample pass is one launch with one tail instead of one per bounce.
+template <int BLOCK, int SSTACK, bool STAGED, bool TWO_LEVEL, bool COUNT, bool FUSED>
 __global__ void __launch_bounds__(BLOCK, BLOCK == kTraceBlock ? 1 : BPT_TRACE_CTAS_G) k_trace(TraceArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     uint2* slut = reinterpret_cast<uint2*>(smem_raw + 16);  // byte o of slut[b]: bit p = bit (p ^ o) of b
     unsigned char* spool = smem_raw + 16 + 2048;  // ray pools: 32 rays x 48 B ({o,tmin} {d,tmax} {1/d,octant}) per warp
-    uint2* sstack = reinterpret_cast<uint2*>(smem_raw + trace_smem_fixed(BLOCK));
-    unsigned char* srecs = smem_raw + trace_smem_fixed(BLOCK) + (size_t)SSTACK * BLOCK * sizeof(uint2);  // staged records
+    unsigned char* sfused = smem_raw + 16 + 2048;  // FUSED instead: FusedArgs, then per warp {done, ready, counters, slots}
+    uint2* sstack = reinterpret_cast<uint2*>(smem_raw + trace_smem_fixed(BLOCK, FUSED));
+    unsigned char* srecs = smem_raw + trace_smem_fixed(BLOCK, FUSED) + (size_t)SSTACK * BLOCK * sizeof(uint2);  // staged records
 
-    const uint32_t nrays = *a.count_ptr;
-    if (nrays == 0u) return;  // uniform across the grid: an exhausted bounce costs one launch and nothing else
+    const uint32_t nrays = FUSED ? 0u : *a.count_ptr;
+    if (!FUSED && nrays == 0u) return;  // uniform across the grid: an exhausted bounce costs one launch and nothing else
 
     // ---- STAGED: the whole record array moves into shared memory with TMA bulk copies
     if (STAGED) {
@@ -235,27 +345,51 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kTraceBlock ? 1 : BPT_TRACE_CT
         }
         slut[b] = make_uint2(w[0], w[1]);
     }
+    if (FUSED) {
+        // arguments of the shade batch into shared memory (the frame index from device memory under graph replay);
+        // every slot starts on its warp's done list as "never held a path", so the first batches generate primary rays
+        uint32_t* fdst = reinterpret_cast<uint32_t*>(sfused);
+        const uint32_t* fsrc = reinterpret_cast<const uint32_t*>(&a.f);
+        for (uint32_t i = threadIdx.x; i < sizeof(FusedArgs) / 4u; i += BLOCK) fdst[i] = fsrc[i];
+        unsigned char* wb = sfused + kFusedArgsBytes + (threadIdx.x >> 5) * kFusedWarpBytes;
+        for (uint32_t i = threadIdx.x & 31u; i < (uint32_t)kFusedSlots; i += 32u) {
+            wb[i] = (unsigned char)i;
+            *reinterpret_cast<uint4*>(wb + kFusedSlot0 + i * 64u + 32u) = make_uint4(0u, kNewPath, 0u, 0u);
+        }
+        if ((threadIdx.x & 31u) == 0u) *reinterpret_cast<uint2*>(wb + kFusedCtl) = make_uint2(0u, 0u);
+        __syncthreads();
+        if (threadIdx.x == 0 && a.f.frame_dev) reinterpret_cast<FusedArgs*>(sfused)->p.frame = *a.f.frame_dev;
+    }
     __syncthreads();
 
-    if (blockIdx.x == 0 && threadIdx.x == 0 && a.stat && a.count_rays) atomicAdd(a.stat + BPT_STAT_RAYS, (unsigned long long)nrays);
+    if (!FUSED && blockIdx.x == 0 && threadIdx.x == 0 && a.stat && a.count_rays) atomicAdd(a.stat + BPT_STAT_RAYS, (unsigned long long)nrays);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
-    const uint32_t stack_a = smem_u32(sstack + threadIdx.x);  // entry i of this lane: stack_a + i * BLOCK * 8
-    const uint32_t srecs_a = smem_u32(srecs), slut_a = smem_u32(slut);
-    const uint32_t pool_a = smem_u32(spool) + (threadIdx.x >> 5) * 1536u;
+    const FusedArgs* fargs = reinterpret_cast<const FusedArgs*>(sfused);
+    // every shared-memory address below is the one base plus compile-time offsets
+    uint32_t smem_a;  // opaque to the compiler: it would otherwise rebuild it (S2R SR_CgaCtaId + LEA) at every use under pressure
+    asm volatile("mov.u32 %0, %1;" : "=r"(smem_a) : "r"(smem_u32(smem_raw)));
+    constexpr uint32_t kFixed = (uint32_t)trace_smem_fixed(BLOCK, FUSED);
+    const uint32_t wf_a = smem_a + 16u + 2048u + kFusedArgsBytes + (threadIdx.x >> 5) * kFusedWarpBytes;  // FUSED: the warp's block
+    uint32_t n_done = kFusedSlots, n_ready = 0u;  // FUSED, warp-uniform: lengths of the warp's done and ready lists
+    const uint32_t stack_a = smem_a + kFixed + threadIdx.x * 8u;  // entry i of this lane: stack_a + i * BLOCK * 8
+    const uint32_t srecs_a = smem_a + kFixed + (uint32_t)SSTACK * BLOCK * 8u, slut_a = smem_a + 16u;
+    const uint32_t pool_a = smem_a + 16u + 2048u + (threadIdx.x >> 5) * 1536u;
     uint2 lstack[kLocalStack];
+    volatile uint32_t park[FUSED ? 22 : 1];  // FUSED: a lane's traversal state while the warp shades
     const uint32_t magic = a.magic;
     const int refill_below = a.refill_below, steps_per_refill = a.steps_per_refill;
     const int tris_per_step = STAGED ? a.staged_tris_per_step : 1;
 
     RayState r;
+    if (FUSED) r.tmin = a.f.p.tmin;  // every ray of a frame has the frame's tmin / tmax
     uint2 G = make_uint2(0u, 0u);  // node group: x = first internal child, y = hits by priority << 24 | internal mask
     uint2 T = make_uint2(0u, 0u);  // triangle group: x = node the triangles belong to, y = hit bits (valid layout)
     uint32_t Tb = 0u, Tv = 0u;     // tri_base and valid word of node T.x
     uint32_t octsel = 0u;          // byte-permute selector that picks byte `oct` of a slut row into byte 3
     uint32_t inst_base = 0u;       // TWO_LEVEL: instance * mesh triangles while inside an instance
     int sp = 0;
-    uint32_t ray_idx = 0;
+    uint32_t ray_idx = FUSED ? 0xffu : 0u;  // FUSED: the lane's path slot (0xff: none)
     bool active = false, exhausted = false;
     uint32_t pool_base = 0u, pool_count = 0u, pool_next = 0u;  // warp-uniform: the warp's ray pool in shared memory
     unsigned long long cnt_nodes = 0, cnt_tris = 0, cnt_witer = 0, cnt_wnode = 0, cnt_wtri = 0, cnt_liter = 0;
@@ -269,6 +403,64 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kTraceBlock ? 1 : BPT_TRACE_CT
 
     for (;;) {
         unsigned actmask = __ballot_sync(FULL, active);
+        if (FUSED) {
+            if (__popc(actmask) < refill_below) {
+                // finished rays go onto the done list; idle lanes take ready slots; an empty ready list is refilled by
+                // shading the tail of the done list. With all 64 slots alive the done list holds >= 32 entries whenever
+                // the ready list runs dry, so the batches are full until the pass drains.
+                const bool fin = !active && ray_idx != 0xffu;
+                const unsigned fm = __ballot_sync(FULL, fin);
+                if (fin) { sts8(wf_a + n_done + __popc(fm & lt), ray_idx); ray_idx = 0xffu; }
+                n_done += __popc(fm);
+                __syncwarp();
+                unsigned idle = ~actmask;
+                for (;;) {
+                    if (n_ready == 0u) {
+                        if (n_done == 0u) break;
+                        // the lanes' traversal state waits in local memory while the warp shades: the batch needs the
+                        // registers, and spelled out like this the allocator does not keep loop state spilled instead
+                        park[0] = __float_as_uint(r.ox); park[1] = __float_as_uint(r.oy); park[2] = __float_as_uint(r.oz);
+                        park[3] = __float_as_uint(r.dx); park[4] = __float_as_uint(r.dy); park[5] = __float_as_uint(r.dz);
+                        park[6] = __float_as_uint(r.idx); park[7] = __float_as_uint(r.idy); park[8] = __float_as_uint(r.idz);
+                        park[9] = __float_as_uint(r.tbest); park[10] = r.hprim; park[11] = r.oct;
+                        park[12] = G.x; park[13] = G.y; park[14] = T.x; park[15] = T.y; park[16] = Tb; park[17] = Tv;
+                        park[18] = inst_base; park[19] = (uint32_t)sp; park[20] = ray_idx; park[21] = active ? 1u : 0u;
+                        uint32_t res = fused_shade_batch(fargs, wf_a, n_done);
+                        res = __shfl_sync(FULL, res, 0);  // warp-uniform, and known to be
+                        n_done = res & 0xffu; n_ready = res >> 8;
+                        r.ox = __uint_as_float(park[0]); r.oy = __uint_as_float(park[1]); r.oz = __uint_as_float(park[2]);
+                        r.dx = __uint_as_float(park[3]); r.dy = __uint_as_float(park[4]); r.dz = __uint_as_float(park[5]);
+                        r.idx = __uint_as_float(park[6]); r.idy = __uint_as_float(park[7]); r.idz = __uint_as_float(park[8]);
+                        r.tbest = __uint_as_float(park[9]); r.hprim = park[10]; r.oct = park[11]; octsel = r.oct << 12;
+                        G.x = park[12]; G.y = park[13]; T.x = park[14]; T.y = park[15]; Tb = park[16]; Tv = park[17];
+                        inst_base = park[18]; sp = (int)park[19]; ray_idx = park[20]; active = park[21] != 0u;
+                        continue;  // an empty ready list again: every shaded path ended and the pass has no primary ray left
+                    }
+                    const uint32_t rank = __popc(idle & lt);
+                    if (!active && rank < n_ready) {
+                        ray_idx = lds8(wf_a + kFusedReady + (n_ready - 1u - rank));
+                        const uint32_t sa = wf_a + kFusedSlot0 + ray_idx * 64u;
+                        const uint4 q0 = lds128(sa), q1 = lds128(sa + 16u), q2 = lds128(sa + 32u);
+                        r.ox = __uint_as_float(q0.x); r.oy = __uint_as_float(q0.y); r.oz = __uint_as_float(q0.z);
+                        r.dx = __uint_as_float(q1.x); r.dy = __uint_as_float(q1.y); r.dz = __uint_as_float(q1.z); r.tbest = a.f.p.tmax;
+                        r.idx = __uint_as_float(q2.x); r.idy = __uint_as_float(q2.y); r.idz = __uint_as_float(q2.z);
+                        r.oct = q2.w & 7u;
+                        octsel = r.oct << 12;
+                        r.hprim = BPT_MISS;
+                        inst_base = 0u;
+                        G = make_uint2(a.root, 0x80000000u);
+                        T = make_uint2(0u, 0u);
+                        sp = 0;
+                        active = true;
+                    }
+                    n_ready -= min(n_ready, (uint32_t)__popc(idle));
+                    __syncwarp();  // the list and slot reads are done before a batch rewrites them
+                    idle = ~__ballot_sync(FULL, active);
+                    if (!idle) break;
+                }
+                actmask = ~idle;
+            }
+        } else
         if (__popc(actmask) < refill_below && (!exhausted || pool_next < pool_count)) {
             // Refill idle lanes from the warp's ray pool: 32 consecutive rays fetched with one atomic and two coalesced
             // 128-bit loads per lane into shared memory; lanes that finish take the next pool entries without touching
@@ -342,8 +534,14 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kTraceBlock ? 1 : BPT_TRACE_CT
                 else if (TWO_LEVEL && e.y == 0u) {
                     if (T.y == 0u) {  // sentinel: the instance is done (its triangles too) -> back to world space
                         --sp;
-                        const float4 ro = __ldg(&a.rays[2 * (size_t)ray_idx]);
-                        const float4 rd = __ldg(&a.rays[2 * (size_t)ray_idx + 1]);
+                        float4 ro, rd;
+                        if (FUSED) {
+                            const uint32_t sa = wf_a + kFusedSlot0 + ray_idx * 64u;
+                            ro = as_float4(lds128(sa)); rd = as_float4(lds128(sa + 16u));
+                        } else {
+                            ro = __ldg(&a.rays[2 * (size_t)ray_idx]);
+                            rd = __ldg(&a.rays[2 * (size_t)ray_idx + 1]);
+                        }
                         r.ox = ro.x; r.oy = ro.y; r.oz = ro.z;
                         r.dx = rd.x; r.dy = rd.y; r.dz = rd.z;
                         r.idx = safe_rcp(rd.x);
@@ -448,10 +646,10 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kTraceBlock ? 1 : BPT_TRACE_CT
                     const float m00 = __uint_as_float(w0.lo.x), m01 = __uint_as_float(w0.lo.y), m02 = __uint_as_float(w0.lo.z), m03 = __uint_as_float(w0.lo.w);
                     const float m10 = __uint_as_float(w0.hi.x), m11 = __uint_as_float(w0.hi.y), m12 = __uint_as_float(w0.hi.z), m13 = __uint_as_float(w0.hi.w);
                     const float m20 = __uint_as_float(w1.lo.x), m21 = __uint_as_float(w1.lo.y), m22 = __uint_as_float(w1.lo.z), m23 = __uint_as_float(w1.lo.w);
-                    const float ox = m00 * r.ox + m01 * r.oy + m02 * r.oz + m03, oy = m10 * r.ox + m11 * r.oy + m12 * r.oz + m13,
-                                oz = m20 * r.ox + m21 * r.oy + m22 * r.oz + m23;
-                    const float dx = m00 * r.dx + m01 * r.dy + m02 * r.dz, dy = m10 * r.dx + m11 * r.dy + m12 * r.dz,
-                                dz = m20 * r.dx + m21 * r.dy + m22 * r.dz;
+                    const float ox = dot3p(m00, m01, m02, r.ox, r.oy, r.oz, m03), oy = dot3p(m10, m11, m12, r.ox, r.oy, r.oz, m13),
+                                oz = dot3p(m20, m21, m22, r.ox, r.oy, r.oz, m23);
+                    const float dx = dot3(m00, m01, m02, r.dx, r.dy, r.dz), dy = dot3(m10, m11, m12, r.dx, r.dy, r.dz),
+                                dz = dot3(m20, m21, m22, r.dx, r.dy, r.dz);
                     r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
                     r.idx = safe_rcp(dx);
                     r.idy = safe_rcp(dy);
@@ -463,8 +661,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kTraceBlock ? 1 : BPT_TRACE_CT
                     T = make_uint2(0u, 0u);
                 } else {
                 const float rwx = __uint_as_float(w1.lo.x), rwy = __uint_as_float(w1.lo.y), rwz = __uint_as_float(w1.lo.z);
-                const float oz = __uint_as_float(w1.lo.w) + r.ox * rwx + r.oy * rwy + r.oz * rwz;
-                const float dz = r.dx * rwx + r.dy * rwy + r.dz * rwz;
+                const float oz = dot3p(r.ox, r.oy, r.oz, rwx, rwy, rwz, __uint_as_float(w1.lo.w));
+                const float dz = dot3(r.dx, r.dy, r.dz, rwx, rwy, rwz);
                 float rdz;  // MUFU.RCP alone: a denormal dz (ray in the triangle's plane) gives inf / NaN, which fails the range test
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rdz) : "f"(dz));
                 const float t = -oz * rdz;
@@ -478,12 +676,12 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kTraceBlock ? 1 : BPT_TRACE_CT
                     // spares the arithmetic
                     const float rux = __uint_as_float(w0.lo.x), ruy = __uint_as_float(w0.lo.y), ruz = __uint_as_float(w0.lo.z);
                     const float rvx = __uint_as_float(w0.hi.x), rvy = __uint_as_float(w0.hi.y), rvz = __uint_as_float(w0.hi.z);
-                    const float ou = __uint_as_float(w0.lo.w) + r.ox * rux + r.oy * ruy + r.oz * ruz;
-                    const float du = r.dx * rux + r.dy * ruy + r.dz * ruz;
-                    const float u = ou + t * du;
-                    const float ov = __uint_as_float(w0.hi.w) + r.ox * rvx + r.oy * rvy + r.oz * rvz;
-                    const float dv = r.dx * rvx + r.dy * rvy + r.dz * rvz;
-                    const float v = ov + t * dv;
+                    const float ou = dot3p(r.ox, r.oy, r.oz, rux, ruy, ruz, __uint_as_float(w0.lo.w));
+                    const float du = dot3(r.dx, r.dy, r.dz, rux, ruy, ruz);
+                    const float u = fmaf(t, du, ou);
+                    const float ov = dot3p(r.ox, r.oy, r.oz, rvx, rvy, rvz, __uint_as_float(w0.hi.w));
+                    const float dv = dot3(r.dx, r.dy, r.dz, rvx, rvy, rvz);
+                    const float v = fmaf(t, dv, ov);
                     // equal distance (exact duplicate triangles): lowest primitive id wins
                     const uint32_t prim = inst_base + w1.hi.x;
                     if (t >= r.tmin && t <= r.tbest && u >= 0.f && v >= 0.f && u + v <= 1.f && (t < r.tbest || prim < r.hprim)) {
@@ -497,13 +695,18 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kTraceBlock ? 1 : BPT_TRACE_CT
             __syncwarp();
             if (active && !(G.y & 0xff000000u) && T.y == 0u && sp == 0) {
                 // {t, -, -, prim}: u, v are re-derived from the original vertices by the consumer (shade.cu)
-                a.hits[ray_idx] = make_uint4(__float_as_uint(r.tbest), 0u, 0u, r.hprim);
+                if (FUSED) sts64(wf_a + kFusedSlot0 + ray_idx * 64u + 32u, make_uint2(__float_as_uint(r.tbest), r.hprim));
+                else a.hits[ray_idx] = make_uint4(__float_as_uint(r.tbest), 0u, 0u, r.hprim);
                 active = false;
             }
         }
     }
 #undef BPT_PUSH
 #undef BPT_LEADER
+    if (FUSED && lane == 0u && a.stat && a.count_rays) {
+        const uint2 c = lds64(wf_a + kFusedCtl);
+        atomicAdd(a.stat + BPT_STAT_RAYS, ((unsigned long long)c.y << 32) | c.x);
+    }
     if (COUNT) {
         unsigned long long c[6] = {cnt_nodes, cnt_tris, cnt_witer, cnt_wnode, cnt_wtri, cnt_liter};
 #pragma unroll
@@ -518,34 +721,38 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kTraceBlock ? 1 : BPT_TRACE_CT
 }  // namespace
 
 // shared memory the traversal kernel needs with `staged_recs` records staged
-size_t trace_smem_bytes(uint32_t staged_recs, int block) {
-    return trace_smem_fixed(block) + (size_t)kTraceSmemStack * block * sizeof(uint2) + (size_t)staged_recs * BPT_REC_BYTES;
+size_t trace_smem_bytes(uint32_t staged_recs, int block, bool fused) {
+    return trace_smem_fixed(block, fused) + (size_t)kTraceSmemStack * block * sizeof(uint2) + (size_t)staged_recs * BPT_REC_BYTES;
 }
 
 cudaError_t trace_configure() {
     cudaError_t e;
-#define CFG(B, S, L, C)                                                                               \
-    if ((e = cudaFuncSetAttribute(k_trace<B, kTraceSmemStack, S, L, C>,                                \
+#define CFG(B, S, L, C, F)                                                                            \
+    if ((e = cudaFuncSetAttribute(k_trace<B, kTraceSmemStack, S, L, C, F>,                             \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, B == kTraceBlock ? kTraceMaxSmem : kTraceMaxSmem / BPT_TRACE_CTAS_G)) != cudaSuccess) \
         return e;
-    CFG(BPT_TRACE_BLOCK_G, false, false, false) CFG(BPT_TRACE_BLOCK_G, false, false, true) CFG(kTraceBlock, true, false, false)
-    CFG(kTraceBlock, true, false, true) CFG(BPT_TRACE_BLOCK_G, false, true, false) CFG(BPT_TRACE_BLOCK_G, false, true, true)
-    CFG(kTraceBlock, true, true, false) CFG(kTraceBlock, true, true, true)
+#define CFG2(B, S, L, C) CFG(B, S, L, C, false) CFG(B, S, L, C, true)
+    CFG2(BPT_TRACE_BLOCK_G, false, false, false) CFG2(BPT_TRACE_BLOCK_G, false, false, true) CFG2(kTraceBlock, true, false, false)
+    CFG2(kTraceBlock, true, false, true) CFG2(BPT_TRACE_BLOCK_G, false, true, false) CFG2(BPT_TRACE_BLOCK_G, false, true, true)
+    CFG2(kTraceBlock, true, true, false) CFG2(kTraceBlock, true, true, true)
+#undef CFG2
 #undef CFG
     return cudaSuccess;
 }
 
-void trace_launch(const TraceArgs& a, unsigned num_sms, bool staged, bool two_level, bool count, cudaStream_t st) {
+void trace_launch(const TraceArgs& a, unsigned num_sms, bool staged, bool two_level, bool count, bool fused, cudaStream_t st) {
     const int block = staged ? kTraceBlock : BPT_TRACE_BLOCK_G;
-    const size_t smem = trace_smem_bytes(a.staged_recs, block);
+    const size_t smem = trace_smem_bytes(a.staged_recs, block, fused);
     const unsigned grid = staged ? num_sms : num_sms * (unsigned)BPT_TRACE_CTAS_G;
-#define GO(B, S, L, C) k_trace<B, kTraceSmemStack, S, L, C><<<grid, B, smem, st>>>(a)
+#define GO(B, S, L, C, F) k_trace<B, kTraceSmemStack, S, L, C, F><<<grid, B, smem, st>>>(a)
+#define GO2(B, S, L, C) { if (fused) GO(B, S, L, C, true); else GO(B, S, L, C, false); }
     if (staged) {
-        if (two_level) { if (count) GO(kTraceBlock, true, true, true); else GO(kTraceBlock, true, true, false); }
-        else { if (count) GO(kTraceBlock, true, false, true); else GO(kTraceBlock, true, false, false); }
+        if (two_level) { if (count) GO2(kTraceBlock, true, true, true) else GO2(kTraceBlock, true, true, false) }
+        else { if (count) GO2(kTraceBlock, true, false, true) else GO2(kTraceBlock, true, false, false) }
     } else {
-        if (two_level) { if (count) GO(BPT_TRACE_BLOCK_G, false, true, true); else GO(BPT_TRACE_BLOCK_G, false, true, false); }
-        else { if (count) GO(BPT_TRACE_BLOCK_G, false, false, true); else GO(BPT_TRACE_BLOCK_G, false, false, false); }
+        if (two_level) { if (count) GO2(BPT_TRACE_BLOCK_G, false, true, true) else GO2(BPT_TRACE_BLOCK_G, false, true, false) }
+        else { if (count) GO2(BPT_TRACE_BLOCK_G, false, false, true) else GO2(BPT_TRACE_BLOCK_G, false, false, false) }
     }
+#undef GO2
 #undef GO
 }

@@ -599,14 +599,21 @@ def test_graph_replay_is_bit_identical(pt_cornell):
     plain, replay = run(0), run(1)
     for a, b in zip(plain, replay):
         assert np.array_equal(a, b)
-    pt_cornell.reset_stats()
-    pt_cornell.set_option(bpt.OPT_USE_GRAPH, 1)
-    pt_cornell.clear_image()
-    pt_cornell.render(bpt.default_params(256, 256, 1, 2), frames=4)
-    st = pt_cornell.stats()
-    pt_cornell.set_option(bpt.OPT_USE_GRAPH, 0)
-    pt_cornell.clear_image()
-    assert st.trace_launches == 4 * 2 and st.kernel_launches == 4 * (7 + 1)   # 7 kernels in the graph + the frame setter
+    # the wavefront frame loop: generate, 2 x (traverse, shade), gather, accumulate = 7 kernels in the graph + the
+    # frame setter; the fused path kernel (opt-in): path kernel, gather, accumulate + the frame setter
+    for fused, traces, kernels in ((0, 2, 7 + 1), (1, 1, 3 + 1)):
+        pt_cornell.set_option(bpt.OPT_FUSED_PATHS, fused)
+        pt_cornell.reset_stats()
+        pt_cornell.set_option(bpt.OPT_USE_GRAPH, 1)
+        pt_cornell.clear_image()
+        img = pt_cornell.render(bpt.default_params(256, 256, 1, 2), frames=4).copy()
+        st = pt_cornell.stats()
+        pt_cornell.set_option(bpt.OPT_USE_GRAPH, 0)
+        pt_cornell.clear_image()
+        assert st.trace_launches == 4 * traces and st.kernel_launches == 4 * kernels
+        assert np.array_equal(img, pt_cornell.render(bpt.default_params(256, 256, 1, 2), frames=4))
+        pt_cornell.clear_image()
+    pt_cornell.set_option(bpt.OPT_FUSED_PATHS, 0)
 
 
 def test_error_paths(cornell):
@@ -1000,3 +1007,79 @@ def test_flat_and_rescaled_scenes(cornell):
         assert 1.0 - same.mean() <= 5e-4, scale
         hit = same & (ref["prim"] != O.MISS)
         np.testing.assert_allclose(gpu["t"][hit], ref["t"][hit], rtol=3e-4)
+
+
+# ------------------------------------------------------------------------------------------ fused path kernel
+def _both_frame_loops(pt, params, frames=1, **opts):
+    """The same frames through the per-bounce wavefront and through the fused path kernel; returns both images and
+    both statistics."""
+    out = []
+    for fused in (0, 1):
+        pt.set_option(bpt.OPT_FUSED_PATHS, fused)
+        pt.clear_image(); pt.reset_stats()
+        img = pt.render(params, frames=frames).copy()
+        out.append((img, pt.stats()))
+    pt.set_option(bpt.OPT_FUSED_PATHS, 0)
+    pt.clear_image()
+    return out
+
+
+def test_fused_path_kernel_is_bit_identical_to_the_wavefront(pt_cornell, soup20k):
+    """BPT_OPT_FUSED_PATHS: one path kernel per sample pass (primary rays, traversal, closest-hit / miss and the bounce
+    inside the SMs, path state in shared memory) runs the same paths with the same arithmetic as generate + per-bounce
+    traverse + shade: images are bit-identical, ray counts equal, and a pass is ONE traversal launch. Cornell box =
+    the instance with the records staged in shared memory; the soup and SMEM_TOP_NODES = 0 = the global-memory instance."""
+    cases = [dict(width=256, height=256, spp=1, depth=2),                       # Cfg1
+             dict(width=160, height=96, spp=7, depth=6),
+             dict(width=61, height=37, spp=32, depth=8),                        # ragged: fewer paths than slots in places
+             dict(width=128, height=128, spp=4, depth=8, tile_y0=40, tile_rows=24),
+             dict(width=128, height=128, spp=4, depth=8, tile_block=8, tile_nranks=4, tile_rank=1),
+             dict(width=96, height=96, spp=8, depth=8, accum_mode=bpt.ACCUM_RGBA8),
+             dict(width=96, height=96, spp=8, depth=5, sampler=bpt.SAMPLER_COSINE),
+             dict(width=64, height=64, spp=3, depth=1),                         # primary rays only
+             dict(width=8, height=4, spp=1, depth=3)]                           # fewer paths than one warp has slots
+    for staged in (1, 0):
+        pt_cornell.set_option(bpt.OPT_SMEM_TOP_NODES, (1 << 20) if staged else 0)
+        for kw in cases:
+            kw = dict(kw)
+            p = bpt.default_params(kw.pop("width"), kw.pop("height"), kw.pop("spp"), kw.pop("depth"), **kw)
+            (wi, ws), (fi, fs) = _both_frame_loops(pt_cornell, p, frames=2)
+            assert np.array_equal(wi.view(np.uint32), fi.view(np.uint32)), (staged, kw, np.abs(wi - fi).max())
+            assert ws.rays_traced == fs.rays_traced and ws.paths == fs.paths
+            assert fs.trace_launches == 2 and ws.trace_launches == 2 * p.max_depth
+    pt_cornell.set_option(bpt.OPT_SMEM_TOP_NODES, 1 << 20)
+    # several passes per frame (pass size below the frame's paths), and the instrumented kernel: same node / triangle counts
+    pt_cornell.set_option(bpt.OPT_PASS_PATHS, 64 * 64 * 3)
+    pt_cornell.set_option(bpt.OPT_COUNT_TRAVERSAL, 1)
+    (wi, ws), (fi, fs) = _both_frame_loops(pt_cornell, bpt.default_params(64, 64, 8, 6), frames=2)
+    pt_cornell.set_option(bpt.OPT_COUNT_TRAVERSAL, 0)
+    pt_cornell.set_option(bpt.OPT_PASS_PATHS, 1 << 27)
+    assert np.array_equal(wi, fi) and fs.trace_launches == 2 * 3
+    assert (ws.nodes_visited, ws.tris_tested, ws.rays_traced) == (fs.nodes_visited, fs.tris_tested, fs.rays_traced)
+    # the soup: global-memory records, deep stacks, emissive triangles
+    verts, idx, faces, scene = soup20k
+    with bpt.PathTracer(0) as pt:
+        pt.upload_mesh(verts, idx, faces)
+        pt.build_accel()
+        for (w, h, spp, depth) in ((128, 128, 4, 8), (333, 77, 2, 8)):
+            (wi, ws), (fi, fs) = _both_frame_loops(pt, bpt.default_params(w, h, spp, depth), frames=2)
+            assert np.array_equal(wi.view(np.uint32), fi.view(np.uint32)), np.abs(wi - fi).max()
+            assert ws.rays_traced == fs.rays_traced
+        # the estimators the path kernel does not know stay with the wavefront, whatever the option says
+        pt.set_option(bpt.OPT_FUSED_PATHS, 1)
+        pt.reset_stats()
+        pt.render(bpt.default_params(64, 64, 2, 4, nee=1))
+        assert pt.stats().trace_launches > 1
+
+
+def test_fused_path_kernel_on_instanced_scenes(pt_instanced, cornell):
+    """Two-level scenes through the path kernel: the instance sentinel reloads the world-space ray from the path slot.
+    27 instances are staged in shared memory next to the path slots; with staging off the records come from global memory."""
+    pt, xf, scene = pt_instanced
+    kw = dict(cam_origin=(0.0, -1.0, 14.0), cam_target=(0.0, -1.0, 11.0))
+    for staged in (1, 0):
+        pt.set_option(bpt.OPT_SMEM_TOP_NODES, (1 << 20) if staged else 0)
+        (wi, ws), (fi, fs) = _both_frame_loops(pt, bpt.default_params(160, 160, 4, 6, **kw), frames=2)
+        assert np.array_equal(wi.view(np.uint32), fi.view(np.uint32)), (staged, np.abs(wi - fi).max())
+        assert ws.rays_traced == fs.rays_traced and fs.trace_launches == 2
+    pt.set_option(bpt.OPT_SMEM_TOP_NODES, 1 << 20)

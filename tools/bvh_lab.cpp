@@ -64,11 +64,52 @@ static uint32_t expand10(uint32_t v) {
     return v;
 }
 
+struct Ref { Box box; uint32_t tri; };
+static Bin build_lbvh_refs(const std::vector<Ref>& refs);
 static Bin build_lbvh(const std::vector<Tri>& tris) {
-    const uint32_t n = (uint32_t)tris.size();
+    std::vector<Ref> refs(tris.size());
+    for (uint32_t i = 0; i < tris.size(); ++i) { for (int k = 0; k < 3; ++k) refs[i].box.grow(tris[i].v[k]); refs[i].tri = i; }
+    return build_lbvh_refs(refs);
+}
+
+// ---------------------------------------------------------------- triangle pre-splitting (references)
+// a triangle becomes up to 2^levels references: its box is halved along its longest axis and the triangle is clipped
+// to each half (Sutherland-Hodgman), recursively; a half is not split further once its longest side is below `min_side`
+static void clip_poly(std::vector<V3>& poly, int axis, float plane, bool keep_below) {
+    std::vector<V3> out;
+    const size_t m = poly.size();
+    auto get = [&](const V3& p) { return axis == 0 ? p.x : axis == 1 ? p.y : p.z; };
+    for (size_t i = 0; i < m; ++i) {
+        const V3 a = poly[i], b = poly[(i + 1) % m];
+        const float da = get(a) - plane, db = get(b) - plane;
+        const bool ia = keep_below ? da <= 0.f : da >= 0.f, ib = keep_below ? db <= 0.f : db >= 0.f;
+        if (ia) out.push_back(a);
+        if (ia != ib) { const float t = da / (da - db); out.push_back(a + (b - a) * t); }
+    }
+    poly.swap(out);
+}
+static void split_rec(const std::vector<V3>& poly, uint32_t tri, int levels, float min_side, std::vector<Ref>& out) {
+    Box bx; for (const V3& p : poly) bx.grow(p);
+    int ax = 0; float ext = 0.f;
+    for (int a = 0; a < 3; ++a) if (bx.hi[a] - bx.lo[a] > ext) { ext = bx.hi[a] - bx.lo[a]; ax = a; }
+    if (levels == 0 || ext <= min_side) { out.push_back(Ref{bx, tri}); return; }
+    const float mid = 0.5f * (bx.lo[ax] + bx.hi[ax]);
+    std::vector<V3> lo = poly, hi = poly;
+    clip_poly(lo, ax, mid, true); clip_poly(hi, ax, mid, false);
+    if (lo.size() < 3 || hi.size() < 3) { out.push_back(Ref{bx, tri}); return; }
+    split_rec(lo, tri, levels - 1, min_side, out); split_rec(hi, tri, levels - 1, min_side, out);
+}
+static std::vector<Ref> presplit(const std::vector<Tri>& tris, int levels, float min_side) {
+    std::vector<Ref> out; out.reserve(tris.size() << levels);
+    for (uint32_t i = 0; i < tris.size(); ++i) split_rec({tris[i].v[0], tris[i].v[1], tris[i].v[2]}, i, levels, min_side, out);
+    return out;
+}
+
+static Bin build_lbvh_refs(const std::vector<Ref>& refs) {
+    const uint32_t n = (uint32_t)refs.size();
     std::vector<Box> pb(n);
     Box scene;
-    for (uint32_t i = 0; i < n; ++i) { for (int k = 0; k < 3; ++k) pb[i].grow(tris[i].v[k]); scene.grow(pb[i]); }
+    for (uint32_t i = 0; i < n; ++i) { pb[i] = refs[i].box; scene.grow(pb[i]); }
     std::vector<uint64_t> keys(n);
     for (uint32_t i = 0; i < n; ++i) {
         uint32_t q[3];
@@ -85,7 +126,7 @@ static Bin build_lbvh(const std::vector<Tri>& tris) {
     b.n = n;
     b.left.assign(2 * n - 1, 0); b.right.assign(2 * n - 1, 0); b.count.assign(2 * n - 1, 1); b.box.resize(2 * n - 1);
     b.prim.resize(n);
-    for (uint32_t k = 0; k < n; ++k) { b.prim[k] = (uint32_t)(keys[k] & 0xffffffffu); b.box[n - 1 + k] = pb[b.prim[k]]; }
+    for (uint32_t k = 0; k < n; ++k) { const uint32_t ri = (uint32_t)(keys[k] & 0xffffffffu); b.prim[k] = refs[ri].tri; b.box[n - 1 + k] = pb[ri]; }
     // top-down: split a key range at the highest differing bit (what Karras' bottom-up construction yields)
     uint32_t next = 0;
     struct Job { uint32_t lo, hi, node; };
@@ -647,6 +688,19 @@ int main(int argc, char** argv) {
             char nm[64]; snprintf(nm, sizeof nm, "+ rotation pass %d (%d rotations)", pass, r);
             report(nm, b, tris, nrays);
         }
+    }
+    if (argc > 3 && !strcmp(argv[3], "split")) {
+        for (int lv : {0, 1, 2, 3}) for (float ms : {0.f, 0.5f, 1.0f}) {
+            if (lv == 0 && ms > 0.f) continue;
+            std::vector<Ref> refs = presplit(tris, lv, ms * scale);
+            Bin b = build_lbvh_refs(refs); refit(b);
+            char nm[64]; snprintf(nm, sizeof nm, "split lv %d min %.1fs refs %.2fx", lv, ms, (double)refs.size() / n);
+            report(nm, b, tris, nrays, 1, 2);
+            rebuild_small_subtrees(b, 32);
+            snprintf(nm, sizeof nm, "  + SAH<=32");
+            report(nm, b, tris, nrays, 1, 2);
+        }
+        return 0;
     }
     for (uint32_t m : {32u, 512u, 0xffffffffu}) {
         Bin b = build_lbvh(tris); refit(b);
