@@ -78,7 +78,8 @@ def test_soup10m_closest_hits_match_the_oracle(pt_soup10m, oracle_soup10m):
 
 def test_soup10m_4096_invariances(pt_soup10m):
     """One 4096 x 4096 frame of 2 spp: the image does not depend on how many samples a pass carries, on the refill
-    policy of the traversal kernel, or on rendering it as 4 interleaved tiles (the multi-GPU decomposition); rays are conserved."""
+    policy of the traversal kernel, on whether the wavefront or the fused path kernel runs the paths, or on rendering it
+    as 4 interleaved tiles (the multi-GPU decomposition); rays are conserved."""
     pt = pt_soup10m
     W = H = 4096
     p = bpt.default_params(W, H, 2, 8)
@@ -89,7 +90,9 @@ def test_soup10m_4096_invariances(pt_soup10m):
     sky = np.array([0.7, 0.6, 0.5], np.float32)
     assert np.array_equal(full[0, 0, :3], sky) and np.array_equal(full[-1, -1, :3], sky)   # corners see the sky (KAT-2)
     assert np.isfinite(full).all() and (full[H // 2 - 200:H // 2 + 200, W // 2 - 200:W // 2 + 200, :3] != sky).any()
-    for opt, val, back in ((bpt.OPT_PASS_PATHS, 1, 1 << 27), (bpt.OPT_TRACE_REFILL_BELOW, 20, 30)):
+    # OPT_FUSED_PATHS: the same 33.5 M paths through a different scheduler altogether — one persistent path kernel with
+    # the path state in shared memory instead of generate + 8 x (traverse, shade) through queues in HBM
+    for opt, val, back in ((bpt.OPT_PASS_PATHS, 1, 1 << 27), (bpt.OPT_TRACE_REFILL_BELOW, 20, 30), (bpt.OPT_FUSED_PATHS, 1, 0)):
         pt.set_option(opt, val)
         pt.clear_image(); pt.reset_stats()
         assert np.array_equal(pt.render(p), full), opt
