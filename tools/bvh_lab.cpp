@@ -11,6 +11,7 @@
 //   g++ -O3 -march=native -std=c++17 -pthread tools/bvh_lab.cpp -o /tmp/bvh_lab
 //   /tmp/bvh_lab 1000000 200000        builder / traversal variants
 //   /tmp/bvh_lab 1000000 100000 simt   warp-level model of the traversal loop and its triangle-step policies
+//   /tmp/bvh_lab 1000000 100000 split  triangle pre-splitting (clipped references before the Morton sort)
 #include <algorithm>
 #include <array>
 #include <atomic>
