@@ -77,7 +77,15 @@ __device__ __forceinline__ void barycentrics(V3 o, V3 d, V3 v0, V3 v1, V3 v2, fl
 // by one thread at a time: a plain load - add - store. (A vector reduction, RED.ADD.F32x4, would spare the thread the
 // wait for the load, but the L2 atomic units sustain only ~7 G of them per second: measured +20 ms per 440 M-ray frame,
 // Cornell box 12.1 -> 7.9 Gray/s.)
+template <bool RED = false>
 __device__ __forceinline__ void add_color(float4* path_color, uint32_t pix, V3 c) {
+    if (RED) {
+        // the fused path kernel: nothing else runs in the warp while it shades, so it must not wait for the load; one
+        // vector reduction per contribution (a path contributes about once, far below the L2 atomic rate). A path's
+        // contributions arrive one after the other, in bounce order, so the sum has the same value as below.
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(path_color + pix), "f"(c.x), "f"(c.y), "f"(c.z), "f"(0.0f) : "memory");
+        return;
+    }
     float4 acc = path_color[pix];
     acc.x += c.x; acc.y += c.y; acc.z += c.z;
     path_color[pix] = acc;
@@ -90,7 +98,7 @@ struct ShadeOut { float4 ro, rd, st; };
 // (o holds its next ray and state). EXTRA: the instance that also knows the estimators the reference does not have
 // (next-event estimation, Russian roulette); the reference's estimator runs the instance without that code (the extra
 // branches and registers cost the Cornell box 6 % of its step).
-template <bool EXTRA>
+template <bool EXTRA, bool RED = false>
 __device__ __forceinline__ bool shade_one(const FrameParams& p, const SceneView& s, uint32_t depth, uint4 h, float4 st, uint32_t pix,
                                           float4 ro, float4 rd, float4 ra, float4 rb, float4 rc, float4 rdd, float4* path_color,
                                           float* pdf_prev, float light_area, ShadeOut& o) {
@@ -98,7 +106,7 @@ __device__ __forceinline__ bool shade_one(const FrameParams& p, const SceneView&
     uint32_t seed = __float_as_uint(st.w);
     if (h.w == BPT_MISS) {
         // miss.rmiss:10-11 then raygen.rgen:76 and the break at :81
-        add_color(path_color, pix, w * V3{p.sky[0], p.sky[1], p.sky[2]});
+        add_color<RED>(path_color, pix, w * V3{p.sky[0], p.sky[1], p.sky[2]});
         return false;
     }
     const float* m = s.xforms ? s.xforms + 12 * (size_t)(h.w / s.ntris) : nullptr;
@@ -121,7 +129,7 @@ __device__ __forceinline__ bool shade_one(const FrameParams& p, const SceneView&
             const float pp = pdf_prev[pix];
             c = c * (pp / (pp + pl));
         }
-        add_color(path_color, pix, c);
+        add_color<RED>(path_color, pix, c);
     }
     if (depth + 1u >= p.max_depth) return false;             // the next segment would not be traced
     const V3 brdf = kd / kPi;                                // closesthit.rchit:61

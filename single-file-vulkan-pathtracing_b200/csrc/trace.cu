@@ -222,6 +222,7 @@ __device__ __forceinline__ uint32_t test_quad(uint32_t xn, uint32_t yn, uint32_t
 // carries kNewPath as its primitive.
 constexpr uint32_t kNewPath = 0xfffffffeu;
 constexpr uint32_t kFusedReady = 64u, kFusedCtl = 128u, kFusedSlot0 = 192u;  // offsets inside a warp's block
+constexpr uint32_t kFusedChunk = 256u;  // path ids a warp takes from the pass's counter at a time
 
 // Shades up to 32 finished rays of the calling warp (the tail of its done list), one per lane, at full SIMD width:
 // closest-hit / miss + path update exactly as the wavefront shade kernel does (shade_one), then every path that ended
@@ -255,20 +256,29 @@ __device__ __noinline__ uint32_t fused_shade_batch(const FusedArgs* f, uint32_t 
                 const float4* rp = f->s.srec + 4 * (size_t)(f->s.xforms ? prim % f->s.ntris : prim);
                 ra = __ldg(rp); rb = __ldg(rp + 1); rc = __ldg(rp + 2); rdd = __ldg(rp + 3);
             }
-            alive = shade_one<false>(f->p, f->s, depth, make_uint4(q2.x, 0u, 0u, prim), st, pix, ro, rd, ra, rb, rc, rdd,
+            alive = shade_one<false, true>(f->p, f->s, depth, make_uint4(q2.x, 0u, 0u, prim), st, pix, ro, rd, ra, rb, rc, rdd,
                                      f->path_color, nullptr, 0.f, o);
             if (alive) ++depth; else need_new = true;
         }
     }
     const unsigned nm = __ballot_sync(FULL, need_new);
     if (nm) {
-        // the counter may run past npaths while a pass drains: it is 32 bits, a pass has < 2^31 paths
-        const int leader = __ffs(nm) - 1;
-        uint32_t base = 0u;
-        if ((int)lane == leader) base = atomicAdd(f->path_ctr, (uint32_t)__popc(nm));
-        base = __shfl_sync(FULL, base, leader);
+        // Path ids come from the warp's own chunk of kFusedChunk consecutive ids (counters + 8: next id, + 12: end of the
+        // chunk); one atomic on the pass's counter per chunk, and most batches do not wait for one. Ids run past npaths
+        // while a pass drains: the counter is 32 bits, a pass has < 2^31 paths. Ids are handed out in increasing order,
+        // so a warp that meets an id >= npaths has used every id before it.
+        const uint2 ch = lds64(wf_a + kFusedCtl + 8u);
+        const uint32_t need = (uint32_t)__popc(nm), rem = ch.y - ch.x;
+        uint32_t fresh = 0u;
+        if (rem < need) {
+            if (lane == 0u) fresh = atomicAdd(f->path_ctr, kFusedChunk);
+            fresh = __shfl_sync(FULL, fresh, 0);
+        }
+        __syncwarp();
+        if (lane == 0u) sts64(wf_a + kFusedCtl + 8u, rem < need ? make_uint2(fresh + (need - rem), fresh + kFusedChunk) : make_uint2(ch.x + need, ch.y));
         if (need_new) {
-            const uint32_t i = base + __popc(nm & lt);
+            const uint32_t rk = (uint32_t)__popc(nm & lt);
+            const uint32_t i = rk < rem ? ch.x + rk : fresh + (rk - rem);
             if (i < f->npaths) {
                 uint32_t seed;
                 gen_primary(f->p, f->s0, f->npix, i, o.ro, o.rd, seed);
@@ -348,15 +358,15 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kTraceBlock ? 1 : BPT_TRACE_CT
     if (FUSED) {
         // arguments of the shade batch into shared memory (the frame index from device memory under graph replay);
         // every slot starts on its warp's done list as "never held a path", so the first batches generate primary rays
-        uint32_t* fdst = reinterpret_cast<uint32_t*>(sfused);
-        const uint32_t* fsrc = reinterpret_cast<const uint32_t*>(&a.f);
-        for (uint32_t i = threadIdx.x; i < sizeof(FusedArgs) / 4u; i += BLOCK) fdst[i] = fsrc[i];
+        // (one thread, constant indices: a run-time index into the kernel parameters would make the compiler keep a
+        // copy of all of them in local memory and read traversal constants from there)
+        if (threadIdx.x == 0) *reinterpret_cast<FusedArgs*>(sfused) = a.f;
         unsigned char* wb = sfused + kFusedArgsBytes + (threadIdx.x >> 5) * kFusedWarpBytes;
         for (uint32_t i = threadIdx.x & 31u; i < (uint32_t)kFusedSlots; i += 32u) {
             wb[i] = (unsigned char)i;
             *reinterpret_cast<uint4*>(wb + kFusedSlot0 + i * 64u + 32u) = make_uint4(0u, kNewPath, 0u, 0u);
         }
-        if ((threadIdx.x & 31u) == 0u) *reinterpret_cast<uint2*>(wb + kFusedCtl) = make_uint2(0u, 0u);
+        if ((threadIdx.x & 31u) == 0u) *reinterpret_cast<uint4*>(wb + kFusedCtl) = make_uint4(0u, 0u, 0u, 0u);  // rays traced; path id chunk
         __syncthreads();
         if (threadIdx.x == 0 && a.f.frame_dev) reinterpret_cast<FusedArgs*>(sfused)->p.frame = *a.f.frame_dev;
     }
@@ -376,7 +386,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kTraceBlock ? 1 : BPT_TRACE_CT
     const uint32_t srecs_a = smem_a + kFixed + (uint32_t)SSTACK * BLOCK * 8u, slut_a = smem_a + 16u;
     const uint32_t pool_a = smem_a + 16u + 2048u + (threadIdx.x >> 5) * 1536u;
     uint2 lstack[kLocalStack];
-    volatile uint32_t park[FUSED ? 22 : 1];  // FUSED: a lane's traversal state while the warp shades
+    volatile uint32_t park[FUSED ? 20 : 1];  // FUSED: a lane's traversal state while the warp shades
     const uint32_t magic = a.magic;
     const int refill_below = a.refill_below, steps_per_refill = a.steps_per_refill;
     const int tris_per_step = STAGED ? a.staged_tris_per_step : 1;
@@ -410,30 +420,51 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kTraceBlock ? 1 : BPT_TRACE_CT
                 // the ready list runs dry, so the batches are full until the pass drains.
                 const bool fin = !active && ray_idx != 0xffu;
                 const unsigned fm = __ballot_sync(FULL, fin);
-                if (fin) { sts8(wf_a + n_done + __popc(fm & lt), ray_idx); ray_idx = 0xffu; }
+                if (fin) {
+                    sts8(wf_a + n_done + __popc(fm & lt), ray_idx);
+                    // the shading record of the hit on its way into the L2 while the ray waits for its batch
+                    const uint32_t hp = lds32(wf_a + kFusedSlot0 + ray_idx * 64u + 36u);
+                    if (!TWO_LEVEL && hp != BPT_MISS) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.f.s.srec + 4 * (size_t)hp));
+                    ray_idx = 0xffu;
+                }
                 n_done += __popc(fm);
                 __syncwarp();
                 unsigned idle = ~actmask;
                 for (;;) {
                     if (n_ready == 0u) {
                         if (n_done == 0u) break;
-                        // the lanes' traversal state waits in local memory while the warp shades: the batch needs the
-                        // registers, and spelled out like this the allocator does not keep loop state spilled instead
-                        park[0] = __float_as_uint(r.ox); park[1] = __float_as_uint(r.oy); park[2] = __float_as_uint(r.oz);
-                        park[3] = __float_as_uint(r.dx); park[4] = __float_as_uint(r.dy); park[5] = __float_as_uint(r.dz);
-                        park[6] = __float_as_uint(r.idx); park[7] = __float_as_uint(r.idy); park[8] = __float_as_uint(r.idz);
-                        park[9] = __float_as_uint(r.tbest); park[10] = r.hprim; park[11] = r.oct;
-                        park[12] = G.x; park[13] = G.y; park[14] = T.x; park[15] = T.y; park[16] = Tb; park[17] = Tv;
-                        park[18] = inst_base; park[19] = (uint32_t)sp; park[20] = ray_idx; park[21] = active ? 1u : 0u;
+                        // The lanes' traversal state waits in local memory while the warp shades: the batch needs the
+                        // registers, and spelled out like this the allocator does not keep loop state spilled instead.
+                        // One-level scenes reload the ray itself from the lane's path slot.
+                        if (TWO_LEVEL) {
+                            park[9] = __float_as_uint(r.ox); park[10] = __float_as_uint(r.oy); park[11] = __float_as_uint(r.oz);
+                            park[12] = __float_as_uint(r.dx); park[13] = __float_as_uint(r.dy); park[14] = __float_as_uint(r.dz);
+                            park[15] = __float_as_uint(r.idx); park[16] = __float_as_uint(r.idy); park[17] = __float_as_uint(r.idz);
+                            park[18] = r.oct; park[19] = inst_base;
+                        }
+                        park[0] = __float_as_uint(r.tbest); park[1] = r.hprim;
+                        park[2] = G.x; park[3] = G.y; park[4] = T.x; park[5] = T.y; park[6] = Tb; park[7] = Tv;
+                        park[8] = (uint32_t)sp | (ray_idx << 8) | (active ? 0x10000u : 0u);
                         uint32_t res = fused_shade_batch(fargs, wf_a, n_done);
                         res = __shfl_sync(FULL, res, 0);  // warp-uniform, and known to be
                         n_done = res & 0xffu; n_ready = res >> 8;
-                        r.ox = __uint_as_float(park[0]); r.oy = __uint_as_float(park[1]); r.oz = __uint_as_float(park[2]);
-                        r.dx = __uint_as_float(park[3]); r.dy = __uint_as_float(park[4]); r.dz = __uint_as_float(park[5]);
-                        r.idx = __uint_as_float(park[6]); r.idy = __uint_as_float(park[7]); r.idz = __uint_as_float(park[8]);
-                        r.tbest = __uint_as_float(park[9]); r.hprim = park[10]; r.oct = park[11]; octsel = r.oct << 12;
-                        G.x = park[12]; G.y = park[13]; T.x = park[14]; T.y = park[15]; Tb = park[16]; Tv = park[17];
-                        inst_base = park[18]; sp = (int)park[19]; ray_idx = park[20]; active = park[21] != 0u;
+                        r.tbest = __uint_as_float(park[0]); r.hprim = park[1];
+                        G.x = park[2]; G.y = park[3]; T.x = park[4]; T.y = park[5]; Tb = park[6]; Tv = park[7];
+                        { const uint32_t pk = park[8]; sp = (int)(pk & 0xffu); ray_idx = (pk >> 8) & 0xffu; active = (pk & 0x10000u) != 0u; }
+                        if (TWO_LEVEL) {
+                            r.ox = __uint_as_float(park[9]); r.oy = __uint_as_float(park[10]); r.oz = __uint_as_float(park[11]);
+                            r.dx = __uint_as_float(park[12]); r.dy = __uint_as_float(park[13]); r.dz = __uint_as_float(park[14]);
+                            r.idx = __uint_as_float(park[15]); r.idy = __uint_as_float(park[16]); r.idz = __uint_as_float(park[17]);
+                            r.oct = park[18]; inst_base = park[19];
+                        } else {  // every lane, live or not (an idle lane reads some slot: nothing looks at its ray)
+                            const uint32_t sa = wf_a + kFusedSlot0 + (ray_idx & (kFusedSlots - 1u)) * 64u;
+                            const uint4 q0 = lds128(sa), q1 = lds128(sa + 16u), q2 = lds128(sa + 32u);
+                            r.ox = __uint_as_float(q0.x); r.oy = __uint_as_float(q0.y); r.oz = __uint_as_float(q0.z);
+                            r.dx = __uint_as_float(q1.x); r.dy = __uint_as_float(q1.y); r.dz = __uint_as_float(q1.z);
+                            r.idx = __uint_as_float(q2.x); r.idy = __uint_as_float(q2.y); r.idz = __uint_as_float(q2.z);
+                            r.oct = q2.w & 7u;
+                        }
+                        octsel = r.oct << 12;
                         continue;  // an empty ready list again: every shaded path ended and the pass has no primary ray left
                     }
                     const uint32_t rank = __popc(idle & lt);
