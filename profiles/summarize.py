@@ -114,10 +114,11 @@ def sass(lib):
     blocks = re.split(r"(?=\t\tFunction : )", txt)
     for b in blocks:
         m = re.match(r"\t\tFunction : (\S+)", b)
-        if m and "k_trace" in m.group(1) and "Lb0ELb0ELb0E" in m.group(1):
+        # STAGED, TWO_LEVEL, COUNT, FUSED all false: the instance bpt_trace runs on the big scenes
+        if m and "k_trace" in m.group(1) and "ELi8ELb0ELb0ELb0ELb0E" in m.group(1):
             print(b.rstrip())
             return
-    raise SystemExit("k_trace<.., false, false, false> not found")
+    raise SystemExit("k_trace<.., false, false, false, false> not found")
 
 
 if __name__ == "__main__":

@@ -10,6 +10,7 @@ constexpr int kTraceMaxSmem = 227 * 1024;
 // 1/d, octant | depth, throughput, seed, path id, and the closest hit once the ray is done — plus the lists of the
 // slots whose ray is finished ("done": waiting to be shaded) and of those that hold a fresh ray ("ready")
 constexpr int kFusedSlots = 64;
+static_assert((kFusedSlots & (kFusedSlots - 1)) == 0 && kFusedSlots <= 128, "slot ids are masked with kFusedSlots - 1 and kept in bytes");
 constexpr int kFusedArgsBytes = 256;                              // copy of FusedArgs
 constexpr int kFusedWarpBytes = 64 + 64 + 64 + kFusedSlots * 64;  // done list, ready list, counters | slots
 // mbarrier + octant permutation table + (wavefront instance: per-warp ray pools | fused instance: arguments + per-warp path slots)
