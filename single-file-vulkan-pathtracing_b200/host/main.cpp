@@ -130,7 +130,7 @@ void write_pfm(const std::string& path, const std::vector<float>& rgba, uint32_t
 int main(int argc, char** argv) {
     std::string obj, scene_bin, out = "bpt_out";
     int frames = 8, device = 0;
-    bool want_display = false;
+    bool want_display = false, fused = false;
     bpt_params p;
     bpt_params_default(&p);  // WIDTH/HEIGHT 1024 (main.cpp:16-17), 32 spp, depth 8, camera, sky: the shader constants
     for (int i = 1; i < argc; ++i) {
@@ -150,9 +150,10 @@ int main(int argc, char** argv) {
         else if (a == "--depth") p.max_depth = (uint32_t)std::atoi(next());
         else if (a == "--rgba8-feedback") p.accum_mode = BPT_ACCUM_RGBA8;  // raygen.rgen:88-90 on the rgba8 image
         else if (a == "--display") want_display = true;  // let GLFW pick a real platform (none is compiled in here)
+        else if (a == "--fused") fused = true;           // BPT_OPT_FUSED_PATHS: one path kernel per sample pass (small frames)
         else if (a == "--help" || a == "-h") {
             std::printf("usage: %s (--obj file.obj | --scene scene.bin) [--frames N] [--width W --height H --spp S --depth D]\n"
-                        "          [--rgba8-feedback] [--device I] [--out prefix] [--display]\n", argv[0]);
+                        "          [--rgba8-feedback] [--fused] [--device I] [--out prefix] [--display]\n", argv[0]);
             return 0;
         } else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
@@ -174,6 +175,7 @@ int main(int argc, char** argv) {
         check(pt, bpt_upload_mesh(pt, &scene.vertices[0].position[0], (uint32_t)scene.vertices.size(), scene.indices.data(),
                                   (uint32_t)scene.indices.size(), &scene.faces[0].diffuse[0], (uint32_t)scene.faces.size()));
         check(pt, bpt_build_accel(pt));  // Accel bottomAccel + topAccel (main.cpp:512, :538)
+        if (fused) check(pt, bpt_set_option(pt, BPT_OPT_FUSED_PATHS, 1));
         bpt_accel_info info;
         check(pt, bpt_accel_info_get(pt, &info));
         std::printf("accel: %u BVH8 nodes, depth %u, %s\n", info.num_nodes8, info.max_depth8,

@@ -59,6 +59,13 @@ def test_host_app_renders_the_oracle_image(tmp_path, cornell, cornell_oracle):
     assert O.rel_l2(img, ref[..., :3]) <= 1e-3
     ppm = open(str(out) + ".ppm", "rb").read()
     assert ppm.startswith(b"P6\n96 96\n255\n") and len(ppm) == len(b"P6\n96 96\n255\n") + 96 * 96 * 3
+    # --fused: the same frames through the fused path kernel, the same bytes
+    out2 = tmp_path / "img_fused"
+    r = subprocess.run([HOST, "--scene", str(scene), "--frames", "3", "--width", "96", "--height", "96", "--spp", "4",
+                        "--depth", "5", "--fused", "--out", str(out2)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(str(out2) + ".pfm", "rb").read() == open(str(out) + ".pfm", "rb").read()
+    assert open(str(out2) + ".ppm", "rb").read() == ppm
 
 
 def write_obj(path, verts, idx, faces):
