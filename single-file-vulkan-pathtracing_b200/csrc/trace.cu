@@ -222,7 +222,6 @@ __device__ __forceinline__ uint32_t test_quad(uint32_t xn, uint32_t yn, uint32_t
 // carries kNewPath as its primitive.
 constexpr uint32_t kNewPath = 0xfffffffeu;
 constexpr uint32_t kFusedReady = 64u, kFusedCtl = 128u, kFusedSlot0 = 192u;  // offsets inside a warp's block
-constexpr uint32_t kFusedChunk = 256u;  // path ids a warp takes from the pass's counter at a time
 
 // Shades up to 32 finished rays of the calling warp (the tail of its done list), one per lane, at full SIMD width:
 // closest-hit / miss + path update exactly as the wavefront shade kernel does (shade_one), then every path that ended
@@ -263,22 +262,15 @@ __device__ __noinline__ uint32_t fused_shade_batch(const FusedArgs* f, uint32_t 
     }
     const unsigned nm = __ballot_sync(FULL, need_new);
     if (nm) {
-        // Path ids come from the warp's own chunk of kFusedChunk consecutive ids (counters + 8: next id, + 12: end of the
-        // chunk); one atomic on the pass's counter per chunk, and most batches do not wait for one. Ids run past npaths
-        // while a pass drains: the counter is 32 bits, a pass has < 2^31 paths. Ids are handed out in increasing order,
-        // so a warp that meets an id >= npaths has used every id before it.
-        const uint2 ch = lds64(wf_a + kFusedCtl + 8u);
-        const uint32_t need = (uint32_t)__popc(nm), rem = ch.y - ch.x;
-        uint32_t fresh = 0u;
-        if (rem < need) {
-            if (lane == 0u) fresh = atomicAdd(f->path_ctr, kFusedChunk);
-            fresh = __shfl_sync(FULL, fresh, 0);
-        }
-        __syncwarp();
-        if (lane == 0u) sts64(wf_a + kFusedCtl + 8u, rem < need ? make_uint2(fresh + (need - rem), fresh + kFusedChunk) : make_uint2(ch.x + need, ch.y));
+        // one atomic per batch: consecutive path ids for the lanes whose path ended. (Handing a warp 256 ids at a time
+        // was tried: nothing on the big frames, and small frames — fewer chunks than warps — ran on a fraction of the
+        // machine.) The counter runs past npaths while a pass drains: it is 32 bits, a pass has < 2^31 paths.
+        const int leader = __ffs(nm) - 1;
+        uint32_t base = 0u;
+        if ((int)lane == leader) base = atomicAdd(f->path_ctr, (uint32_t)__popc(nm));
+        base = __shfl_sync(FULL, base, leader);
         if (need_new) {
-            const uint32_t rk = (uint32_t)__popc(nm & lt);
-            const uint32_t i = rk < rem ? ch.x + rk : fresh + (rk - rem);
+            const uint32_t i = base + __popc(nm & lt);
             if (i < f->npaths) {
                 uint32_t seed;
                 gen_primary(f->p, f->s0, f->npix, i, o.ro, o.rd, seed);
@@ -366,7 +358,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kTraceBlock ? 1 : BPT_TRACE_CT
             wb[i] = (unsigned char)i;
             *reinterpret_cast<uint4*>(wb + kFusedSlot0 + i * 64u + 32u) = make_uint4(0u, kNewPath, 0u, 0u);
         }
-        if ((threadIdx.x & 31u) == 0u) *reinterpret_cast<uint4*>(wb + kFusedCtl) = make_uint4(0u, 0u, 0u, 0u);  // rays traced; path id chunk
+        if ((threadIdx.x & 31u) == 0u) *reinterpret_cast<uint2*>(wb + kFusedCtl) = make_uint2(0u, 0u);  // rays traced
         __syncthreads();
         if (threadIdx.x == 0 && a.f.frame_dev) reinterpret_cast<FusedArgs*>(sfused)->p.frame = *a.f.frame_dev;
     }
