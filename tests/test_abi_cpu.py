@@ -34,6 +34,16 @@ def test_struct_layouts_match_header():
     assert bpt.NODE8_DTYPE.itemsize == 64 and bpt.WOOP_DTYPE.itemsize == 64 and bpt.HIT_DTYPE.itemsize == 16
 
 
+def test_python_constants_match_the_header():
+    """Every BPT_OPT_* / BPT_ACCUM_* / BPT_SAMPLER_* the header defines has the same value in the ctypes mirror."""
+    text = open(os.path.join(ROOT, "include", "bpt.h")).read()
+    defs = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+BPT_((?:OPT|ACCUM|SAMPLER)_[A-Z0-9_]+)\s+(-?\w+)", text)}
+    assert len([k for k in defs if k.startswith("OPT_")]) >= 12 and "OPT_FUSED_PATHS" in defs
+    for name, value in defs.items():
+        assert getattr(bpt, name) == value, name
+    assert len({v for k, v in defs.items() if k.startswith("OPT_")}) == len([k for k in defs if k.startswith("OPT_")])  # ids unique
+
+
 def test_default_params_are_the_reference_constants():
     p = bpt.default_params()
     assert (p.width, p.height, p.spp_per_frame, p.max_depth, p.frame) == (1024, 1024, 32, 8, 0)  # main.cpp:16-17, raygen.rgen:43,62
