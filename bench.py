@@ -497,6 +497,19 @@ def run_ours(args):
     pt.set_option(bpt.OPT_STREAMS, lanes)
     nodes_per_ray = sc.nodes_visited / max(sc.rays_traced, 1)
     tris_per_ray = sc.tris_tested / max(sc.rays_traced, 1)
+    # what the quality stage of the build (BPT_OPT_BVH_SAH_SUBTREE, default 32) buys: the same instrumented frame through
+    # a plain Morton LBVH, on a second context (rank 0 of a single-GPU run only; soups only — the Cornell box has 36 triangles)
+    nodes_per_ray_plain = None
+    if d.world == 1 and w["tris"] and not any(o.split("=")[0] == str(bpt.OPT_BVH_SAH_SUBTREE) for o in args.opt):
+        pt2 = bpt.PathTracer(d.local_rank, stream.cuda_stream)
+        pt2.set_option(bpt.OPT_BVH_SAH_SUBTREE, 0)
+        build_scene(pt2)
+        pt2.set_option(bpt.OPT_COUNT_TRAVERSAL, 1)
+        pt2.reset_stats()
+        pt2.trace(params(frame - 1))
+        s2 = pt2.stats()
+        nodes_per_ray_plain = s2.nodes_visited / max(s2.rays_traced, 1)
+        pt2.close()
     # Requested bytes (SURVEY 8d "modelled"): 32 B ray + 16 B hit + one 64 B record per node visited and per triangle
     # tested. Almost all of them are served by L1/L2 (ncu: L2 hit rate 83-90 %), so this is NOT DRAM traffic and is
     # reported under its own name only.
@@ -549,6 +562,7 @@ def run_ours(args):
                 "requested_bytes_per_ray": requested_per_ray,
                 "requested_frac": requested_per_ray * st.rays_traced / kernel_s / 1e9 / peak,
                 "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
+                "nodes_per_ray_plain_lbvh": nodes_per_ray_plain,
                 "lanes_per_node_step": sc.nodes_visited / max(sc.warp_node_steps, 1),
                 "lanes_per_tri_step": sc.tris_tested / max(sc.warp_tri_steps, 1), "avg_launch_ms": avg_launch_ms,
                 "launches": int(st.trace_launches), "rays_per_launch": rays_per_launch,
