@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call AA: per-lane stack entries in shared memory 8 (default) / 6 / 4 — fewer entries = smaller shared-memory
-# carve-out = more L1 (make VARIANT=ssN EXTRA_ALL=-DBPT_TRACE_SSTACK=N)
+# carve-out = more L1 (git apply tools/experiments/smem_stack_entries.patch; make VARIANT=ssN EXTRA_ALL=-DBPT_TRACE_SSTACK=N)
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 O=gpurun_out
